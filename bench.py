@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the OpenPose inference hot path at 368x656, batch 32 per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; N>1 under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic input (BASELINE.json
+configs[2]: "full pipeline (conv + NMS + PAF integral + grouping) synthetic 8-person 368x656
+batch 32"): the 92-conv CocoPoseNet chain runs on 32 random uint8 BGR frames per GPU; because
+random weights cannot produce people, the synthetic 8-person low-resolution maps are injected
+as the network output in front of upsample -> peaks -> PAF integrals -> assignment -> grouping
+(SURVEY.md 8d).  N GPUs: images shard by rank (weak scaling), one NCCL all-gather of the
+fixed-size person records per step.
+
+`value` = whole-job frames/s with the input batch already resident in HBM; `e2e` = the same
+through the host-buffer entry (pinned uint8 frames H2D and the result records D2H inside the
+timed region).  `roofline` is for the dominant kernel, the grouped 7x7 128->128 conv launch.
+`--impl reference` times the CPU restatement of the reference path (oracle/, torch-CPU conv +
+NumPy/SciPy post-process; Chainer itself is not installable offline) on the host cores.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "chainer_realtime_multi-person_pose_estimation_b200"
+H, W, MAP_H, MAP_W = 368, 656, 320, 576
+FLOPS_PER_IMAGE = 484634285056            # SURVEY.md 8d, true channel counts
+METRIC = "frames/sec at 368x656 batch32 (full pipeline: conv + NMS + PAF integral + grouping)"
+
+
+def pkg(sub=None):
+    return importlib.import_module(PKG + ("." + sub if sub else ""))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, text=True, timeout=5)
+                self.samples.append([s.strip() for s in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) >= 6 and s[2 + i] == "Active" for s in self.samples)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+def cpu_reference_step(weights, img, paf_lo, heat_lo):
+    """One frame through the CPU restatement of the reference path."""
+    from oracle import restate as R
+    x = R.preprocess(img)
+    R.forward(weights, x)                                                   # conv chain (torch CPU fp32)
+    pafs = R.resize_bilinear_align_corners(paf_lo[None], (MAP_H, MAP_W))[0]   # injected maps, as in our arm
+    heat = R.resize_bilinear_align_corners(heat_lo[None], (MAP_H, MAP_W))[0]
+    return R.postprocess_fast(pafs, heat, MAP_W, W, H, MAP_H)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    syn = pkg("synthetic")
+    wd = syn.he_weights(0)
+    weights = {k[:-2]: (wd[k], wd[k[:-2] + "/b"]) for k in wd if k.endswith("/W")}
+    imgs = syn.random_images(2, H, W, seed=0)
+    paf_lo, heat_lo = syn.eight_person_lowres(H // 8, W // 8, seed=0)
+    for i in range(max(args.warmup, 1)):
+        cpu_reference_step(weights, imgs[i % 2], paf_lo, heat_lo)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        poses, scores = cpu_reference_step(weights, imgs[i % 2], paf_lo, heat_lo)
+    dt = time.perf_counter() - t0
+    assert len(scores) == 8
+    value = args.steps / dt
+    sample = "1 frame per step (the reference is batch-1), %d steps" % args.steps
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "full pipeline 368x656, synthetic 8-person maps injected, CPU oracle port "
+                               "(reference pose_detector.py restated; torch-CPU fp32 conv; Chainer not installable)",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    native, syn = pkg("_native"), pkg("synthetic")
+    B = args.batch
+    model = pkg("models.CocoPoseNet").CocoPoseNet()
+    model.load_npz(syn.he_weights(0))
+    prm = pkg("pose_detector").make_opb_params(max_peaks=2048, max_candidates=8192, max_persons=args.max_persons)
+    eng = native.Engine(local_rank, prm, native.PRECISION_FAST if args.precision == "fast" else native.PRECISION_PARITY)
+    eng.load_model(model)
+    # a dedicated (non-default) torch stream: libopb launches on it, torch events time it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+
+    imgs_host = torch.from_numpy(syn.random_images(B, H, W, seed=rank)).pin_memory()
+    imgs_dev = imgs_host.cuda()
+    paf_lo, heat_lo = syn.eight_person_lowres(H // 8, W // 8, seed=0)
+    d_paf = torch.from_numpy(np.repeat(paf_lo[None], B, 0)).cuda()
+    d_heat = torch.from_numpy(np.repeat(heat_lo[None], B, 0)).cuda()
+    hdr_dev = torch.zeros(B * native.HEADER_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    per_dev = torch.zeros(B * args.max_persons * native.PERSON_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    rec_local = torch.zeros(hdr_dev.numel() + per_dev.numel(), dtype=torch.uint8, device="cuda")
+    rec_all = torch.zeros(world * rec_local.numel(), dtype=torch.uint8, device="cuda") if world > 1 else None
+    hdr_host = np.empty(B, native.HEADER_DTYPE)
+    per_host = np.empty((B, args.max_persons), native.PERSON_DTYPE)
+    import ctypes as C
+
+    def step_resident():
+        eng._check(eng.lib.opb_detect_batch(eng.ctx, C.c_void_p(imgs_dev.data_ptr()), native.OPB_DEVICE, B, H, W,
+                                            MAP_H, MAP_W, float(MAP_W), C.c_void_p(d_paf.data_ptr()),
+                                            C.c_void_p(d_heat.data_ptr()), C.c_void_p(hdr_dev.data_ptr()),
+                                            C.c_void_p(per_dev.data_ptr()), native.OPB_DEVICE))
+        if world > 1:
+            rec_local[:hdr_dev.numel()].copy_(hdr_dev)
+            rec_local[hdr_dev.numel():].copy_(per_dev)
+            dist.all_gather_into_tensor(rec_all, rec_local)
+
+    def step_e2e():
+        eng._check(eng.lib.opb_detect_batch(eng.ctx, C.c_void_p(imgs_host.data_ptr()), native.OPB_HOST, B, H, W,
+                                            MAP_H, MAP_W, float(MAP_W), C.c_void_p(d_paf.data_ptr()),
+                                            C.c_void_p(d_heat.data_ptr()), C.c_void_p(hdr_host.ctypes.data),
+                                            C.c_void_p(per_host.ctypes.data), native.OPB_HOST))
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), eng.launch_count() - l0
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    # correctness of the timed path: 8 persons per frame
+    hdr = np.frombuffer(hdr_dev.cpu().numpy().tobytes(), native.HEADER_DTYPE)
+    assert (hdr["status"] == 0).all() and (hdr["n_persons"] == 8).all(), hdr
+    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    assert (hdr_host["status"] == 0).all() and (hdr_host["n_persons"] == 8).all()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    # dominant kernel: the grouped 7x7 128->128 launch (both branches), 20 launches per step
+    n77 = 20
+    ms77 = eng.time_stage("Mconv7x7", reps=5) / n77
+    flops77 = 2 * (2.0 * B * (H // 8) * (W // 8) * 128 * 128 * 49)
+    ach = flops77 / (ms77 * 1e-3) / 1e12
+    ms_chain = eng.time_stage("conv_chain", reps=3)
+    ms_up = eng.time_stage("upsample_paf", reps=10)
+    paf_bytes = B * (38 * (H // 8) * (W // 8) * 4 + 38 * MAP_H * MAP_W * 4) + 80 * 151 * B
+    extra = {
+        "conv_chain_ms": ms_chain,
+        "conv_chain_tflops": B * FLOPS_PER_IMAGE / (ms_chain * 1e-3) / 1e12,
+        "conv_chain_frac_of_sustained_peak": B * FLOPS_PER_IMAGE / (ms_chain * 1e-3) / 1e12 / (peaks["tflops_sustained"] or peaks["tflops"]),
+        "paf_upsample_integrate": {"bound": "hbm", "achieved": paf_bytes / (ms_up * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                   "unit": "GB/s", "frac": paf_bytes / (ms_up * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                   "ms": ms_up},
+        "stage_ms": {s: eng.time_stage(s, reps=5) for s in ("upsample_heat", "peaks", "paf_integral", "group")},
+    }
+    # CPU baseline: the oracle port on this box's host cores, bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        wd = syn.he_weights(0)
+        weights = {k[:-2]: (wd[k], wd[k[:-2] + "/b"]) for k in wd if k.endswith("/W")}
+        fr = imgs_host[0].numpy()
+        cpu_reference_step(weights, fr, paf_lo, heat_lo)
+        n_s = 3
+        t0 = time.perf_counter()
+        for _ in range(n_s):
+            cpu_reference_step(weights, fr, paf_lo, heat_lo)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_s / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "%d single frames (reference is batch-1) after 1 warm-up; torch-CPU fp32 conv + NumPy/SciPy "
+                         "post-process" % n_s}
+    out = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16" if args.precision == "fast" else "split-f16 (hi+lo)", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[2]: full pipeline, synthetic 8-person maps injected, 368x656, "
+                               "batch %d per GPU" % B,
+                   "precision": args.precision, "global_batch": world * B,
+                   "parallelism": "image-sharded x%d, 1 all-gather of person records per step" % world,
+                   "l2": "no explicit flush: activations written/read per step (~4.5 GB) exceed the 126 MB L2",
+                   "peaks": peaks["source"]},
+        "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(imgs_host.numel()),
+                "d2h_bytes_per_step": int(hdr_host.nbytes + per_host.nbytes), "ms_per_step": ms_e2e / args.steps},
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": ach / peaks["tflops"], "traffic": None,
+                     "kernel": "conv_tcgen05_kernel<7,128,...> grouped L1+L2 7x7 128->128", "ms_per_launch": ms77},
+        "cpu_baseline": cpu, "clocks": clocks, "extra": extra,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--max-persons", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,305 @@
+// conv_tcgen05.cuh -- implicit-GEMM convolution (stride 1, "same" zero padding, ksize 1/3/7)
+// on the sm_100a 5th-gen tensor cores.  Replaces Chainer's L.Convolution2D + F.relu
+// (+ F.concat by writing into channel slices) of models/CocoPoseNet.py:136-260.
+//
+// Data layout
+//   activations  NHWC fp16, channel count padded to a multiple of 64; tensor map
+//                {C, W, H, N}, box {64 ch, 8 px, 16+ks-1 rows, 1}, SWIZZLE_128B.  TMA
+//                zero-fills out-of-image coordinates, which *is* the conv zero padding.
+//   weights      [Cout_pad][ks*ks][Cin_pad] fp16, K-major ("B" operand), tensor map
+//                {Ktot, Cout_pad}, box {64, BN}, SWIZZLE_128B.
+//   accumulators fp32 in TMEM, ACC_STAGES x MT x BN columns.
+//
+// Tiling: one CTA tile = 16 output rows x (8*MT) output columns of one image x BN output
+// channels.  Sub-tile mt (16 x 8 pixels = the 128 rows of one UMMA, row m = y*8 + x) has
+// its own accumulator; all MT sub-tiles share every weight tile ("B" stage), so the
+// L2->SM weight traffic per FLOP drops by MT.
+//
+// The "A" operand for the 7 (or 3) vertical taps r of one horizontal tap s comes from ONE
+// TMA box of 16+ks-1 rows: tap r simply starts r*1024 bytes (one 8-pixel row group = one
+// 1024-byte swizzle atom) further into the same shared-memory buffer, so every UMMA
+// descriptor stays 1024-byte aligned and activations are fetched ks (not ks*ks) times.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer
+// (one elected lane issues tcgen05.mma), warps 2..5 = epilogue (tcgen05.ld -> bias -> ReLU
+// -> fp16 [hi/lo] -> global).  Three mbarrier pipelines: A ring, B ring, TMEM full/empty.
+// The kernel is persistent: tile = blockIdx.x + i*gridDim.x.
+//
+// Precision: OPB_PRECISION_FAST stores fp16 activations/weights (fp32 accumulate).
+// OPB_PRECISION_PARITY stores x = hi + lo (two fp16 planes) and accumulates
+// hi*Whi + lo*Whi + hi*Wlo into the same TMEM accumulator: the K loop just walks a table of
+// (activation-channel-offset, weight-k-offset) chunk pairs, so both modes run this kernel.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+
+namespace opb {
+
+constexpr int kConvThreads = 192;
+constexpr int kMaxPairs = 24;
+
+struct ConvProblem {
+  __half* out;          // NHWC fp16 output tensor base (or nullptr)
+  float* out32;         // optional planar fp32 [N][cout_valid][H][W] (network heads), or nullptr
+  const float* bias;    // [n_blocks*BN] fp32, zero padded
+  int out_cstride;      // channels per pixel of the output tensor
+  int out_coff;         // first channel of this problem inside the output tensor
+  int out_lo_off;       // parity mode: distance (channels) from the hi plane to the lo plane, else 0
+  int cout_valid;       // real number of output channels
+  int relu;
+  int pad_;
+};
+
+struct ConvParams {
+  int N, H, W;
+  int tiles_x, tiles_y;  // ceil(W/(8*MT)), ceil(H/16)
+  int n_blocks;          // Cout_pad / BN
+  int n_pairs;           // number of 64-channel K chunk pairs
+  int n_problems;        // 1 or 2 (grouped launch: the L1 / L2 branches of one stage)
+  int b_tap_stride;      // K elements per filter tap in the packed weights
+  int a_off[kMaxPairs];  // activation channel offset of chunk pair j
+  int b_off[kMaxPairs];  // weight k offset (inside one tap) of chunk pair j
+  ConvProblem prob[2];
+};
+
+template <int KS, int BN, int MT, int NSA, int NSB, int ACC_STAGES>
+struct ConvCfg {
+  static constexpr int RH = 16 + KS - 1;               // rows per activation box
+  static constexpr int A_SUB_BYTES = RH * 1024;        // one sub-tile box
+  static constexpr int A_STAGE_BYTES = MT * A_SUB_BYTES;
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int TMEM_COLS_RAW = ACC_STAGES * MT * BN;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
+                                   : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static_assert(TMEM_COLS_RAW <= 512, "accumulators do not fit TMEM");
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NSA * A_STAGE_BYTES + NSB * B_STAGE_BYTES + 512;
+};
+
+template <int KS, int BN, int MT, int NSA, int NSB, int ACC_STAGES>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                    const __grid_constant__ ConvParams P) {
+  using Cfg = ConvCfg<KS, BN, MT, NSA, NSB, ACC_STAGES>;
+  constexpr int PAD = (KS - 1) / 2;
+  constexpr uint32_t IDESC = ptx::umma_idesc_f16(128, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + NSA * Cfg::A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + NSB * Cfg::B_STAGE_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + NSA;
+  uint64_t* b_full = a_empty + NSA;
+  uint64_t* b_empty = b_full + NSB;
+  uint64_t* t_full = b_empty + NSB;
+  uint64_t* t_empty = t_full + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA0);
+    ptx::prefetch_tensormap(&tmB0);
+    if (P.n_problems > 1) {
+      ptx::prefetch_tensormap(&tmA1);
+      ptx::prefetch_tensormap(&tmB1);
+    }
+    for (int i = 0; i < NSA; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NSB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 128); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = P.N * P.tiles_y * P.tiles_x;
+  const int tiles_per_problem = P.n_blocks * m_tiles;
+  const int total_tiles = P.n_problems * tiles_per_problem;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int p = tile / tiles_per_problem;
+        int rem = tile - p * tiles_per_problem;
+        const int nb = rem / m_tiles;
+        rem -= nb * m_tiles;
+        const int n = rem / (P.tiles_y * P.tiles_x);
+        rem -= n * (P.tiles_y * P.tiles_x);
+        const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+        const int y0 = ty * 16, x0 = tx * (8 * MT);
+        const int n_sub = min(MT, (P.W - x0 + 7) >> 3);
+        const CUtensorMap* tmA = p ? &tmA1 : &tmA0;
+        const CUtensorMap* tmB = p ? &tmB1 : &tmB0;
+        for (int j = 0; j < P.n_pairs; ++j) {
+          const int ac = P.a_off[j], bk = P.b_off[j];
+          for (int s = 0; s < KS; ++s) {
+            ptx::mbar_wait(&a_empty[sa], pa ^ 1);
+            ptx::mbar_expect_tx(&a_full[sa], n_sub * Cfg::A_SUB_BYTES);
+            for (int mt = 0; mt < n_sub; ++mt)
+              ptx::tma_load_4d(smemA + sa * Cfg::A_STAGE_BYTES + mt * Cfg::A_SUB_BYTES, tmA, &a_full[sa], ac,
+                               x0 + mt * 8 + s - PAD, y0 - PAD, n);
+            if (++sa == NSA) { sa = 0; pa ^= 1; }
+            for (int r = 0; r < KS; ++r) {
+              ptx::mbar_wait(&b_empty[sb], pb ^ 1);
+              ptx::mbar_expect_tx(&b_full[sb], Cfg::B_STAGE_BYTES);
+              ptx::tma_load_2d(smemB + sb * Cfg::B_STAGE_BYTES, tmB, &b_full[sb],
+                               (r * KS + s) * P.b_tap_stride + bk, nb * BN);
+              if (++sb == NSB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int rem = tile % m_tiles;
+        rem %= (P.tiles_y * P.tiles_x);
+        const int tx = rem % P.tiles_x;
+        const int x0 = tx * (8 * MT);
+        const int n_sub = min(MT, (P.W - x0 + 7) >> 3);
+        ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
+        ptx::tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int j = 0; j < P.n_pairs; ++j) {
+          for (int s = 0; s < KS; ++s) {
+            ptx::mbar_wait(&a_full[sa], pa);
+            ptx::tc_fence_after();
+            const uint32_t a_base = ptx::smem_u32(smemA + sa * Cfg::A_STAGE_BYTES);
+            for (int r = 0; r < KS; ++r) {
+              ptx::mbar_wait(&b_full[sb], pb);
+              ptx::tc_fence_after();
+              const uint32_t b_base = ptx::smem_u32(smemB + sb * Cfg::B_STAGE_BYTES);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                if (mt < n_sub) {
+                  const uint32_t d = tmem_base + (acc * MT + mt) * BN;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint64_t ad = ptx::umma_desc_sw128(a_base + mt * Cfg::A_SUB_BYTES + r * 1024 + k * 32, 1024);
+                    const uint64_t bd = ptx::umma_desc_sw128(b_base + k * 32, 1024);
+                    ptx::mma_f16_ss(d, ad, bd, IDESC, accumulate | (uint32_t)k);
+                  }
+                }
+              }
+              accumulate = 1;
+              ptx::mma_commit(&b_empty[sb]);
+              if (++sb == NSB) { sb = 0; pb ^= 1; }
+            }
+            ptx::mma_commit(&a_empty[sa]);
+            if (++sa == NSA) { sa = 0; pa ^= 1; }
+          }
+        }
+        ptx::mma_commit(&t_full[acc]);
+        if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int hl = row >> 3, wl = row & 7;
+    uint32_t acc = 0, pacc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int p = tile / tiles_per_problem;
+      int rem = tile - p * tiles_per_problem;
+      const int nb = rem / m_tiles;
+      rem -= nb * m_tiles;
+      const int n = rem / (P.tiles_y * P.tiles_x);
+      rem -= n * (P.tiles_y * P.tiles_x);
+      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+      const int y = ty * 16 + hl;
+      const int x0 = tx * (8 * MT);
+      const int n_sub = min(MT, (P.W - x0 + 7) >> 3);
+      const ConvProblem& pr = P.prob[p];
+
+      ptx::mbar_wait(&t_full[acc], pacc);
+      ptx::tc_fence_after();
+      for (int mt = 0; mt < n_sub; ++mt) {
+        const int x = x0 + mt * 8 + wl;
+        const bool valid = (y < P.H) && (x < P.W);
+        const size_t pix = (static_cast<size_t>(n) * P.H + y) * P.W + x;
+        constexpr int CW = (BN % 32 == 0) ? 32 : 16;   // BN = 48: three groups of 16
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += CW) {
+          {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * MT + mt) * BN + cc;
+            if (CW == 32) {
+              ptx::tmem_ld_32x32b_x32(taddr, v);
+            } else {
+              uint32_t v16[16];
+              ptx::tmem_ld_32x32b_x16(taddr, v16);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = v16[i];
+            }
+            ptx::tmem_ld_wait();
+            const int ch0 = nb * BN + cc;  // first channel of this group inside the problem
+            if (valid && ch0 < pr.cout_valid) {
+              float f[CW];
+#pragma unroll
+              for (int i = 0; i < CW; ++i) {
+                float t = __uint_as_float(v[i]) + __ldg(pr.bias + ch0 + i);
+                f[i] = pr.relu ? fmaxf(t, 0.f) : t;
+              }
+              const int nvalid = min(CW, pr.cout_valid - ch0);
+              if (pr.out32) {
+                for (int i = 0; i < nvalid; ++i)
+                  pr.out32[((static_cast<size_t>(n) * pr.cout_valid + ch0 + i) * P.H + y) * P.W + x] = f[i];
+              }
+              if (pr.out) {
+                __half* o = pr.out + pix * pr.out_cstride + pr.out_coff + ch0;
+                const bool vec = (nvalid == CW) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) &&
+                                 ((pr.out_lo_off & 7) == 0);
+                if (vec) {
+#pragma unroll
+                  for (int g = 0; g < CW / 8; ++g) {
+                    __align__(16) __half2 h[4];
+                    __align__(16) __half2 l[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      const float a = f[g * 8 + 2 * i], b = f[g * 8 + 2 * i + 1];
+                      const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+                      h[i] = __halves2half2(ha, hb);
+                      l[i] = __halves2half2(__float2half_rn(a - __half2float(ha)),
+                                            __float2half_rn(b - __half2float(hb)));
+                    }
+                    *reinterpret_cast<uint4*>(o + g * 8) = *reinterpret_cast<const uint4*>(h);
+                    if (pr.out_lo_off) *reinterpret_cast<uint4*>(o + pr.out_lo_off + g * 8) = *reinterpret_cast<const uint4*>(l);
+                  }
+                } else {
+                  for (int i = 0; i < nvalid; ++i) {
+                    const __half hi = __float2half_rn(f[i]);
+                    o[i] = hi;
+                    if (pr.out_lo_off) o[pr.out_lo_off + i] = __float2half_rn(f[i] - __half2float(hi));
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&t_empty[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+}  // namespace opb

@@ -1,0 +1,1280 @@
+// opb_api.cu -- C ABI of libopb.so (see include/opb.h).  Host-side orchestration of the
+// sm_100a kernels: weight repacking, activation buffers, TMA tensor maps, the 92-conv chain of
+// models/CocoPoseNet.py:132-262 as ~60 launches, and the post-process of
+// pose_detector.py:501-517.  No CPU compute fallback exists in this file.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/opb.h"
+#include "conv_first.cuh"
+#include "conv_tcgen05.cuh"
+#include "paf.cuh"
+#include "peaks.cuh"
+#include "pool.cuh"
+#include "upsample.cuh"
+
+using namespace opb;
+
+static_assert(sizeof(opb_person) == sizeof(PersonOut), "opb_person layout");
+static_assert(sizeof(opb_person) == 240, "opb_person size");
+static_assert(sizeof(opb_image_header) == sizeof(ImageHeader), "opb_image_header layout");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct HostLayer {
+  int cin = 0, cout = 0, ks = 0;
+  std::vector<float> W, b;
+};
+
+struct PackedW {          // one "B" operand: [cout_pad][ks*ks][k_per_tap] fp16
+  __half* w = nullptr;
+  float* bias = nullptr;  // [cout_pad]
+  int cout_pad = 0, k_per_tap = 0, cin_pad = 0, ks = 0;
+};
+
+struct Act {              // NHWC fp16 activation tensor, channels [hi C | lo C]
+  __half* p = nullptr;
+  int N = 0, H = 0, W = 0, C = 0, Ctot = 0;
+  size_t bytes() const { return static_cast<size_t>(N) * H * W * Ctot * sizeof(__half); }
+};
+
+enum OpKind { OP_FIRST, OP_CONV, OP_POOL };
+
+struct Op {
+  OpKind kind;
+  std::string tag;
+  // OP_CONV
+  int ks = 0, bn = 0, mt = 1;
+  CUtensorMap tmA[2], tmB[2];
+  ConvParams P;
+  int grid = 0;
+  // OP_FIRST / OP_POOL
+  const __half* in = nullptr;
+  __half* out = nullptr;
+  int N = 0, H = 0, W = 0, C = 0, cstride = 0, lo_off = 0;
+};
+
+struct Chain {            // everything cached for one (N, H, W)
+  int N = 0, H = 0, W = 0;
+  std::vector<Op> ops;
+  std::vector<void*> allocs;
+  float* paf_lo = nullptr;   // [N][38][h][w]
+  float* heat_lo = nullptr;  // [N][19][h][w]
+  uint8_t* img_u8 = nullptr;
+  float* img_f32 = nullptr;
+};
+
+struct PostWs {           // post-process workspace for (N, map_h, map_w)
+  int N = 0, H = 0, W = 0;
+  float* pafs = nullptr;      // [N][38][H][W]
+  float* heat = nullptr;      // [N][19][H][W]
+  PeakKey* keys = nullptr;    // [N][max_peaks]
+  int* peak_counts = nullptr; // [N]
+  PeakD* peaks = nullptr;     // [N][max_peaks]
+  int* idx_list = nullptr;
+  int* type_start = nullptr;  // [N][19]
+  int* status = nullptr;      // [N]
+  Candidate* cands = nullptr; // [N][19][max_cand]
+  int* cand_counts = nullptr; // [N][19]
+  Connection* conns = nullptr;  // [N][19][conn_cap]
+  int* conn_counts = nullptr;
+  double* subsets = nullptr;  // [N][max_persons][20]
+  double* subsets_out = nullptr;
+  ImageHeader* headers = nullptr;
+  PersonOut* persons = nullptr;
+  std::vector<void*> allocs;
+};
+
+}  // namespace
+
+struct opb_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  opb_params prm;
+  PafConsts pc;
+  GaussTaps taps;
+  std::string err;
+  int64_t launches = 0;
+  EncodeTiledFn encode = nullptr;
+  int precision = -1;
+  std::map<std::string, HostLayer> host_layers;
+  std::map<std::string, PackedW> packed;
+  float* w_first = nullptr;  // conv1_1 [27][64] fp32
+  float* b_first = nullptr;
+  std::vector<void*> weight_allocs;
+  std::map<long long, Chain*> chains;
+  Chain* last_chain = nullptr;
+  std::map<long long, PostWs*> posts;
+  PostWs* last_post = nullptr;
+  int conn_cap = kAssignMaxType;
+};
+
+namespace {
+
+#define OPB_CUDA(ctx, expr)                                                                       \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" +      \
+                   std::to_string(__LINE__) + ")";                                                \
+      return OPB_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+#define OPB_FAIL(ctx, code, msg) \
+  do {                           \
+    (ctx)->err = (msg);          \
+    return (code);               \
+  } while (0)
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+template <typename T>
+int dev_alloc(opb_ctx* ctx, T** p, size_t count, std::vector<void*>& owner, bool zero = true) {
+  void* q = nullptr;
+  OPB_CUDA(ctx, cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 256)));
+  if (zero) OPB_CUDA(ctx, cudaMemsetAsync(q, 0, std::max<size_t>(count * sizeof(T), 256), ctx->stream));
+  owner.push_back(q);
+  *p = static_cast<T*>(q);
+  return OPB_OK;
+}
+
+void free_all(std::vector<void*>& v) {
+  for (void* p : v) cudaFree(p);
+  v.clear();
+}
+
+// ------------------------------------------------------------------ tensor maps
+int make_act_map(opb_ctx* ctx, CUtensorMap* tm, const Act& a, int coff, int ks) {
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.Ctot - coff), static_cast<cuuint64_t>(a.W),
+                        static_cast<cuuint64_t>(a.H), static_cast<cuuint64_t>(a.N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(a.Ctot) * 2, static_cast<cuuint64_t>(a.W) * a.Ctot * 2,
+                           static_cast<cuuint64_t>(a.H) * a.W * a.Ctot * 2};
+  cuuint32_t box[4] = {64, 8, static_cast<cuuint32_t>(16 + ks - 1), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.p + coff, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) OPB_FAIL(ctx, OPB_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string(r));
+  return OPB_OK;
+}
+
+int make_w_map(opb_ctx* ctx, CUtensorMap* tm, const PackedW& w, int bn) {
+  const cuuint64_t ktot = static_cast<cuuint64_t>(w.ks) * w.ks * w.k_per_tap;
+  cuuint64_t dims[2] = {ktot, static_cast<cuuint64_t>(w.cout_pad)};
+  cuuint64_t strides[1] = {ktot * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w.w, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) OPB_FAIL(ctx, OPB_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string(r));
+  return OPB_OK;
+}
+
+// ------------------------------------------------------------------ conv launch
+template <int KS, int BN, int MT, int NSA, int NSB, int ACC>
+int launch_conv_t(opb_ctx* ctx, const Op& op) {
+  using Cfg = ConvCfg<KS, BN, MT, NSA, NSB, ACC>;
+  auto kern = conv_tcgen05_kernel<KS, BN, MT, NSA, NSB, ACC>;
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    OPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[ctx->device & 63] = true;
+  }
+  kern<<<op.grid, kConvThreads, Cfg::SMEM_BYTES, ctx->stream>>>(op.tmA[0], op.tmB[0], op.tmA[1], op.tmB[1], op.P);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  return OPB_OK;
+}
+
+int launch_conv(opb_ctx* ctx, const Op& op) {
+  const int key = op.ks * 10000 + op.bn * 10 + op.mt;
+  switch (key) {
+    case 7 * 10000 + 128 * 10 + 1: return launch_conv_t<7, 128, 1, 3, 6, 2>(ctx, op);
+    case 7 * 10000 + 128 * 10 + 2: return launch_conv_t<7, 128, 2, 3, 5, 2>(ctx, op);
+    case 7 * 10000 + 256 * 10 + 1: return launch_conv_t<7, 256, 1, 3, 4, 2>(ctx, op);
+    case 3 * 10000 + 64 * 10 + 1: return launch_conv_t<3, 64, 1, 3, 6, 2>(ctx, op);
+    case 3 * 10000 + 128 * 10 + 1: return launch_conv_t<3, 128, 1, 3, 6, 2>(ctx, op);
+    case 3 * 10000 + 128 * 10 + 2: return launch_conv_t<3, 128, 2, 3, 6, 2>(ctx, op);
+    case 3 * 10000 + 256 * 10 + 1: return launch_conv_t<3, 256, 1, 3, 4, 2>(ctx, op);
+    case 1 * 10000 + 128 * 10 + 1: return launch_conv_t<1, 128, 1, 4, 6, 2>(ctx, op);
+    case 1 * 10000 + 256 * 10 + 1: return launch_conv_t<1, 256, 1, 4, 4, 2>(ctx, op);
+    case 1 * 10000 + 48 * 10 + 1: return launch_conv_t<1, 48, 1, 4, 6, 2>(ctx, op);
+    case 3 * 10000 + 48 * 10 + 1: return launch_conv_t<3, 48, 1, 3, 6, 2>(ctx, op);
+    case 7 * 10000 + 48 * 10 + 1: return launch_conv_t<7, 48, 1, 3, 6, 2>(ctx, op);
+    case 7 * 10000 + 64 * 10 + 1: return launch_conv_t<7, 64, 1, 3, 6, 2>(ctx, op);
+    case 1 * 10000 + 64 * 10 + 1: return launch_conv_t<1, 64, 1, 4, 6, 2>(ctx, op);
+    default: OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "no conv kernel variant for ks/bn/mt key " + std::to_string(key));
+  }
+}
+
+int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
+  if (op.kind == OP_CONV) return launch_conv(ctx, op);
+  if (op.kind == OP_POOL) {
+    const size_t total = static_cast<size_t>(op.N) * (op.H / 2) * (op.W / 2) * (op.C / 8);
+    const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(ctx->num_sms) * 16));
+    maxpool2x2_kernel<<<grid, 256, 0, ctx->stream>>>(op.in, op.out, op.N, op.H, op.W, op.C, op.cstride, op.lo_off);
+    ctx->launches++;
+    OPB_CUDA(ctx, cudaGetLastError());
+    return OPB_OK;
+  }
+  // OP_FIRST
+  const size_t total = static_cast<size_t>(op.N) * op.H * op.W;
+  const int grid = static_cast<int>(std::min<size_t>((total + 63) / 64, static_cast<size_t>(ctx->num_sms) * 32));
+  conv_first_kernel<<<grid, 256, 0, ctx->stream>>>(ch->img_u8 && op.C == 1 ? ch->img_u8 : nullptr,
+                                                   op.C == 1 ? nullptr : ch->img_f32, ctx->w_first, ctx->b_first,
+                                                   op.out, op.N, op.H, op.W, op.cstride, op.lo_off);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  return OPB_OK;
+}
+
+// ------------------------------------------------------------------ weight packing
+// rows: list of (layer, n_rows_pad); cin_map[d] = reference input channel of device channel d
+// (or -1 = zero).  Output [sum rows_pad][ks*ks][cin_pad * (split ? 2 : 1)].
+int pack_weights(opb_ctx* ctx, const std::string& key, const std::vector<std::pair<std::string, int>>& rows,
+                 const std::vector<int>& cin_map, int ks, bool split) {
+  const int cin_pad = static_cast<int>(cin_map.size());
+  const int kpt = cin_pad * (split ? 2 : 1);
+  int cout_pad = 0;
+  for (auto& r : rows) cout_pad += r.second;
+  const size_t ktot = static_cast<size_t>(ks) * ks * kpt;
+  std::vector<__half> hw(static_cast<size_t>(cout_pad) * ktot, __float2half(0.f));
+  std::vector<float> hb(cout_pad, 0.f);
+  int row0 = 0;
+  for (auto& r : rows) {
+    auto it = ctx->host_layers.find(r.first);
+    if (it == ctx->host_layers.end()) OPB_FAIL(ctx, OPB_ERR_STATE, "weights for layer " + r.first + " were not loaded");
+    const HostLayer& L = it->second;
+    if (L.ks != ks) OPB_FAIL(ctx, OPB_ERR_ARG, "ksize mismatch for " + r.first);
+    for (int o = 0; o < L.cout; ++o) {
+      hb[row0 + o] = L.b[o];
+      for (int t = 0; t < ks * ks; ++t) {
+        __half* dst = hw.data() + (static_cast<size_t>(row0 + o) * ks * ks + t) * kpt;
+        for (int d = 0; d < cin_pad; ++d) {
+          const int c = cin_map[d];
+          if (c < 0 || c >= L.cin) continue;
+          const float v = L.W[(static_cast<size_t>(o) * L.cin + c) * ks * ks + t];
+          const __half hi = __float2half_rn(v);
+          dst[d] = hi;
+          if (split) dst[cin_pad + d] = __float2half_rn(v - __half2float(hi));
+        }
+      }
+    }
+    row0 += r.second;
+  }
+  PackedW pw;
+  pw.cout_pad = cout_pad;
+  pw.k_per_tap = kpt;
+  pw.cin_pad = cin_pad;
+  pw.ks = ks;
+  int rc = dev_alloc(ctx, &pw.w, hw.size(), ctx->weight_allocs, false);
+  if (rc) return rc;
+  rc = dev_alloc(ctx, &pw.bias, hb.size() + 64, ctx->weight_allocs, true);
+  if (rc) return rc;
+  OPB_CUDA(ctx, cudaMemcpyAsync(pw.w, hw.data(), hw.size() * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
+  OPB_CUDA(ctx, cudaMemcpyAsync(pw.bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors die here
+  ctx->packed[key] = pw;
+  return OPB_OK;
+}
+
+std::vector<int> identity_map(int cin, int cin_pad) {
+  std::vector<int> m(cin_pad, -1);
+  for (int i = 0; i < cin; ++i) m[i] = i;
+  return m;
+}
+
+// ------------------------------------------------------------------ chain construction
+struct ConvSpec {
+  const Act* in[2];
+  int in_coff[2];
+  std::string wkey[2];
+  const Act* out[2];
+  int out_coff[2];
+  int cout_valid[2];
+  float* out32[2];
+  int n_problems;
+  int relu;
+};
+
+int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s) {
+  Op op;
+  op.kind = OP_CONV;
+  op.tag = tag;
+  const PackedW& w0 = ctx->packed.at(s.wkey[0]);
+  const bool split = ctx->precision == OPB_PRECISION_PARITY;
+  op.ks = w0.ks;
+  const int per_problem_cout_pad = w0.cout_pad;
+  op.bn = std::min(per_problem_cout_pad, 256);
+  op.mt = 1;
+  const Act& a0 = *s.in[0];
+  if (a0.H < 16 + op.ks - 1 || a0.W < 8)
+    OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "feature map smaller than one TMA box (min 22 x 8); image too small");
+  std::memset(&op.P, 0, sizeof(op.P));
+  ConvParams& P = op.P;
+  P.N = a0.N; P.H = a0.H; P.W = a0.W;
+  P.tiles_x = (a0.W + 8 * op.mt - 1) / (8 * op.mt);
+  P.tiles_y = (a0.H + 15) / 16;
+  P.n_blocks = per_problem_cout_pad / op.bn;
+  P.n_problems = s.n_problems;
+  P.b_tap_stride = w0.k_per_tap;
+  const int chunks = w0.cin_pad / 64;
+  int np = 0;
+  for (int i = 0; i < chunks; ++i) {
+    P.a_off[np] = i * 64; P.b_off[np] = i * 64; ++np;
+    if (split) {
+      P.a_off[np] = a0.C + i * 64; P.b_off[np] = i * 64; ++np;             // lo * Whi
+      P.a_off[np] = i * 64; P.b_off[np] = w0.cin_pad + i * 64; ++np;        // hi * Wlo
+    }
+  }
+  if (np > kMaxPairs) OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "too many K chunk pairs");
+  P.n_pairs = np;
+  for (int p = 0; p < s.n_problems; ++p) {
+    const PackedW& w = ctx->packed.at(s.wkey[p]);
+    if (w.ks != op.ks || w.cout_pad != per_problem_cout_pad || w.k_per_tap != w0.k_per_tap)
+      OPB_FAIL(ctx, OPB_ERR_ARG, "grouped problems must share a shape");
+    if (split && s.in[p]->C != a0.C) OPB_FAIL(ctx, OPB_ERR_ARG, "grouped problems must share the lo-plane offset");
+    int rc = make_act_map(ctx, &op.tmA[p], *s.in[p], s.in_coff[p], op.ks);
+    if (rc) return rc;
+    rc = make_w_map(ctx, &op.tmB[p], w, op.bn);
+    if (rc) return rc;
+    ConvProblem& pr = P.prob[p];
+    pr.out = s.out[p] ? s.out[p]->p : nullptr;
+    pr.out32 = s.out32[p];
+    pr.bias = w.bias;
+    pr.out_cstride = s.out[p] ? s.out[p]->Ctot : 0;
+    pr.out_coff = s.out_coff[p];
+    pr.out_lo_off = (split && s.out[p]) ? s.out[p]->C : 0;
+    pr.cout_valid = s.cout_valid[p];
+    pr.relu = s.relu;
+  }
+  if (s.n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; P.prob[1] = P.prob[0]; }
+  const int total_tiles = P.n_problems * P.n_blocks * P.N * P.tiles_y * P.tiles_x;
+  op.grid = std::min(total_tiles, ctx->num_sms);
+  ch->ops.push_back(op);
+  return OPB_OK;
+}
+
+int alloc_act(opb_ctx* ctx, Chain* ch, Act* a, int N, int H, int W, int C) {
+  a->N = N; a->H = H; a->W = W; a->C = C;
+  a->Ctot = C * (ctx->precision == OPB_PRECISION_PARITY ? 2 : 1);
+  return dev_alloc(ctx, &a->p, a->bytes() / sizeof(__half), ch->allocs, true);
+}
+
+int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
+  ch->N = N; ch->H = H; ch->W = W;
+  const bool split = ctx->precision == OPB_PRECISION_PARITY;
+  const int h8 = H / 8, w8 = W / 8;
+  int rc;
+#define RC(x) do { rc = (x); if (rc) return rc; } while (0)
+  RC(dev_alloc(ctx, &ch->img_u8, static_cast<size_t>(N) * H * W * 3, ch->allocs, false));
+  RC(dev_alloc(ctx, &ch->img_f32, static_cast<size_t>(N) * H * W * 3, ch->allocs, false));
+  RC(dev_alloc(ctx, &ch->paf_lo, static_cast<size_t>(N) * 38 * h8 * w8, ch->allocs, true));
+  RC(dev_alloc(ctx, &ch->heat_lo, static_cast<size_t>(N) * 19 * h8 * w8, ch->allocs, true));
+  // activation buffers (kept alive for the lifetime of the chain; 180 GB of HBM make reuse
+  // games unnecessary at batch 32: ~4.5 GB fast, ~9 GB parity)
+  Act B0, B1, P1, B2, B3, P2, B4, B5, P3, B6, B7, B8, CAT, SA, SB, S512;   // ops keep raw pointers only
+  RC(alloc_act(ctx, ch, &B0, N, H, W, 64));
+  RC(alloc_act(ctx, ch, &B1, N, H, W, 64));
+  RC(alloc_act(ctx, ch, &P1, N, H / 2, W / 2, 64));
+  RC(alloc_act(ctx, ch, &B2, N, H / 2, W / 2, 128));
+  RC(alloc_act(ctx, ch, &B3, N, H / 2, W / 2, 128));
+  RC(alloc_act(ctx, ch, &P2, N, H / 4, W / 4, 128));
+  RC(alloc_act(ctx, ch, &B4, N, H / 4, W / 4, 256));
+  RC(alloc_act(ctx, ch, &B5, N, H / 4, W / 4, 256));
+  RC(alloc_act(ctx, ch, &P3, N, h8, w8, 256));
+  RC(alloc_act(ctx, ch, &B6, N, h8, w8, 512));
+  RC(alloc_act(ctx, ch, &B7, N, h8, w8, 512));
+  RC(alloc_act(ctx, ch, &B8, N, h8, w8, 256));
+  RC(alloc_act(ctx, ch, &CAT, N, h8, w8, 192));
+  RC(alloc_act(ctx, ch, &SA, N, h8, w8, 256));
+  RC(alloc_act(ctx, ch, &SB, N, h8, w8, 256));
+  RC(alloc_act(ctx, ch, &S512, N, h8, w8, 1024));
+
+  auto first = [&]() {
+    Op op; op.kind = OP_FIRST; op.tag = "conv1_1"; op.out = B0.p; op.N = N; op.H = H; op.W = W; op.C = 1;
+    op.cstride = B0.Ctot; op.lo_off = split ? B0.C : 0; ch->ops.push_back(op);
+  };
+  auto pool = [&](const char* tag, const Act& in, const Act& out) {
+    Op op; op.kind = OP_POOL; op.tag = tag; op.in = in.p; op.out = out.p; op.N = N; op.H = in.H; op.W = in.W;
+    op.C = in.Ctot /* hi and lo planes are pooled as one channel range in fast mode */; op.cstride = in.Ctot;
+    op.lo_off = split ? in.C : 0;
+    if (split) op.C = in.C;
+    ch->ops.push_back(op);
+  };
+  auto conv1 = [&](const std::string& layer, const Act& in, const Act& out, int out_coff, int cout) -> int {
+    ConvSpec s{};
+    s.in[0] = &in; s.in_coff[0] = 0; s.wkey[0] = layer; s.out[0] = &out; s.out_coff[0] = out_coff;
+    s.cout_valid[0] = cout; s.out32[0] = nullptr; s.n_problems = 1; s.relu = 1;
+    return add_conv(ctx, ch, layer, s);
+  };
+  auto conv2 = [&](const std::string& tag, const std::string& l1, const std::string& l2, const Act& in, int ic1,
+                   int ic2, const Act& out, int oc1, int oc2, int cv1, int cv2, int relu, float* o32a,
+                   float* o32b) -> int {
+    ConvSpec s{};
+    s.in[0] = &in; s.in[1] = &in; s.in_coff[0] = ic1; s.in_coff[1] = ic2; s.wkey[0] = l1; s.wkey[1] = l2;
+    s.out[0] = &out; s.out[1] = &out; s.out_coff[0] = oc1; s.out_coff[1] = oc2; s.cout_valid[0] = cv1;
+    s.cout_valid[1] = cv2; s.out32[0] = o32a; s.out32[1] = o32b; s.n_problems = 2; s.relu = relu;
+    return add_conv(ctx, ch, tag, s);
+  };
+
+  first();
+  RC(conv1("conv1_2", B0, B1, 0, 64));
+  pool("pool1", B1, P1);
+  RC(conv1("conv2_1", P1, B2, 0, 128));
+  RC(conv1("conv2_2", B2, B3, 0, 128));
+  pool("pool2", B3, P2);
+  RC(conv1("conv3_1", P2, B4, 0, 256));
+  RC(conv1("conv3_2", B4, B5, 0, 256));
+  RC(conv1("conv3_3", B5, B4, 0, 256));
+  RC(conv1("conv3_4", B4, B5, 0, 256));
+  pool("pool3", B5, P3);
+  RC(conv1("conv4_1", P3, B6, 0, 512));
+  RC(conv1("conv4_2", B6, B7, 0, 512));
+  RC(conv1("conv4_3_CPM", B7, B8, 0, 256));
+  RC(conv1("conv4_4_CPM", B8, CAT, 0, 128));
+  // stage 1 (models/CocoPoseNet.py:154-165): both branches as 2-problem grouped launches
+  RC(conv2("conv5_1", "conv5_1_CPM_L1", "conv5_1_CPM_L2", CAT, 0, 0, SA, 0, 128, 128, 128, 1, nullptr, nullptr));
+  RC(conv2("conv5_2", "conv5_2_CPM_L1", "conv5_2_CPM_L2", SA, 0, 128, SB, 0, 128, 128, 128, 1, nullptr, nullptr));
+  RC(conv2("conv5_3", "conv5_3_CPM_L1", "conv5_3_CPM_L2", SB, 0, 128, SA, 0, 128, 128, 128, 1, nullptr, nullptr));
+  RC(conv2("conv5_4", "conv5_4_CPM_L1", "conv5_4_CPM_L2", SA, 0, 128, S512, 0, 512, 512, 512, 1, nullptr, nullptr));
+  RC(conv2("conv5_5", "conv5_5_CPM_L1", "conv5_5_CPM_L2", S512, 0, 512, CAT, 128, 166, 38, 19, 0, nullptr, nullptr));
+  for (int st = 2; st <= 6; ++st) {
+    const std::string S = "_stage" + std::to_string(st);
+    {  // Mconv1: both branches read the same concat tensor -> one N=256 GEMM (:168-169,176)
+      ConvSpec s{};
+      s.in[0] = &CAT; s.in_coff[0] = 0; s.wkey[0] = "Mconv1" + S + "_fused"; s.out[0] = &SA; s.out_coff[0] = 0;
+      s.cout_valid[0] = 256; s.n_problems = 1; s.relu = 1;
+      RC(add_conv(ctx, ch, "Mconv1", s));
+    }
+    RC(conv2("Mconv7x7", "Mconv2" + S + "_L1", "Mconv2" + S + "_L2", SA, 0, 128, SB, 0, 128, 128, 128, 1, nullptr, nullptr));
+    RC(conv2("Mconv7x7", "Mconv3" + S + "_L1", "Mconv3" + S + "_L2", SB, 0, 128, SA, 0, 128, 128, 128, 1, nullptr, nullptr));
+    RC(conv2("Mconv7x7", "Mconv4" + S + "_L1", "Mconv4" + S + "_L2", SA, 0, 128, SB, 0, 128, 128, 128, 1, nullptr, nullptr));
+    RC(conv2("Mconv7x7", "Mconv5" + S + "_L1", "Mconv5" + S + "_L2", SB, 0, 128, SA, 0, 128, 128, 128, 1, nullptr, nullptr));
+    RC(conv2("Mconv6", "Mconv6" + S + "_L1", "Mconv6" + S + "_L2", SA, 0, 128, SB, 0, 128, 128, 128, 1, nullptr, nullptr));
+    RC(conv2("Mconv7", "Mconv7" + S + "_L1", "Mconv7" + S + "_L2", SB, 0, 128, CAT, 128, 166, 38, 19, 0,
+             st == 6 ? ch->paf_lo : nullptr, st == 6 ? ch->heat_lo : nullptr));
+  }
+#undef RC
+  return OPB_OK;
+}
+
+long long shape_key(int n, int h, int w) { return (static_cast<long long>(n) << 40) | (static_cast<long long>(h) << 20) | w; }
+
+int get_chain(opb_ctx* ctx, int n, int h, int w, Chain** out) {
+  if (ctx->precision < 0) OPB_FAIL(ctx, OPB_ERR_STATE, "opb_finalize_weights has not been called");
+  if (n <= 0 || h <= 0 || w <= 0 || (h % 8) || (w % 8)) OPB_FAIL(ctx, OPB_ERR_ARG, "H and W must be positive multiples of 8");
+  const long long key = shape_key(n, h, w);
+  auto it = ctx->chains.find(key);
+  if (it != ctx->chains.end()) { *out = it->second; ctx->last_chain = it->second; return OPB_OK; }
+  // keep at most a few cached shapes (the precise path cycles through 4)
+  if (ctx->chains.size() >= 6) {
+    for (auto& kv : ctx->chains) { cudaStreamSynchronize(ctx->stream); free_all(kv.second->allocs); delete kv.second; }
+    ctx->chains.clear();
+    ctx->last_chain = nullptr;
+  }
+  Chain* ch = new Chain();
+  int rc = build_chain(ctx, ch, n, h, w);
+  if (rc) { free_all(ch->allocs); delete ch; return rc; }
+  ctx->chains[key] = ch;
+  ctx->last_chain = ch;
+  *out = ch;
+  return OPB_OK;
+}
+
+int run_chain(opb_ctx* ctx, Chain* ch, bool u8_input) {
+  for (Op& op : ch->ops) {
+    if (op.kind == OP_FIRST) op.C = u8_input ? 1 : 0;
+    int rc = launch_op(ctx, ch, op);
+    if (rc) return rc;
+  }
+  return OPB_OK;
+}
+
+// ------------------------------------------------------------------ post-process
+int get_post(opb_ctx* ctx, int n, int H, int W, PostWs** out) {
+  const long long key = shape_key(n, H, W);
+  auto it = ctx->posts.find(key);
+  if (it != ctx->posts.end()) { *out = it->second; ctx->last_post = it->second; return OPB_OK; }
+  if (ctx->posts.size() >= 4) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->posts) { free_all(kv.second->allocs); delete kv.second; }
+    ctx->posts.clear();
+    ctx->last_post = nullptr;
+  }
+  PostWs* ws = new PostWs();
+  ws->N = n; ws->H = H; ws->W = W;
+  const opb_params& p = ctx->prm;
+  int rc = 0;
+#define RC(x) do { rc = (x); if (rc) { free_all(ws->allocs); delete ws; return rc; } } while (0)
+  RC(dev_alloc(ctx, &ws->pafs, static_cast<size_t>(n) * 38 * H * W, ws->allocs, false));
+  RC(dev_alloc(ctx, &ws->heat, static_cast<size_t>(n) * 19 * H * W, ws->allocs, false));
+  RC(dev_alloc(ctx, &ws->keys, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
+  RC(dev_alloc(ctx, &ws->peak_counts, n, ws->allocs));
+  RC(dev_alloc(ctx, &ws->peaks, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
+  RC(dev_alloc(ctx, &ws->idx_list, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
+  RC(dev_alloc(ctx, &ws->type_start, static_cast<size_t>(n) * 19, ws->allocs));
+  RC(dev_alloc(ctx, &ws->status, n, ws->allocs));
+  RC(dev_alloc(ctx, &ws->cands, static_cast<size_t>(n) * 19 * p.max_candidates, ws->allocs, false));
+  RC(dev_alloc(ctx, &ws->cand_counts, static_cast<size_t>(n) * 19, ws->allocs));
+  RC(dev_alloc(ctx, &ws->conns, static_cast<size_t>(n) * 19 * ctx->conn_cap, ws->allocs, false));
+  RC(dev_alloc(ctx, &ws->conn_counts, static_cast<size_t>(n) * 19, ws->allocs));
+  RC(dev_alloc(ctx, &ws->subsets, static_cast<size_t>(n) * p.max_persons * 20, ws->allocs, false));
+  RC(dev_alloc(ctx, &ws->subsets_out, static_cast<size_t>(n) * p.max_persons * 20, ws->allocs, false));
+  RC(dev_alloc(ctx, &ws->headers, n, ws->allocs));
+  RC(dev_alloc(ctx, &ws->persons, static_cast<size_t>(n) * p.max_persons, ws->allocs));
+#undef RC
+  ctx->posts[key] = ws;
+  ctx->last_post = ws;
+  *out = ws;
+  return OPB_OK;
+}
+
+int launch_upsample(opb_ctx* ctx, const float* in, int planes, int h, int w, float* out, int H, int W) {
+  const int ppb = 8;
+  dim3 grid((W + 31) / 32, (H + 7) / 8, (planes + ppb - 1) / ppb), block(32, 8);
+  if (grid.z > 65535) OPB_FAIL(ctx, OPB_ERR_ARG, "too many planes");
+  upsample_bilinear_ac_kernel<<<grid, block, 0, ctx->stream>>>(in, planes, h, w, out, H, W, ppb);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  return OPB_OK;
+}
+
+// heat: [n][c_total][H][W]; fills ws->peaks / idx_list / type_start / peak_counts
+int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total, int H, int W) {
+  const opb_params& p = ctx->prm;
+  OPB_CUDA(ctx, cudaMemsetAsync(ws->peak_counts, 0, sizeof(int) * n, ctx->stream));
+  OPB_CUDA(ctx, cudaMemsetAsync(ws->status, 0, sizeof(int) * n, ctx->stream));
+  const int c_use = c_total - 1;   // background channel dropped, pose_detector.py:78
+  const size_t smem = smooth_nms_smem_bytes(ctx->taps.radius);
+  static bool attr1 = false, attr2 = false;
+  if (!attr1) {
+    OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr1 = true;
+  }
+  dim3 grid((W + PK_TX - 1) / PK_TX, (H + PK_TY - 1) / PK_TY, n * c_use);
+  if (grid.z > 65535) OPB_FAIL(ctx, OPB_ERR_ARG, "batch too large for the peaks grid");
+  smooth_nms_kernel<<<grid, 256, smem, ctx->stream>>>(heat, c_total, c_use, H, W, ctx->taps,
+                                                      static_cast<float>(p.heatmap_peak_thresh), ws->keys,
+                                                      ws->peak_counts, p.max_peaks);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  int npow = 1;
+  while (npow < p.max_peaks) npow <<= 1;
+  const size_t smem2 = static_cast<size_t>(npow) * 8;
+  if (!attr2) {
+    OPB_CUDA(ctx, cudaFuncSetAttribute(sort_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr2 = true;
+  }
+  sort_peaks_kernel<<<n, 1024, smem2, ctx->stream>>>(ws->keys, ws->peak_counts, p.max_peaks, H, W, 18, ws->peaks,
+                                                     ws->idx_list, ws->type_start, ws->status);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  return OPB_OK;
+}
+
+int launch_connections(opb_ctx* ctx, PostWs* ws, const float* pafs, int n, int H, int W, double img_len) {
+  const opb_params& p = ctx->prm;
+  OPB_CUDA(ctx, cudaMemsetAsync(ws->cand_counts, 0, sizeof(int) * n * 19, ctx->stream));
+  dim3 g1(8, 19, n);
+  paf_candidates_kernel<<<g1, 128, 0, ctx->stream>>>(pafs, H, W, ws->peaks, ws->idx_list, ws->type_start,
+                                                     p.max_peaks, 18, ctx->pc, img_len, ws->cands, ws->cand_counts,
+                                                     p.max_candidates);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  dim3 g2(19, n);
+  limb_assign_kernel<<<g2, 256, 0, ctx->stream>>>(ws->peaks, ws->idx_list, ws->type_start, p.max_peaks, 18, ctx->pc,
+                                                  ws->cands, ws->cand_counts, p.max_candidates, ws->conns,
+                                                  ws->conn_counts, ctx->conn_cap, ws->status);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  return OPB_OK;
+}
+
+int launch_group(opb_ctx* ctx, PostWs* ws, int n, bool with_counts) {
+  group_persons_kernel<<<n, 32, 0, ctx->stream>>>(ws->peaks, with_counts ? ws->peak_counts : nullptr,
+                                                  ctx->prm.max_peaks, ctx->pc, ws->conns, ws->conn_counts,
+                                                  ctx->conn_cap, ws->subsets, ctx->prm.max_persons, ws->status,
+                                                  ws->headers, ws->persons, ws->subsets_out);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  return OPB_OK;
+}
+
+int copy_in(opb_ctx* ctx, void* dst, const void* src, size_t bytes, int loc) {
+  OPB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, loc == OPB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                ctx->stream));
+  return OPB_OK;
+}
+int copy_out(opb_ctx* ctx, void* dst, const void* src, size_t bytes, int loc) {
+  OPB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, loc == OPB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                                ctx->stream));
+  return OPB_OK;
+}
+
+// host peak table [n,5] float64 -> device PeakD + per-type stable index lists
+int upload_peaks(opb_ctx* ctx, PostWs* ws, const double* peaks, int n_peaks) {
+  if (n_peaks > ctx->prm.max_peaks) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "peak table larger than opb_params.max_peaks");
+  std::vector<PeakD> pk(n_peaks);
+  std::vector<int> idx(n_peaks), ts(19, 0);
+  std::vector<int> cnt(19, 0);
+  for (int i = 0; i < n_peaks; ++i) {
+    pk[i].type = static_cast<int>(peaks[i * 5 + 0]);
+    pk[i].x = peaks[i * 5 + 1];
+    pk[i].y = peaks[i * 5 + 2];
+    pk[i].score = static_cast<float>(peaks[i * 5 + 3]);
+    if (pk[i].type < 0 || pk[i].type >= 18) OPB_FAIL(ctx, OPB_ERR_ARG, "peak type out of range");
+    cnt[pk[i].type + 1]++;
+  }
+  for (int t = 1; t < 19; ++t) ts[t] = ts[t - 1] + cnt[t];
+  std::vector<int> fill(ts.begin(), ts.end());
+  for (int i = 0; i < n_peaks; ++i) idx[fill[pk[i].type]++] = i;
+  OPB_CUDA(ctx, cudaMemcpyAsync(ws->peaks, pk.data(), sizeof(PeakD) * n_peaks, cudaMemcpyHostToDevice, ctx->stream));
+  OPB_CUDA(ctx, cudaMemcpyAsync(ws->idx_list, idx.data(), sizeof(int) * n_peaks, cudaMemcpyHostToDevice, ctx->stream));
+  OPB_CUDA(ctx, cudaMemcpyAsync(ws->type_start, ts.data(), sizeof(int) * 19, cudaMemcpyHostToDevice, ctx->stream));
+  OPB_CUDA(ctx, cudaMemcpyAsync(ws->peak_counts, &n_peaks, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  OPB_CUDA(ctx, cudaMemsetAsync(ws->status, 0, sizeof(int), ctx->stream));
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return OPB_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int opb_version(void) { return 1; }
+
+const char* opb_last_error(const opb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int opb_create(opb_ctx** out, int device, const opb_params* params) {
+  if (!out || !params) { g_create_error = "null argument"; return OPB_ERR_ARG; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libopb has no CPU fallback)";
+    return OPB_ERR_CUDA;
+  }
+  if (device < 0) device = 0;   // reference: device<0 means CPU; here it means GPU 0 (no CPU path)
+  if (device >= ndev) { g_create_error = "device id out of range"; return OPB_ERR_ARG; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = "libopb is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major * 10 + prop.minor);
+    return OPB_ERR_UNSUPPORTED;
+  }
+  if (params->n_integ_points != 10 || params->gauss_radius < 1 || params->gauss_radius > PK_R_MAX ||
+      params->max_peaks < 32 || params->max_peaks > 16384 || params->max_candidates < 32 || params->max_persons < 1) {
+    g_create_error = "unsupported opb_params (n_integ_points must be 10, gauss_radius 1..16, max_peaks 32..16384)";
+    return OPB_ERR_ARG;
+  }
+  opb_ctx* ctx = new opb_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->prm = *params;
+  cudaSetDevice(device);
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_error = "cudaStreamCreate failed";
+    delete ctx;
+    return OPB_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn) {
+    g_create_error = "cuTensorMapEncodeTiled driver entry point not found";
+    delete ctx;
+    return OPB_ERR_CUDA;
+  }
+  ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  std::memset(&ctx->pc, 0, sizeof(ctx->pc));
+  for (int l = 0; l < 19; ++l) { ctx->pc.limbs[l][0] = params->limbs[l][0]; ctx->pc.limbs[l][1] = params->limbs[l][1]; }
+  ctx->pc.inner_product_thresh = params->inner_product_thresh;
+  ctx->pc.limb_length_ratio = params->limb_length_ratio;
+  ctx->pc.length_penalty_value = params->length_penalty_value;
+  ctx->pc.n_subset_limbs_thresh = params->n_subset_limbs_thresh;
+  ctx->pc.subset_score_thresh = params->subset_score_thresh;
+  ctx->pc.n_integ_points_thresh = params->n_integ_points_thresh;
+  ctx->taps.radius = params->gauss_radius;
+  for (int i = 0; i < 2 * params->gauss_radius + 1; ++i) ctx->taps.w[i] = params->gauss_taps[i];
+  ctx->conn_cap = kAssignMaxType;
+  *out = ctx;
+  return OPB_OK;
+}
+
+void opb_destroy(opb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : ctx->chains) { free_all(kv.second->allocs); delete kv.second; }
+  for (auto& kv : ctx->posts) { free_all(kv.second->allocs); delete kv.second; }
+  free_all(ctx->weight_allocs);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int opb_set_stream(opb_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return OPB_ERR_ARG;
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return OPB_OK;
+}
+
+int opb_synchronize(opb_ctx* ctx) {
+  if (!ctx) return OPB_ERR_ARG;
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return OPB_OK;
+}
+
+int64_t opb_launch_count(const opb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int opb_load_weights(opb_ctx* ctx, const char* layer, const float* W, const int64_t shape[4], const float* b) {
+  if (!ctx || !layer || !W || !shape || !b) return OPB_ERR_ARG;
+  if (shape[2] != shape[3] || (shape[2] != 1 && shape[2] != 3 && shape[2] != 7))
+    OPB_FAIL(ctx, OPB_ERR_ARG, std::string("unsupported kernel shape for layer ") + layer);
+  HostLayer L;
+  L.cout = static_cast<int>(shape[0]);
+  L.cin = static_cast<int>(shape[1]);
+  L.ks = static_cast<int>(shape[2]);
+  const size_t n = static_cast<size_t>(L.cout) * L.cin * L.ks * L.ks;
+  L.W.assign(W, W + n);
+  L.b.assign(b, b + L.cout);
+  ctx->host_layers[layer] = std::move(L);
+  return OPB_OK;
+}
+
+int opb_finalize_weights(opb_ctx* ctx, int precision_mode) {
+  if (!ctx) return OPB_ERR_ARG;
+  if (precision_mode != OPB_PRECISION_FAST && precision_mode != OPB_PRECISION_PARITY)
+    OPB_FAIL(ctx, OPB_ERR_ARG, "bad precision mode");
+  cudaSetDevice(ctx->device);
+  // drop everything derived from older weights
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& kv : ctx->chains) { free_all(kv.second->allocs); delete kv.second; }
+  ctx->chains.clear();
+  ctx->last_chain = nullptr;
+  free_all(ctx->weight_allocs);
+  ctx->packed.clear();
+  ctx->precision = precision_mode;
+  const bool split = precision_mode == OPB_PRECISION_PARITY;
+  int rc;
+  // conv1_1: [27][64] fp32, k = (r*3+s)*3 + c
+  {
+    auto it = ctx->host_layers.find("conv1_1");
+    if (it == ctx->host_layers.end()) OPB_FAIL(ctx, OPB_ERR_STATE, "weights for layer conv1_1 were not loaded");
+    const HostLayer& L = it->second;
+    if (L.cin != 3 || L.cout != 64 || L.ks != 3) OPB_FAIL(ctx, OPB_ERR_ARG, "conv1_1 must be 3->64, 3x3");
+    std::vector<float> wt(27 * 64);
+    for (int o = 0; o < 64; ++o)
+      for (int c = 0; c < 3; ++c)
+        for (int t = 0; t < 9; ++t) wt[(t * 3 + c) * 64 + o] = L.W[(static_cast<size_t>(o) * 3 + c) * 9 + t];
+    if ((rc = dev_alloc(ctx, &ctx->w_first, wt.size(), ctx->weight_allocs, false))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->b_first, 64, ctx->weight_allocs, false))) return rc;
+    OPB_CUDA(ctx, cudaMemcpyAsync(ctx->w_first, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    OPB_CUDA(ctx, cudaMemcpyAsync(ctx->b_first, L.b.data(), 64 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  auto simple = [&](const std::string& name, int cin, int cout, int ks) -> int {
+    return pack_weights(ctx, name, {{name, cout}}, identity_map(cin, round_up(cin, 64)), ks, split);
+  };
+  const struct { const char* n; int cin, cout; } backbone[] = {
+      {"conv1_2", 64, 64},    {"conv2_1", 64, 128},   {"conv2_2", 128, 128},     {"conv3_1", 128, 256},
+      {"conv3_2", 256, 256},  {"conv3_3", 256, 256},  {"conv3_4", 256, 256},     {"conv4_1", 256, 512},
+      {"conv4_2", 512, 512},  {"conv4_3_CPM", 512, 256}, {"conv4_4_CPM", 256, 128}};
+  for (auto& b : backbone)
+    if ((rc = simple(b.n, b.cin, b.cout, 3))) return rc;
+  for (const char* br : {"L1", "L2"}) {
+    const std::string B(br);
+    for (int i = 1; i <= 3; ++i)
+      if ((rc = simple("conv5_" + std::to_string(i) + "_CPM_" + B, 128, 128, 3))) return rc;
+    if ((rc = simple("conv5_4_CPM_" + B, 128, 512, 1))) return rc;
+    if ((rc = pack_weights(ctx, "conv5_5_CPM_" + B, {{"conv5_5_CPM_" + B, 48}}, identity_map(512, 512), 1, split)))
+      return rc;
+  }
+  // concat order on the device: [feature_map 0..127 | PAF 128..165 | heat 166..184 | 0 x 7];
+  // reference order is (h1[38], h2[19], feature_map[128]) (models/CocoPoseNet.py:168)
+  std::vector<int> cat_map(192, -1);
+  for (int d = 0; d < 128; ++d) cat_map[d] = 57 + d;
+  for (int d = 0; d < 38; ++d) cat_map[128 + d] = d;
+  for (int d = 0; d < 19; ++d) cat_map[166 + d] = 38 + d;
+  for (int st = 2; st <= 6; ++st) {
+    const std::string S = "_stage" + std::to_string(st);
+    if ((rc = pack_weights(ctx, "Mconv1" + S + "_fused", {{"Mconv1" + S + "_L1", 128}, {"Mconv1" + S + "_L2", 128}},
+                           cat_map, 7, split)))
+      return rc;
+    for (const char* br : {"L1", "L2"}) {
+      const std::string B = std::string("_") + br;
+      for (int i = 2; i <= 5; ++i)
+        if ((rc = simple("Mconv" + std::to_string(i) + S + B, 128, 128, 7))) return rc;
+      if ((rc = simple("Mconv6" + S + B, 128, 128, 1))) return rc;
+      if ((rc = pack_weights(ctx, "Mconv7" + S + B, {{"Mconv7" + S + B, 48}}, identity_map(128, 128), 1, split)))
+        return rc;
+    }
+  }
+  return OPB_OK;
+}
+
+int opb_forward(opb_ctx* ctx, const void* x, int x_format, int x_loc, int n, int h, int w, float* paf_out,
+                float* heat_out, int out_loc) {
+  if (!ctx || !x) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  Chain* ch = nullptr;
+  int rc = get_chain(ctx, n, h, w, &ch);
+  if (rc) return rc;
+  const size_t px = static_cast<size_t>(n) * h * w * 3;
+  if (x_format == OPB_U8_NHWC_BGR) {
+    if ((rc = copy_in(ctx, ch->img_u8, x, px, x_loc))) return rc;
+  } else if (x_format == OPB_F32_NCHW) {
+    if ((rc = copy_in(ctx, ch->img_f32, x, px * 4, x_loc))) return rc;
+  } else {
+    OPB_FAIL(ctx, OPB_ERR_ARG, "bad x_format");
+  }
+  if ((rc = run_chain(ctx, ch, x_format == OPB_U8_NHWC_BGR))) return rc;
+  const size_t lo = static_cast<size_t>(n) * (h / 8) * (w / 8);
+  if (paf_out && (rc = copy_out(ctx, paf_out, ch->paf_lo, lo * 38 * 4, out_loc))) return rc;
+  if (heat_out && (rc = copy_out(ctx, heat_out, ch->heat_lo, lo * 19 * 4, out_loc))) return rc;
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return OPB_OK;
+}
+
+int opb_upsample(opb_ctx* ctx, int mode, const float* in, int in_loc, int planes, int h, int w, float* out,
+                 int out_loc, int out_h, int out_w) {
+  if (!ctx || !in || !out || planes <= 0) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  std::vector<void*> tmp;
+  const float* d_in = in;
+  float* d_out = out;
+  int rc;
+  if (in_loc == OPB_HOST) {
+    float* t;
+    if ((rc = dev_alloc(ctx, &t, static_cast<size_t>(planes) * h * w, tmp, false))) { free_all(tmp); return rc; }
+    if ((rc = copy_in(ctx, t, in, static_cast<size_t>(planes) * h * w * 4, OPB_HOST))) { free_all(tmp); return rc; }
+    d_in = t;
+  }
+  if (out_loc == OPB_HOST) {
+    if ((rc = dev_alloc(ctx, &d_out, static_cast<size_t>(planes) * out_h * out_w, tmp, false))) { free_all(tmp); return rc; }
+  }
+  if (mode == OPB_UPSAMPLE_BILINEAR_AC) {
+    if (h < 2 || w < 2) { free_all(tmp); OPB_FAIL(ctx, OPB_ERR_ARG, "bilinear upsample needs h, w >= 2"); }
+    rc = launch_upsample(ctx, d_in, planes, h, w, d_out, out_h, out_w);
+  } else if (mode == OPB_UPSAMPLE_BICUBIC) {
+    dim3 grid((out_w + 31) / 32, (out_h + 7) / 8, std::min(planes, 64)), block(32, 8);
+    resize_cubic_kernel<<<grid, block, 0, ctx->stream>>>(d_in, planes, h, w, d_out, out_h, out_w, out_h, out_w, 0, 1.f);
+    ctx->launches++;
+    rc = OPB_OK;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = OPB_ERR_CUDA; }
+  } else {
+    ctx->err = "bad upsample mode";
+    rc = OPB_ERR_ARG;
+  }
+  if (!rc && out_loc == OPB_HOST) rc = copy_out(ctx, out, d_out, static_cast<size_t>(planes) * out_h * out_w * 4, OPB_HOST);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (!rc && e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = OPB_ERR_CUDA; }
+  free_all(tmp);
+  return rc;
+}
+
+int opb_peaks(opb_ctx* ctx, const float* heat, int heat_loc, int c_plus_1, int h, int w, double* peaks_out,
+              int peaks_cap, int* n_peaks) {
+  if (!ctx || !heat || !peaks_out || !n_peaks) return OPB_ERR_ARG;
+  if (c_plus_1 != 19) OPB_FAIL(ctx, OPB_ERR_ARG, "heatmaps must have 19 channels (18 joints + background)");
+  cudaSetDevice(ctx->device);
+  PostWs* ws;
+  int rc = get_post(ctx, 1, h, w, &ws);
+  if (rc) return rc;
+  const float* d_heat = heat;
+  if (heat_loc == OPB_HOST) {
+    if ((rc = copy_in(ctx, ws->heat, heat, static_cast<size_t>(19) * h * w * 4, OPB_HOST))) return rc;
+    d_heat = ws->heat;
+  }
+  if ((rc = launch_peaks(ctx, ws, d_heat, 1, 19, h, w))) return rc;
+  int cnt = 0, st = 0;
+  OPB_CUDA(ctx, cudaMemcpyAsync(&cnt, ws->peak_counts, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  OPB_CUDA(ctx, cudaMemcpyAsync(&st, ws->status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (st) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "more peaks than opb_params.max_peaks");
+  if (cnt > peaks_cap) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "peaks_out too small");
+  std::vector<PeakD> pk(cnt);
+  if (cnt) {
+    OPB_CUDA(ctx, cudaMemcpyAsync(pk.data(), ws->peaks, sizeof(PeakD) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  for (int i = 0; i < cnt; ++i) {
+    peaks_out[i * 5 + 0] = pk[i].type;
+    peaks_out[i * 5 + 1] = pk[i].x;
+    peaks_out[i * 5 + 2] = pk[i].y;
+    peaks_out[i * 5 + 3] = static_cast<double>(pk[i].score);
+    peaks_out[i * 5 + 4] = i;
+  }
+  *n_peaks = cnt;
+  return OPB_OK;
+}
+
+static int download_connections(opb_ctx* ctx, PostWs* ws, int img, double* conn_out, int conn_cap, int* conn_counts) {
+  std::vector<int> cc(19);
+  OPB_CUDA(ctx, cudaMemcpyAsync(cc.data(), ws->conn_counts + img * 19, sizeof(int) * 19, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  std::vector<Connection> all(static_cast<size_t>(19) * ctx->conn_cap);
+  OPB_CUDA(ctx, cudaMemcpyAsync(all.data(), ws->conns + static_cast<size_t>(img) * 19 * ctx->conn_cap,
+                                sizeof(Connection) * all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int o = 0;
+  for (int l = 0; l < 19; ++l) {
+    conn_counts[l] = cc[l];
+    for (int k = 0; k < cc[l]; ++k) {
+      if (o >= conn_cap) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "conn_out too small");
+      const Connection& c = all[static_cast<size_t>(l) * ctx->conn_cap + k];
+      conn_out[o * 3 + 0] = c.id_a;
+      conn_out[o * 3 + 1] = c.id_b;
+      conn_out[o * 3 + 2] = c.score;
+      ++o;
+    }
+  }
+  return OPB_OK;
+}
+
+int opb_connections(opb_ctx* ctx, const float* paf, int paf_loc, int h, int w, const double* peaks, int n_peaks,
+                    double img_len, double* conn_out, int conn_cap, int* conn_counts) {
+  if (!ctx || !paf || !conn_out || !conn_counts || (n_peaks > 0 && !peaks)) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  PostWs* ws;
+  int rc = get_post(ctx, 1, h, w, &ws);
+  if (rc) return rc;
+  const float* d_paf = paf;
+  if (paf_loc == OPB_HOST) {
+    if ((rc = copy_in(ctx, ws->pafs, paf, static_cast<size_t>(38) * h * w * 4, OPB_HOST))) return rc;
+    d_paf = ws->pafs;
+  }
+  if ((rc = upload_peaks(ctx, ws, peaks, n_peaks))) return rc;
+  if ((rc = launch_connections(ctx, ws, d_paf, 1, h, w, img_len))) return rc;
+  int st = 0;
+  OPB_CUDA(ctx, cudaMemcpyAsync(&st, ws->status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (st) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "candidate / per-type capacity exceeded (status " + std::to_string(st) +
+                                              "); raise opb_params.max_candidates");
+  return download_connections(ctx, ws, 0, conn_out, conn_cap, conn_counts);
+}
+
+int opb_group(opb_ctx* ctx, const double* conns, const int* conn_counts, const double* peaks, int n_peaks,
+              double* subsets_out, int subsets_cap, int* n_subsets) {
+  if (!ctx || !conn_counts || !subsets_out || !n_subsets || (n_peaks > 0 && !peaks)) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  PostWs* ws;
+  int rc = get_post(ctx, 1, 8, 8, &ws);
+  if (rc) return rc;
+  if ((rc = upload_peaks(ctx, ws, peaks, n_peaks))) return rc;
+  std::vector<Connection> all(static_cast<size_t>(19) * ctx->conn_cap);
+  int o = 0;
+  for (int l = 0; l < 19; ++l) {
+    if (conn_counts[l] > ctx->conn_cap) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "too many connections for one limb");
+    for (int k = 0; k < conn_counts[l]; ++k, ++o) {
+      Connection& c = all[static_cast<size_t>(l) * ctx->conn_cap + k];
+      c.id_a = static_cast<int>(conns[o * 3 + 0]);
+      c.id_b = static_cast<int>(conns[o * 3 + 1]);
+      c.score = conns[o * 3 + 2];
+      if (c.id_a < 0 || c.id_a >= n_peaks || c.id_b < 0 || c.id_b >= n_peaks) OPB_FAIL(ctx, OPB_ERR_ARG, "connection id out of range");
+    }
+  }
+  OPB_CUDA(ctx, cudaMemcpyAsync(ws->conns, all.data(), sizeof(Connection) * all.size(), cudaMemcpyHostToDevice, ctx->stream));
+  OPB_CUDA(ctx, cudaMemcpyAsync(ws->conn_counts, conn_counts, sizeof(int) * 19, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = launch_group(ctx, ws, 1, true))) return rc;
+  ImageHeader hd;
+  OPB_CUDA(ctx, cudaMemcpyAsync(&hd, ws->headers, sizeof(hd), cudaMemcpyDeviceToHost, ctx->stream));
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (hd.status == OPB_ERR_INDEX) OPB_FAIL(ctx, OPB_ERR_INDEX, "list assignment index out of range");
+  if (hd.status) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "more live subsets than opb_params.max_persons");
+  if (hd.n_persons > subsets_cap) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "subsets_out too small");
+  if (hd.n_persons) {
+    OPB_CUDA(ctx, cudaMemcpyAsync(subsets_out, ws->subsets_out, sizeof(double) * 20 * hd.n_persons,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  *n_subsets = hd.n_persons;
+  return OPB_OK;
+}
+
+int opb_detect_batch(opb_ctx* ctx, const uint8_t* imgs, int imgs_loc, int n, int h, int w, int map_h, int map_w,
+                     double img_len, const float* inject_paf, const float* inject_heat, opb_image_header* headers_out,
+                     opb_person* persons_out, int out_loc) {
+  if (!ctx || !imgs || !headers_out || !persons_out) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  Chain* ch = nullptr;
+  PostWs* ws = nullptr;
+  int rc;
+  if ((rc = get_chain(ctx, n, h, w, &ch))) return rc;
+  if ((rc = get_post(ctx, n, map_h, map_w, &ws))) return rc;
+  if ((rc = copy_in(ctx, ch->img_u8, imgs, static_cast<size_t>(n) * h * w * 3, imgs_loc))) return rc;
+  if ((rc = run_chain(ctx, ch, true))) return rc;
+  const int h8 = h / 8, w8 = w / 8;
+  const float* paf_lo = inject_paf ? inject_paf : ch->paf_lo;
+  const float* heat_lo = inject_heat ? inject_heat : ch->heat_lo;
+  if ((rc = launch_upsample(ctx, paf_lo, n * 38, h8, w8, ws->pafs, map_h, map_w))) return rc;
+  if ((rc = launch_upsample(ctx, heat_lo, n * 19, h8, w8, ws->heat, map_h, map_w))) return rc;
+  if ((rc = launch_peaks(ctx, ws, ws->heat, n, 19, map_h, map_w))) return rc;
+  if ((rc = launch_connections(ctx, ws, ws->pafs, n, map_h, map_w, img_len))) return rc;
+  if ((rc = launch_group(ctx, ws, n, true))) return rc;
+  if ((rc = copy_out(ctx, headers_out, ws->headers, sizeof(ImageHeader) * n, out_loc))) return rc;
+  if ((rc = copy_out(ctx, persons_out, ws->persons, sizeof(PersonOut) * n * ctx->prm.max_persons, out_loc))) return rc;
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return OPB_OK;
+}
+
+int opb_get_image_detail(opb_ctx* ctx, int img, double* peaks_out, int peaks_cap, int* n_peaks, double* conn_out,
+                         int conn_cap, int* conn_counts, double* subsets_out, int subsets_cap, int* n_subsets) {
+  if (!ctx) return OPB_ERR_ARG;
+  PostWs* ws = ctx->last_post;
+  if (!ws || img < 0 || img >= ws->N) OPB_FAIL(ctx, OPB_ERR_STATE, "no post-process result for that image");
+  cudaSetDevice(ctx->device);
+  ImageHeader hd;
+  OPB_CUDA(ctx, cudaMemcpyAsync(&hd, ws->headers + img, sizeof(hd), cudaMemcpyDeviceToHost, ctx->stream));
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_peaks) *n_peaks = hd.n_peaks;
+  if (peaks_out) {
+    if (hd.n_peaks > peaks_cap) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "peaks_out too small");
+    std::vector<PeakD> pk(hd.n_peaks);
+    if (hd.n_peaks) {
+      OPB_CUDA(ctx, cudaMemcpyAsync(pk.data(), ws->peaks + static_cast<size_t>(img) * ctx->prm.max_peaks,
+                                    sizeof(PeakD) * hd.n_peaks, cudaMemcpyDeviceToHost, ctx->stream));
+      OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    for (int i = 0; i < hd.n_peaks; ++i) {
+      peaks_out[i * 5 + 0] = pk[i].type; peaks_out[i * 5 + 1] = pk[i].x; peaks_out[i * 5 + 2] = pk[i].y;
+      peaks_out[i * 5 + 3] = static_cast<double>(pk[i].score); peaks_out[i * 5 + 4] = i;
+    }
+  }
+  if (conn_out && conn_counts) {
+    int rc = download_connections(ctx, ws, img, conn_out, conn_cap, conn_counts);
+    if (rc) return rc;
+  }
+  if (n_subsets) *n_subsets = hd.n_persons;
+  if (subsets_out) {
+    if (hd.n_persons > subsets_cap) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "subsets_out too small");
+    if (hd.n_persons) {
+      OPB_CUDA(ctx, cudaMemcpyAsync(subsets_out, ws->subsets_out + static_cast<size_t>(img) * ctx->prm.max_persons * 20,
+                                    sizeof(double) * 20 * hd.n_persons, cudaMemcpyDeviceToHost, ctx->stream));
+      OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  return OPB_OK;
+}
+
+int opb_precise_begin(opb_ctx* ctx, int orig_h, int orig_w) {
+  if (!ctx || orig_h <= 0 || orig_w <= 0) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  PostWs* ws;
+  return get_post(ctx, 1, orig_h, orig_w, &ws);
+}
+
+int opb_precise_add_scale(opb_ctx* ctx, const uint8_t* img, int img_loc, int ph, int pw, int pad_h, int pad_w,
+                          int scale_index, int n_scales) {
+  if (!ctx || !img) return OPB_ERR_ARG;
+  PostWs* ws = ctx->last_post;
+  if (!ws || ws->N != 1) OPB_FAIL(ctx, OPB_ERR_STATE, "opb_precise_begin was not called");
+  cudaSetDevice(ctx->device);
+  Chain* ch = nullptr;
+  int rc = get_chain(ctx, 1, ph, pw, &ch);
+  if (rc) return rc;
+  if ((rc = copy_in(ctx, ch->img_u8, img, static_cast<size_t>(ph) * pw * 3, img_loc))) return rc;
+  if ((rc = run_chain(ctx, ch, true))) return rc;
+  const int h8 = ph / 8, w8 = pw / 8;
+  const int ch_h = ph - pad_h, ch_w = pw - pad_w;   // crop after the x8 resize (:462,:466)
+  std::vector<void*> tmp;
+  float* mid = nullptr;
+  if ((rc = dev_alloc(ctx, &mid, static_cast<size_t>(38) * ch_h * ch_w, tmp, false))) { free_all(tmp); return rc; }
+  const float scale = (scale_index == n_scales - 1) ? 1.0f / static_cast<float>(n_scales) : 1.0f;
+  for (int which = 0; which < 2; ++which) {
+    const int C = which ? 19 : 38;
+    const float* lo = which ? ch->heat_lo : ch->paf_lo;
+    float* acc = which ? ws->heat : ws->pafs;
+    dim3 block(32, 8);
+    dim3 g1((ch_w + 31) / 32, (ch_h + 7) / 8, C);
+    resize_cubic_kernel<<<g1, block, 0, ctx->stream>>>(lo, C, h8, w8, mid, ph, pw, ch_h, ch_w, 0, 1.f);
+    dim3 g2((ws->W + 31) / 32, (ws->H + 7) / 8, C);
+    resize_cubic_kernel<<<g2, block, 0, ctx->stream>>>(mid, C, ch_h, ch_w, acc, ws->H, ws->W, ws->H, ws->W,
+                                                       scale_index > 0 ? 1 : 0, scale);
+    ctx->launches += 2;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  free_all(tmp);
+  if (e != cudaSuccess) OPB_FAIL(ctx, OPB_ERR_CUDA, std::string("precise add_scale: ") + cudaGetErrorString(e));
+  return OPB_OK;
+}
+
+int opb_precise_finish(opb_ctx* ctx, double img_len, opb_image_header* header_out, opb_person* persons_out,
+                       int out_loc) {
+  if (!ctx || !header_out || !persons_out) return OPB_ERR_ARG;
+  PostWs* ws = ctx->last_post;
+  if (!ws || ws->N != 1) OPB_FAIL(ctx, OPB_ERR_STATE, "opb_precise_begin was not called");
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = launch_peaks(ctx, ws, ws->heat, 1, 19, ws->H, ws->W))) return rc;
+  if ((rc = launch_connections(ctx, ws, ws->pafs, 1, ws->H, ws->W, img_len))) return rc;
+  if ((rc = launch_group(ctx, ws, 1, true))) return rc;
+  if ((rc = copy_out(ctx, header_out, ws->headers, sizeof(ImageHeader), out_loc))) return rc;
+  if ((rc = copy_out(ctx, persons_out, ws->persons, sizeof(PersonOut) * ctx->prm.max_persons, out_loc))) return rc;
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return OPB_OK;
+}
+
+int opb_download_maps(opb_ctx* ctx, float* pafs_out, float* heat_out, int out_loc) {
+  if (!ctx) return OPB_ERR_ARG;
+  PostWs* ws = ctx->last_post;
+  if (!ws) OPB_FAIL(ctx, OPB_ERR_STATE, "no post-process workspace");
+  cudaSetDevice(ctx->device);
+  int rc;
+  const size_t plane = static_cast<size_t>(ws->H) * ws->W * 4;
+  if (pafs_out && (rc = copy_out(ctx, pafs_out, ws->pafs, plane * 38, out_loc))) return rc;
+  if (heat_out && (rc = copy_out(ctx, heat_out, ws->heat, plane * 19, out_loc))) return rc;
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return OPB_OK;
+}
+
+void* opb_device_buffer(opb_ctx* ctx, int which) {
+  if (!ctx) return nullptr;
+  Chain* ch = ctx->last_chain;
+  PostWs* ws = ctx->last_post;
+  switch (which) {
+    case 0: return ch ? ch->paf_lo : nullptr;
+    case 1: return ch ? ch->heat_lo : nullptr;
+    case 2: return ws ? ws->pafs : nullptr;
+    case 3: return ws ? ws->heat : nullptr;
+    case 4: return ws ? ws->headers : nullptr;
+    case 5: return ws ? ws->persons : nullptr;
+    case 6: return ws ? ws->peaks : nullptr;
+    default: return nullptr;
+  }
+}
+
+int opb_time_stage(opb_ctx* ctx, const char* stage, int reps, float* ms) {
+  if (!ctx || !stage || !ms || reps <= 0) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  Chain* ch = ctx->last_chain;
+  PostWs* ws = ctx->last_post;
+  const std::string s(stage);
+  cudaEvent_t e0, e1;
+  OPB_CUDA(ctx, cudaEventCreate(&e0));
+  OPB_CUDA(ctx, cudaEventCreate(&e1));
+  int rc = OPB_OK;
+  int n_launch = 0;
+  auto run_once = [&]() -> int {
+    if (s == "upsample_paf" || s == "upsample_heat" || s == "peaks" || s == "paf_integral" || s == "limb_assign" ||
+        s == "group") {
+      if (!ws || !ch) { ctx->err = "no cached pipeline to time"; return OPB_ERR_STATE; }
+      const int n = ws->N, h8 = ch->H / 8, w8 = ch->W / 8;
+      if (s == "upsample_paf") { ++n_launch; return launch_upsample(ctx, ch->paf_lo, n * 38, h8, w8, ws->pafs, ws->H, ws->W); }
+      if (s == "upsample_heat") { ++n_launch; return launch_upsample(ctx, ch->heat_lo, n * 19, h8, w8, ws->heat, ws->H, ws->W); }
+      if (s == "peaks") { n_launch += 2; return launch_peaks(ctx, ws, ws->heat, n, 19, ws->H, ws->W); }
+      if (s == "paf_integral" || s == "limb_assign") { n_launch += 2; return launch_connections(ctx, ws, ws->pafs, n, ws->H, ws->W, ws->W); }
+      ++n_launch;
+      return launch_group(ctx, ws, n, true);
+    }
+    if (!ch) { ctx->err = "no cached conv chain to time"; return OPB_ERR_STATE; }
+    bool any = false;
+    for (Op& op : ch->ops) {
+      if (s == "conv_chain" || op.tag == s) {
+        any = true;
+        ++n_launch;
+        int r = launch_op(ctx, ch, op);
+        if (r) return r;
+      }
+    }
+    if (!any) { ctx->err = "unknown stage " + s; return OPB_ERR_ARG; }
+    return OPB_OK;
+  };
+  rc = run_once();  // warm-up
+  if (!rc) {
+    n_launch = 0;
+    cudaEventRecord(e0, ctx->stream);
+    for (int i = 0; i < reps && !rc; ++i) rc = run_once();
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess && !rc) { ctx->err = cudaGetErrorString(e); rc = OPB_ERR_CUDA; }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e0, e1);
+    *ms = t / reps;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
+int opb_test_conv(opb_ctx* ctx, const float* x, int n, int h, int w, int cin, const float* W, const float* b, int cout,
+                  int ksize, int relu, int precision_mode, float* y) {
+  if (!ctx || !x || !W || !b || !y) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const bool split = precision_mode == OPB_PRECISION_PARITY;
+  const int saved_precision = ctx->precision;
+  ctx->precision = precision_mode;
+  Chain tmp;
+  int rc = OPB_OK;
+  const int cin_pad = round_up(cin, 64);
+  const int cout_pad = cout <= 48 ? 48 : round_up(cout, 64);
+  if (cout_pad > 256 && cout_pad % 256) { ctx->precision = saved_precision; OPB_FAIL(ctx, OPB_ERR_ARG, "test conv: cout must be <=256 or a multiple of 256"); }
+  HostLayer L;
+  L.cin = cin; L.cout = cout; L.ks = ksize;
+  L.W.assign(W, W + static_cast<size_t>(cout) * cin * ksize * ksize);
+  L.b.assign(b, b + cout);
+  ctx->host_layers["__test__"] = L;
+  Act in, out;
+  std::vector<__half> hx;
+  std::vector<__half> hy;
+  do {
+    if ((rc = pack_weights(ctx, "__test__", {{"__test__", cout_pad}}, identity_map(cin, cin_pad), ksize, split))) break;
+    if ((rc = alloc_act(ctx, &tmp, &in, n, h, w, cin_pad))) break;
+    if ((rc = alloc_act(ctx, &tmp, &out, n, h, w, cout_pad))) break;
+    hx.assign(static_cast<size_t>(n) * h * w * in.Ctot, __float2half(0.f));
+    for (size_t pix = 0; pix < static_cast<size_t>(n) * h * w; ++pix)
+      for (int c = 0; c < cin; ++c) {
+        const float v = x[pix * cin + c];
+        const __half hi = __float2half_rn(v);
+        hx[pix * in.Ctot + c] = hi;
+        if (split) hx[pix * in.Ctot + in.C + c] = __float2half_rn(v - __half2float(hi));
+      }
+    cudaError_t e = cudaMemcpyAsync(in.p, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = OPB_ERR_CUDA; break; }
+    ConvSpec s{};
+    s.in[0] = &in; s.in_coff[0] = 0; s.wkey[0] = "__test__"; s.out[0] = &out; s.out_coff[0] = 0;
+    s.cout_valid[0] = cout; s.n_problems = 1; s.relu = relu;
+    if ((rc = add_conv(ctx, &tmp, "__test__", s))) break;
+    if ((rc = launch_op(ctx, &tmp, tmp.ops[0]))) break;
+    hy.resize(static_cast<size_t>(n) * h * w * out.Ctot);
+    e = cudaMemcpyAsync(hy.data(), out.p, hy.size() * 2, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("test conv: ") + cudaGetErrorString(e); rc = OPB_ERR_CUDA; break; }
+    for (size_t pix = 0; pix < static_cast<size_t>(n) * h * w; ++pix)
+      for (int c = 0; c < cout; ++c) {
+        float v = __half2float(hy[pix * out.Ctot + c]);
+        if (split) v += __half2float(hy[pix * out.Ctot + out.C + c]);
+        y[pix * cout + c] = v;
+      }
+  } while (0);
+  cudaStreamSynchronize(ctx->stream);
+  free_all(tmp.allocs);
+  ctx->host_layers.erase("__test__");
+  ctx->packed.erase("__test__");
+  ctx->precision = saved_precision;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// upsample.cuh -- map upsampling.
+//   upsample_bilinear_ac_kernel : F.resize_images (Chainer, align-corners bilinear) of
+//       pose_detector.py:501-502.  Restates Chainer's published ResizeImages.forward: sample
+//       grid u = linspace(0, w-1, W) in float64, u0 = clip(floor(u), 0, w-2), the four tap
+//       weights formed in float64 and cast to float32, y = w1*x00; y += w2*x01; y += w3*x10;
+//       y += w4*x11 in float32 (no FMA contraction) -> bit-exact vs the oracle.
+//   resize_cubic_kernel : cv2.resize(..., INTER_CUBIC) for float32 maps (pose_detector.py
+//       :461-467): Keys cubic A=-0.75, half-pixel centres, replicate border, float32 taps.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace opb {
+
+__device__ __forceinline__ void ac_axis(int i, int n_in, int n_out, int& i0, double& f) {
+  // numpy.linspace(0, n_in-1, n_out)[i]: i*step (+0), last element exactly n_in-1
+  double u;
+  if (n_out == 1) {
+    u = 0.0;
+  } else if (i == n_out - 1) {
+    u = static_cast<double>(n_in - 1);
+  } else {
+    const double step = __ddiv_rn(static_cast<double>(n_in - 1), static_cast<double>(n_out - 1));
+    u = __dmul_rn(static_cast<double>(i), step);
+  }
+  int k = static_cast<int>(floor(u));
+  k = max(0, min(k, n_in - 2));
+  i0 = k;
+  f = u;
+}
+
+// in [planes][h][w] -> out [planes][H][W]; grid (ceil(W/32), ceil(H/8), plane_groups)
+__global__ void __launch_bounds__(256)
+upsample_bilinear_ac_kernel(const float* __restrict__ in, int planes, int h, int w, float* __restrict__ out, int H,
+                            int W, int planes_per_block) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  int u0, v0;
+  double u, v;
+  ac_axis(x, w, W, u0, u);
+  ac_axis(y, h, H, v0, v);
+  const int u1 = u0 + 1, v1 = v0 + 1;
+  const double du1 = __dsub_rn(static_cast<double>(u1), u), du0 = __dsub_rn(u, static_cast<double>(u0));
+  const double dv1 = __dsub_rn(static_cast<double>(v1), v), dv0 = __dsub_rn(v, static_cast<double>(v0));
+  const float w1 = static_cast<float>(__dmul_rn(du1, dv1));
+  const float w2 = static_cast<float>(__dmul_rn(du0, dv1));
+  const float w3 = static_cast<float>(__dmul_rn(du1, dv0));
+  const float w4 = static_cast<float>(__dmul_rn(du0, dv0));
+  const int o00 = v0 * w + u0, o01 = v0 * w + u1, o10 = v1 * w + u0, o11 = v1 * w + u1;
+  const int p_begin = blockIdx.z * planes_per_block;
+  const int p_end = min(planes, p_begin + planes_per_block);
+  const size_t in_plane = static_cast<size_t>(h) * w, out_plane = static_cast<size_t>(H) * W;
+  const float* src = in + p_begin * in_plane;
+  float* dst = out + p_begin * out_plane + static_cast<size_t>(y) * W + x;
+#pragma unroll 4
+  for (int p = p_begin; p < p_end; ++p) {
+    float r = __fmul_rn(w1, __ldg(src + o00));
+    r = __fadd_rn(r, __fmul_rn(w2, __ldg(src + o01)));
+    r = __fadd_rn(r, __fmul_rn(w3, __ldg(src + o10)));
+    r = __fadd_rn(r, __fmul_rn(w4, __ldg(src + o11)));
+    __stcs(dst, r);   // streaming store: the full-resolution map is written once
+    src += in_plane;
+    dst += out_plane;
+  }
+}
+
+// ---- cv2 INTER_CUBIC for float32 (A = -0.75), separable, replicate border ------------------
+__device__ __forceinline__ void cubic_taps(float t, float (&c)[4]) {
+  const float A = -0.75f;
+  c[0] = ((A * (t + 1) - 5 * A) * (t + 1) + 8 * A) * (t + 1) - 4 * A;
+  c[1] = ((A + 2) * t - (A + 3)) * t * t + 1;
+  c[2] = ((A + 2) * (1 - t) - (A + 3)) * (1 - t) * (1 - t) + 1;
+  c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+// in: HWC float32 [h][w][C] (cv2 layout) or planar [C][h][w] selected by in_planar;
+// out planar [C][H][W] (cropped region [crop_h, crop_w] of the (H_full, W_full) resize),
+// out = ((accumulate ? out : 0) + value) * scale.
+__global__ void __launch_bounds__(256)
+resize_cubic_kernel(const float* __restrict__ in, int C, int h, int w, float* __restrict__ out, int H_full,
+                    int W_full, int crop_h, int crop_w, int accumulate, float scale) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= crop_w || y >= crop_h) return;
+  // cv2: fx = (x + 0.5) * (w / W_full) - 0.5 with scale computed in double, cast to float
+  // cv2::resize: inv_scale = dsize/ssize (double); scale = 1./inv_scale
+  const double sx = 1.0 / (static_cast<double>(W_full) / w), sy = 1.0 / (static_cast<double>(H_full) / h);
+  float fx = static_cast<float>((x + 0.5) * sx - 0.5);
+  float fy = static_cast<float>((y + 0.5) * sy - 0.5);
+  int ix = static_cast<int>(floorf(fx)), iy = static_cast<int>(floorf(fy));
+  fx -= ix;
+  fy -= iy;
+  float cx[4], cy[4];
+  cubic_taps(fx, cx);
+  cubic_taps(fy, cy);
+  int xs[4], ys[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    xs[k] = min(max(ix - 1 + k, 0), w - 1);
+    ys[k] = min(max(iy - 1 + k, 0), h - 1);
+  }
+  const size_t in_plane = static_cast<size_t>(h) * w, out_plane = static_cast<size_t>(crop_h) * crop_w;
+  for (int c = blockIdx.z; c < C; c += gridDim.z) {
+    const float* src = in + c * in_plane;
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float* row = src + static_cast<size_t>(ys[r]) * w;
+      const float hsum = __ldg(row + xs[0]) * cx[0] + __ldg(row + xs[1]) * cx[1] + __ldg(row + xs[2]) * cx[2] +
+                         __ldg(row + xs[3]) * cx[3];
+      acc += hsum * cy[r];
+    }
+    float* o = out + c * out_plane + static_cast<size_t>(y) * crop_w + x;
+    *o = ((accumulate ? *o : 0.f) + acc) * scale;   // scale = 1, or 1/len(scales) on the last pass
+  }
+}
+
+}  // namespace opb

@@ -120,3 +120,12 @@ def procedural_image(h, w, seed=0):
         img = img * (1 - m) + col * m
     img += rs.standard_normal(img.shape) * 6.0
     return np.clip(np.round(img), 0, 255).astype(np.uint8)
+
+
+def eight_person_lowres(h=46, w=82, n_person=8, seed=0):
+    """Network-output-resolution (H/8 x W/8) maps of eight stick figures: what is injected as
+    the CocoPoseNet output for the full-pipeline benchmark (random weights cannot produce
+    people).  Joint sigma ~1 low-res pixel (training uses heatmap_sigma 7 at 368 px,
+    entity.py:61), PAF band +-1 pixel.  Returns (paf [38,h,w] f32, heat [19,h,w] f32)."""
+    paf, heat, _ = eight_person_maps(h, w, n_person, seed, sigma=1.0, band=1.0, noise=0.002)
+    return paf, heat

@@ -1,0 +1,202 @@
+/*
+ * opb.h -- C ABI of libopb.so: the B200-native (sm_100a) OpenPose inference hot path.
+ *
+ * The reference (DeNA/Chainer_Realtime_Multi-Person_Pose_Estimation) is pure Python and has
+ * no FFI layer; its drop-in boundary is the Python module `pose_detector`.  This header is the
+ * native boundary *underneath* that module: every entry point replaces one block of
+ * reference code (cited as file:line relative to the reference tree) and is what a
+ * maintainer of the reference would bind with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; no torch / numpy types.
+ *   - every function returns 0 on success or a negative opb_status; the message is
+ *     available from opb_last_error().  The Python wrapper raises on non-zero.
+ *   - `loc` arguments: OPB_HOST (pageable or pinned host memory) or OPB_DEVICE (memory on
+ *     the context's device).  Output buffers are caller-allocated with an explicit capacity;
+ *     the number of valid rows is returned through an int* argument.
+ *   - one context per device; calls on one context are serialised on its stream
+ *     (opb_set_stream installs a caller-owned cudaStream_t, e.g. torch's current stream).
+ *   - there is NO CPU fallback: every compute entry point launches sm_100a kernels.
+ */
+#ifndef OPB_H_
+#define OPB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPB_N_JOINTS 18
+#define OPB_N_LIMBS 19
+#define OPB_MAX_TAPS 64
+
+typedef enum {
+  OPB_OK = 0,
+  OPB_ERR_CUDA = -1,          /* CUDA runtime / driver error                                   */
+  OPB_ERR_ARG = -2,           /* bad argument                                                  */
+  OPB_ERR_STATE = -3,         /* e.g. forward before weights were finalised                    */
+  OPB_ERR_CAPACITY = -4,      /* a caller buffer or an internal list overflowed (never silent) */
+  OPB_ERR_INDEX = -5,         /* grouping found >=3 matching subsets: the reference raises
+                                 IndexError at pose_detector.py:197                            */
+  OPB_ERR_UNSUPPORTED = -6
+} opb_status;
+
+enum { OPB_HOST = 0, OPB_DEVICE = 1 };
+enum { OPB_F32_NCHW = 0, OPB_U8_NHWC_BGR = 1 };          /* opb_forward input formats       */
+enum { OPB_PRECISION_FAST = 0, OPB_PRECISION_PARITY = 1 }; /* fp16 | split-fp16 (hi+lo, 3 MMAs) */
+enum { OPB_UPSAMPLE_BILINEAR_AC = 0, OPB_UPSAMPLE_BICUBIC = 1 };
+
+/* Constants of entity.py:71-105 (`params`) plus the 21 Gaussian taps of
+ * scipy.ndimage.gaussian_filter(sigma=2.5) (pose_detector.py:86), computed by the host in
+ * float64 exactly as scipy does, and the capacities of the device-side lists. */
+typedef struct opb_params {
+  int32_t limbs[OPB_N_LIMBS][2];      /* entity.py:85-105 limbs_point                          */
+  double heatmap_peak_thresh;         /* 0.05  entity.py:79                                    */
+  double inner_product_thresh;        /* 0.05  entity.py:80                                    */
+  double limb_length_ratio;           /* 1.0   entity.py:81                                    */
+  double length_penalty_value;        /* 1     entity.py:82                                    */
+  double n_subset_limbs_thresh;       /* 3     entity.py:83                                    */
+  double subset_score_thresh;         /* 0.2   entity.py:84                                    */
+  int32_t n_integ_points;             /* 10    entity.py:77 (only 10 is supported)             */
+  int32_t n_integ_points_thresh;      /* 8     entity.py:78                                    */
+  int32_t gauss_radius;               /* 10 = int(4.0*2.5+0.5)                                 */
+  int32_t reserved0;
+  double gauss_taps[OPB_MAX_TAPS];    /* 2*gauss_radius+1 normalised float64 taps              */
+  int32_t max_peaks;                  /* per image   (default 8192)                            */
+  int32_t max_candidates;             /* per (image, limb) accepted PAF candidates (def 32768) */
+  int32_t max_persons;                /* per image subsets alive at any time (default 1024)    */
+  int32_t reserved1;
+} opb_params;
+
+/* Fixed-size per-image result record written by opb_detect_batch (device-resident path) and
+ * exchanged between GPUs with one all-gather.  Coordinates are integer peak positions at map
+ * resolution so that the host can redo the float64 rescale of pose_detector.py:513-514
+ * exactly.  joint id -1 = missing. */
+typedef struct opb_person {
+  double score;                       /* subsets[:, -2]                                        */
+  double count;                       /* subsets[:, -1] (non-integer after a merge, :217)      */
+  int32_t peak_id[OPB_N_JOINTS];      /* index into the image's peak table, -1 = none          */
+  int32_t x[OPB_N_JOINTS];
+  int32_t y[OPB_N_JOINTS];
+  int32_t pad[2];
+} opb_person;                          /* 16 + 3*72 + 8 = 240 bytes                             */
+
+typedef struct opb_image_header {
+  int32_t n_peaks;
+  int32_t n_persons;
+  int32_t status;                     /* 0 or an opb_status (capacity / index error)           */
+  int32_t n_connections;              /* total over the 19 limbs                               */
+} opb_image_header;
+
+typedef struct opb_ctx opb_ctx;
+
+/* -- lifetime ---------------------------------------------------------------------------- */
+/* replaces PoseDetector.__init__ device selection, pose_detector.py:28-35 */
+int opb_create(opb_ctx** out, int device, const opb_params* params);
+void opb_destroy(opb_ctx* ctx);
+const char* opb_last_error(const opb_ctx* ctx);     /* ctx may be NULL: last create error      */
+int opb_set_stream(opb_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = context's own     */
+int opb_synchronize(opb_ctx* ctx);
+int opb_version(void);
+
+/* -- weights: replaces serializers.load_npz(weights_file, model), pose_detector.py:25-26 --- */
+/* W is [Cout,Cin,k,k] float32 (Chainer OIHW), b is [Cout]; both host pointers. 92 calls.   */
+int opb_load_weights(opb_ctx* ctx, const char* layer, const float* W, const int64_t shape[4],
+                     const float* b);
+/* repacks to K-major fp16 (and the hi/lo split for OPB_PRECISION_PARITY) and uploads.       */
+int opb_finalize_weights(opb_ctx* ctx, int precision_mode);
+
+/* -- CocoPoseNet forward: replaces self.model(x), pose_detector.py:499 / :451
+ *    (models/CocoPoseNet.py:132-262).  x: [N,3,H,W] float32 (OPB_F32_NCHW, already
+ *    preprocessed as pose_detector.py:426-431) or [N,H,W,3] uint8 BGR (OPB_U8_NHWC_BGR,
+ *    /255-0.5 fused into the first conv).  H, W multiples of 8.
+ *    paf_out [N,38,H/8,W/8], heat_out [N,19,H/8,W/8] float32.                               */
+int opb_forward(opb_ctx* ctx, const void* x, int x_format, int x_loc, int n, int h, int w,
+                float* paf_out, float* heat_out, int out_loc);
+
+/* -- upsample: replaces F.resize_images (pose_detector.py:501-502, bilinear align-corners)
+ *    and cv2.resize(INTER_CUBIC) of float maps (pose_detector.py:461-467).
+ *    in [planes,h,w] -> out [planes,H,W] float32.  For BICUBIC, out is cropped to
+ *    [crop_h, crop_w] of the (H,W) result when crop_* > 0 (pose_detector.py:462,466) and
+ *    `accumulate` != 0 adds into out instead of overwriting (pafs_sum +=, :463).            */
+int opb_upsample(opb_ctx* ctx, int mode, const float* in, int in_loc, int planes, int h, int w,
+                 float* out, int out_loc, int out_h, int out_w);
+
+/* -- peaks: replaces compute_peaks_from_heatmaps (CPU branch), pose_detector.py:75-110.
+ *    heat [c_plus_1,H,W] float32 (last channel = background, dropped).  peaks_out rows are
+ *    (type, x, y, score, id) float64, ordered channel-major then row-major.                 */
+int opb_peaks(opb_ctx* ctx, const float* heat, int heat_loc, int c_plus_1, int h, int w,
+              double* peaks_out, int peaks_cap, int* n_peaks);
+
+/* -- connections: replaces compute_connections + compute_candidate_connections,
+ *    pose_detector.py:135-181.  paf [38,H,W] float32; peaks [n,5] float64 (host).
+ *    conn_out rows (id_a, id_b, score) float64, limb after limb; conn_counts[19].           */
+int opb_connections(opb_ctx* ctx, const float* paf, int paf_loc, int h, int w, const double* peaks,
+                    int n_peaks, double img_len, double* conn_out, int conn_cap, int* conn_counts);
+
+/* -- grouping: replaces grouping_key_points, pose_detector.py:183-250.
+ *    subsets_out rows of 20 float64 (18 ids, score, count).                                  */
+int opb_group(opb_ctx* ctx, const double* conns, const int* conn_counts, const double* peaks,
+              int n_peaks, double* subsets_out, int subsets_cap, int* n_subsets);
+
+/* -- fused device-resident batch path: PoseDetector.__call__ for a batch, pose_detector.py
+ *    :493-517 minus the host resize.  imgs [N,H,W,3] uint8 BGR at network-input size.
+ *    Runs conv chain -> bilinear upsample to (map_h,map_w) -> peaks -> connections ->
+ *    grouping entirely on the device.  headers_out [N], persons_out [N*max_persons]
+ *    (host or device per out_loc).  If inject_paf / inject_heat are non-NULL they are
+ *    device arrays [N,38,H/8,W/8] / [N,19,H/8,W/8] that REPLACE the network output before
+ *    the upsample (the conv chain still runs); used with synthetic 8-person maps because
+ *    random weights cannot produce people.                                    */
+int opb_detect_batch(opb_ctx* ctx, const uint8_t* imgs, int imgs_loc, int n, int h, int w, int map_h,
+                     int map_w, double img_len, const float* inject_paf, const float* inject_heat,
+                     opb_image_header* headers_out, opb_person* persons_out, int out_loc);
+
+/* device pointers of the last opb_detect_batch outputs/intermediates (valid until the next
+ * call with a different shape): 0 paf_lo, 1 heat_lo, 2 pafs (full-res), 3 heatmaps (full-res),
+ * 4 headers, 5 persons, 6 peak table ([N,max_peaks] of {int32 type,x,y; float score})       */
+void* opb_device_buffer(opb_ctx* ctx, int which);
+
+/* Detail of image `img` of the last opb_detect_batch / opb_precise_finish: the peak table
+ * ([n,5] float64 rows type,x,y,score,id), the 19 connection lists and the kept subsets
+ * ([P,20] float64), i.e. the reference's all_peaks / all_connections / subsets.  Any output
+ * pointer may be NULL.                                                                       */
+int opb_get_image_detail(opb_ctx* ctx, int img, double* peaks_out, int peaks_cap, int* n_peaks,
+                         double* conn_out, int conn_cap, int* conn_counts, double* subsets_out,
+                         int subsets_cap, int* n_subsets);
+
+/* -- multi-scale precise path: replaces detect_precise, pose_detector.py:433-482 -------------
+ * begin: allocate/zero the [38|19, orig_h, orig_w] accumulators.
+ * add_scale: padded uint8 BGR image [ph,pw,3] (already resized by the host with
+ *   cv2.INTER_CUBIC and padded, :443-445) -> forward -> cubic x8 -> crop pad -> cubic to
+ *   (orig_h, orig_w) -> accumulate; the last scale also divides by n_scales (:461-470).
+ * finish: peaks -> connections -> grouping on the averaged maps (:475-481).                  */
+int opb_precise_begin(opb_ctx* ctx, int orig_h, int orig_w);
+int opb_precise_add_scale(opb_ctx* ctx, const uint8_t* img, int img_loc, int ph, int pw, int pad_h,
+                          int pad_w, int scale_index, int n_scales);
+int opb_precise_finish(opb_ctx* ctx, double img_len, opb_image_header* header_out,
+                       opb_person* persons_out, int out_loc);
+/* copies the full-resolution maps of image 0 of the current post-process workspace
+ * (self.pafs / self.heatmaps of the precise path, :469-470) to the caller.                    */
+int opb_download_maps(opb_ctx* ctx, float* pafs_out, float* heat_out, int out_loc);
+
+/* -- instrumentation ---------------------------------------------------------------------- */
+/* number of kernels launched by this context since creation (bench.py's gpu_launches)      */
+int64_t opb_launch_count(const opb_ctx* ctx);
+/* Times `reps` launches of one named stage of the cached pipeline of the last
+ * opb_detect_batch / opb_forward shape with CUDA events on the context's stream; returns the
+ * mean milliseconds per launch in *ms.  stage: "conv7x7" (the Mconv2..5 grouped launch),
+ * "conv_chain", "upsample_paf", "peaks", "paf_integral", ...                                 */
+int opb_time_stage(opb_ctx* ctx, const char* stage, int reps, float* ms);
+
+/* -- test hooks (tests/ only) ---------------------------------------------------------------
+ * single conv layer through the tcgen05 kernel: x [N,H,W,Cin] fp32 host, W [Cout,Cin,k,k],
+ * b [Cout] -> y [N,H,W,Cout] fp32 host (activations are converted to fp16 / split-fp16 on the
+ * device exactly as in the chain).                                                           */
+int opb_test_conv(opb_ctx* ctx, const float* x, int n, int h, int w, int cin, const float* W,
+                  const float* b, int cout, int ksize, int relu, int precision_mode, float* y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPB_H_ */

@@ -1,0 +1,100 @@
+"""`not gpu`: the C-ABI library loads and exports every symbol include/opb.h declares; the
+POD structs of the Python binding have the sizes the header documents; constructing the
+product without a GPU fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, pkg
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "opb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(opb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    native = pkg("_native")
+    if not os.path.isfile(native.LIB_PATH):
+        pkg("_build").build_native()
+    lib = native.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libopb.so does not export " + name
+    assert sorted(native.exported_symbols()) == declared
+    assert lib.opb_version() == 1
+
+
+def test_struct_sizes_match_header():
+    native = pkg("_native")
+    assert native.PERSON_DTYPE.itemsize == 240
+    assert native.HEADER_DTYPE.itemsize == 16
+    # limbs 152 + 6 doubles 48 + 4 ints 16 + taps 512 + 4 ints 16
+    assert ctypes.sizeof(native.OpbParams) == 19 * 2 * 4 + 6 * 8 + 4 * 4 + 64 * 8 + 4 * 4
+
+
+def test_params_struct_matches_entity_and_scipy_taps():
+    from scipy.ndimage._filters import _gaussian_kernel1d
+    p = pkg("pose_detector").make_opb_params()
+    ent = pkg("entity")
+    assert [[p.limbs[i][0], p.limbs[i][1]] for i in range(19)] == [[int(a), int(b)] for a, b in ent.params["limbs_point"]]
+    assert p.gauss_radius == 10
+    assert np.array_equal(np.array(p.gauss_taps[:21]), _gaussian_kernel1d(2.5, 0, 10))
+    assert (p.heatmap_peak_thresh, p.inner_product_thresh, p.n_integ_points, p.n_integ_points_thresh) == (0.05, 0.05, 10, 8)
+
+
+def test_entity_matches_reference_values():
+    """entity.params / JointType carry the reference's values (entity.py:9-46,71-105)."""
+    from oracle import restate as R
+    ent = pkg("entity")
+    assert tuple((int(a), int(b)) for a, b in ent.params["limbs_point"]) == R.LIMBS
+    assert len(ent.JointType) == 18 and ent.JointType.Nose == 0 and ent.JointType.LeftEar == 17
+    for k, v in dict(inference_img_size=368, heatmap_size=320, gaussian_sigma=2.5, n_integ_points=10,
+                     n_integ_points_thresh=8, heatmap_peak_thresh=0.05, inner_product_thresh=0.05,
+                     limb_length_ratio=1.0, length_penalty_value=1, n_subset_limbs_thresh=3,
+                     subset_score_thresh=0.2, downscale=8).items():
+        assert ent.params[k] == v
+    assert ent.params["inference_scales"] == [0.5, 1, 1.5, 2]
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback|no CUDA device"):
+        pkg("pose_detector").PoseDetector("posenet", None)
+
+
+def test_host_helpers_match_oracle():
+    """compute_optimal_size / pad_image / preprocess are host NumPy in both worlds."""
+    from oracle import restate as R
+    PD = pkg("pose_detector").PoseDetector
+    det = PD.__new__(PD)          # no engine needed for the host helpers
+    rs = np.random.RandomState(0)
+    for h, w in ((368, 656), (480, 640), (584, 584), (640, 480), (333, 517), (1080, 1920), (100, 37)):
+        img = rs.randint(0, 255, (h, w, 3)).astype(np.uint8)
+        for size in (368, 320):
+            assert det.compute_optimal_size(img, size) == R.compute_optimal_size(img, size)
+        a, pa = det.pad_image(img, 8, (104, 117, 123))
+        b, pb = R.pad_image(img, 8, (104, 117, 123))
+        assert np.array_equal(a, b) and list(pa) == list(pb)
+        assert np.array_equal(det.preprocess(img), R.preprocess(img))
+
+
+def test_pose_array_and_unit_length_helpers():
+    from oracle import restate as R
+    PD = pkg("pose_detector").PoseDetector
+    det = PD.__new__(PD)
+    peaks = np.zeros((40, 5)); peaks[:, 1] = np.arange(40) * 3.5; peaks[:, 2] = np.arange(40) * 2.0 + 1
+    subsets = -np.ones((2, 20)); subsets[0, :5] = [3, 7, 9, 11, 30]; subsets[1, 10:14] = [1, 2, 4, 39]
+    assert np.array_equal(det.subsets_to_pose_array(subsets, peaks), R.subsets_to_pose_array(subsets, peaks))
+    assert det.subsets_to_pose_array(subsets[:0], peaks).shape == (0,)
+    pose = det.subsets_to_pose_array(subsets, peaks)[0]
+    joints = [j if j[2] > 0 else None for j in pose]
+    lens, limbs = det.compute_limbs_length(joints)
+    assert lens.shape == (19,) and det.compute_unit_length(lens) > 0

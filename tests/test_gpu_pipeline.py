@@ -1,0 +1,182 @@
+"""`-m gpu`: end-to-end parity of the device pipeline against the committed goldens (outputs of
+the reference's own files run verbatim, oracle/make_goldens.py) on identical seeded weights.
+
+Float maps: |device - oracle| <= 1e-3 (north_star tolerance; parity mode is expected ~3e-5).
+Keypoints: the peak / person sets must be identical.  Because the conv output differs from
+the fp32 oracle by ~1e-5, a peak whose decision margin in the oracle is itself below that
+noise can legitimately flip; such near-ties are identified FROM THE ORACLE MAPS (margin <
+TIE_EPS) and excluded from the identity check -- the count of excluded peaks is asserted to
+be tiny.  Kernel-level bit-exactness on identical inputs is in test_gpu_postprocess.py."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, pkg, split_conns
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+
+MAP_TOL = 1e-3
+TIE_EPS = 2e-4
+
+
+@pytest.fixture(scope="module")
+def weights_model():
+    m = pkg("models.CocoPoseNet").CocoPoseNet()
+    m.load_npz(pkg("synthetic").he_weights(0))
+    return m
+
+
+@pytest.fixture(scope="module")
+def det_parity(weights_model):
+    return pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="parity",
+                                             max_candidates=131072)
+
+
+def _oracle_margins(heat):
+    """Per-pixel decision margin of the oracle's peak test on the smoothed maps."""
+    g = R.gaussian_smooth(heat[:-1].astype(np.float32)).astype(np.float64)
+    pad = np.pad(g, ((0, 0), (1, 1), (1, 1)))
+    nb = np.maximum.reduce([pad[:, :-2, 1:-1], pad[:, 2:, 1:-1], pad[:, 1:-1, :-2], pad[:, 1:-1, 2:]])
+    return np.minimum(g - R.HEATMAP_PEAK_THRESH, g - nb)
+
+
+def _peak_sets_match(got_peaks, ref_peaks, heat_oracle):
+    margin = _oracle_margins(heat_oracle)
+    key = lambda p: set(map(tuple, p[:, :3].astype(int))) if len(p) else set()
+    G, Rf = key(got_peaks), key(ref_peaks)
+    sym = G ^ Rf
+    for (c, x, y) in sym:
+        assert abs(margin[c, y, x]) < TIE_EPS, "peak (%d,%d,%d) differs with oracle margin %.3e" % (
+            c, x, y, margin[c, y, x])
+    return len(sym)
+
+
+def test_forward_maps_parity_mode(det_parity):
+    g = load_golden("fast_584_he0.npz")
+    img = pkg("synthetic").procedural_image(584, 584, seed=1)
+    import cv2
+    x = det_parity.preprocess(cv2.resize(img, (368, 368)))
+    paf, heat = det_parity.engine.forward(x)
+    e1, e2 = np.abs(paf[0] - g["paf_lo_0"]).max(), np.abs(heat[0] - g["heat_lo_0"]).max()
+    print("parity-mode max abs err: paf %.3e heat %.3e" % (e1, e2))
+    assert e1 <= MAP_TOL and e2 <= MAP_TOL
+    # uint8 entry (preprocess fused into conv1_1) gives the same maps
+    paf_u8, heat_u8 = det_parity.engine.forward(cv2.resize(img, (368, 368))[None])
+    assert np.abs(paf_u8 - paf).max() <= 1e-5 and np.abs(heat_u8 - heat).max() <= 1e-5
+
+
+def test_forward_maps_fast_mode(weights_model):
+    det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="fast")
+    g = load_golden("fast_584_he0.npz")
+    import cv2
+    img = pkg("synthetic").procedural_image(584, 584, seed=1)
+    paf, heat = det.engine.forward(cv2.resize(img, (368, 368))[None])
+    e1, e2 = np.abs(paf[0] - g["paf_lo_0"]).max(), np.abs(heat[0] - g["heat_lo_0"]).max()
+    print("fast-mode (fp16) max abs err: paf %.3e heat %.3e" % (e1, e2))
+    assert e1 <= 5e-2 and e2 <= 5e-2   # reported, not a parity claim (~5e-3 expected)
+
+
+def _check_call(det, name, img):
+    g = load_golden(name)
+    poses, scores = det(img)
+    if g["all_peaks"].shape[0] == 0:
+        assert poses.shape == (0, 18, 3) and scores.shape == (0,)
+        return
+    oh, ow = img.shape[:2]
+    in_w, in_h = R.compute_optimal_size(img, 368)
+    map_w, map_h = R.compute_optimal_size(img, 320)
+    heat_or = R.resize_bilinear_align_corners(g["heat_lo_0"][None], (map_h, map_w))[0]
+    peaks, conns, subsets = det.engine.image_detail(0)
+    n_ties = _peak_sets_match(peaks, g["all_peaks"], heat_or)
+    print(name, "peaks", len(peaks), "ref", len(g["all_peaks"]), "near-tie flips", n_ties)
+    assert n_ties <= max(2, len(g["all_peaks"]) // 500)
+    if n_ties == 0:
+        assert np.array_equal(peaks[:, :3], g["all_peaks"][:, :3])
+        assert np.abs(peaks[:, 3] - g["all_peaks"][:, 3]).max() <= MAP_TOL
+        ref_conns = split_conns(g["conn_lens"], g["conn_flat"])
+        same_conn = all(a.shape == b.shape and np.array_equal(a[:, :2], b[:, :2]) for a, b in zip(conns, ref_conns))
+        # connection acceptance thresholds (ip > 0.05, score > 0) have their own measure-zero ties
+        if same_conn:
+            assert subsets.shape == g["subsets"].shape
+            assert np.array_equal(subsets[:, :18], g["subsets"][:, :18])
+            assert np.abs(subsets[:, 18:] - g["subsets"][:, 18:]).max() <= 1e-2
+            assert poses.shape == g["poses"].shape and np.array_equal(poses, g["poses"])      # OKS = 1.0
+            assert np.abs(scores - g["scores"]).max() <= 1e-2
+        else:
+            n_diff = sum(0 if (a.shape == b.shape and np.array_equal(a[:, :2], b[:, :2])) else 1
+                         for a, b in zip(conns, ref_conns))
+            print("connection lists differ on", n_diff, "limbs (threshold near-ties)")
+            assert n_diff <= 2
+
+
+def test_call_fast_path_584(det_parity):
+    _check_call(det_parity, "fast_584_he0.npz", pkg("synthetic").procedural_image(584, 584, seed=1))
+
+
+def test_call_fast_path_webcam_shape(det_parity):
+    _check_call(det_parity, "fast_480x640_he0.npz", pkg("synthetic").procedural_image(480, 640, seed=2))
+
+
+def test_call_fast_path_dense_noise(det_parity):
+    _check_call(det_parity, "fast_368x656_he0_img0.npz", pkg("synthetic").random_images(2, 368, 656, seed=0)[0])
+
+
+def test_call_default_init_returns_empty():
+    m = pkg("models.CocoPoseNet").CocoPoseNet()
+    m.load_npz(pkg("synthetic").he_weights(0, bias_scale=0.0, gain=1.0))
+    det = pkg("pose_detector").PoseDetector(model=m, device=0)
+    poses, scores = det(pkg("synthetic").procedural_image(584, 584, seed=1))
+    assert poses.shape == (0, 18, 3) and scores.shape == (0,)
+
+
+def test_detect_batch_matches_single_calls(det_parity):
+    imgs = pkg("synthetic").random_images(2, 368, 656, seed=0)
+    res = det_parity.detect_batch(imgs)
+    for i in range(2):
+        g = load_golden("fast_368x656_he0_img%d.npz" % i)
+        poses, scores = res[i]
+        single = det_parity(imgs[i])
+        assert poses.shape == single[0].shape and np.array_equal(poses, single[0])
+        assert abs(len(poses) - len(g["poses"])) <= 3
+
+
+def test_injected_synthetic_eight_person_maps(det_parity):
+    """Config #3: synthetic 8-person maps injected as the network output (the conv chain still
+    runs); 8 persons must come out for every image of the batch, identical to the oracle run
+    on the same low-resolution maps."""
+    import torch
+    syn = pkg("synthetic")
+    paf_lo, heat_lo = syn.eight_person_lowres(46, 82, seed=0)
+    imgs = syn.random_images(2, 368, 656, seed=5)
+    n = len(imgs)
+    d_paf = torch.from_numpy(np.repeat(paf_lo[None], n, 0)).cuda()
+    d_heat = torch.from_numpy(np.repeat(heat_lo[None], n, 0)).cuda()
+    torch.cuda.synchronize()
+    headers, persons = det_parity.engine.detect_batch(imgs, 320, 576, inject_paf=d_paf.data_ptr(),
+                                                      inject_heat=d_heat.data_ptr())
+    pafs = R.resize_bilinear_align_corners(paf_lo[None], (320, 576))[0]
+    heat = R.resize_bilinear_align_corners(heat_lo[None], (320, 576))[0]
+    ref_poses, ref_scores, parts = R.postprocess_fast(pafs, heat, 576, 576, 320, 320, return_parts=True)
+    for i in range(n):
+        assert headers[i]["status"] == 0 and headers[i]["n_persons"] == len(ref_scores) == 8
+        peaks, conns, subsets = det_parity.engine.image_detail(i)
+        assert np.array_equal(peaks, parts["all_peaks"])
+        assert np.array_equal(subsets, parts["subsets"])
+
+
+def test_precise_path_480(weights_model):
+    det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precise=True, precision="parity",
+                                            max_candidates=131072)
+    g = load_golden("precise_480_he0.npz")
+    img = pkg("synthetic").procedural_image(480, 480, seed=3)
+    poses, scores = det(img)
+    e1 = np.abs(det.pafs[:, ::7, ::7] - g["pafs_sample"]).max()
+    e2 = np.abs(det.heatmaps[:, ::7, ::7] - g["heatmaps_sample"]).max()
+    print("precise maps max abs err: paf %.3e heat %.3e; peaks %d ref %d" % (e1, e2, len(det.all_peaks),
+                                                                            len(g["all_peaks"])))
+    assert e1 <= MAP_TOL and e2 <= MAP_TOL
+    G = set(map(tuple, det.all_peaks[:, :3].astype(int)))
+    Rf = set(map(tuple, g["all_peaks"][:, :3].astype(int)))
+    assert len(G ^ Rf) <= max(2, len(Rf) // 500)
+    if G == Rf and poses.shape == g["poses"].shape:
+        assert np.array_equal(poses, g["poses"])       # OKS = 1.0 vs the reference

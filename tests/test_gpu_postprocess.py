@@ -1,0 +1,190 @@
+"""`-m gpu`: kernel-level parity of the post-process -- every CUDA stage is fed the ORACLE's own
+input arrays and must reproduce the reference bit-for-bit: peak ids / integer coordinates,
+connection lists, subset membership; float64 scores exactly (same operation order) or to
+1e-12 relative where noted.  All calls go through the C ABI (libopb.so via ctypes)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, pkg, split_conns
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    native = pkg("_native")
+    prm = pkg("pose_detector").make_opb_params(max_peaks=8192, max_candidates=131072, max_persons=1024)
+    return native.Engine(0, prm)
+
+
+def test_upsample_bilinear_bit_exact(engine):
+    rs = np.random.RandomState(0)
+    for (h, w, H, W) in ((46, 82, 320, 576), (46, 46, 320, 320), (46, 62, 320, 432), (23, 31, 57, 64), (2, 2, 9, 5)):
+        x = (rs.standard_normal((3, 7, h, w)) * rs.uniform(0.1, 2)).astype(np.float32)
+        got = engine.upsample(x, H, W)
+        ref = R.resize_bilinear_align_corners(x, (H, W))
+        assert np.array_equal(got, ref), (h, w, H, W, np.abs(got - ref).max())
+
+
+def _peaks_case(engine, heat):
+    got = engine.peaks(heat)
+    ref = R.compute_peaks_from_heatmaps(heat)
+    ref = ref.reshape(-1, 5)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)
+    return got
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_peaks_synth8_vs_golden(engine, seed):
+    g = load_golden("synth8_post_seed%d.npz" % seed)
+    paf, heat, _ = pkg("synthetic").eight_person_maps(seed=seed)
+    got = engine.peaks(heat)
+    assert np.array_equal(got, g["all_peaks"])
+
+
+def test_peaks_random_maps_and_edges(engine):
+    rs = np.random.RandomState(3)
+    # noise maps of awkward sizes: tile borders, reflect padding longer than the image
+    for (h, w) in ((320, 576), (37, 53), (16, 64), (17, 65), (9, 7), (130, 21)):
+        heat = (rs.standard_normal((19, h, w)) * 0.3).astype(np.float32)
+        _peaks_case(engine, heat)
+    # exact plateaus produce no peak (strict >), constant maps, all-below-threshold maps
+    heat = np.zeros((19, 40, 40), np.float32)
+    assert len(engine.peaks(heat)) == 0
+    heat[:] = 1.0
+    _peaks_case(engine, heat)
+    heat = np.zeros((19, 40, 40), np.float32)
+    heat[3, 20, 20] = 5.0   # one blob -> exactly one peak of type 3 at (20, 20)
+    got = _peaks_case(engine, heat)
+    assert got.shape == (1, 5) and tuple(got[0, :3]) == (3.0, 20.0, 20.0)
+    heat[3, 0, 0] = 9.0     # corner peak: zero-filled neighbours outside the image
+    _peaks_case(engine, heat)
+
+
+def test_peaks_on_oracle_upsampled_network_maps(engine):
+    g = load_golden("fast_584_he0.npz")
+    heat = R.resize_bilinear_align_corners(g["heat_lo_0"][None], (320, 320))[0]
+    got = engine.peaks(heat)
+    assert np.array_equal(got, g["all_peaks"])
+
+
+def _check_conns(got, ref, exact_scores=True):
+    assert len(got) == 19
+    for l, (a, b) in enumerate(zip(got, ref)):
+        b = np.asarray(b).reshape(-1, 3)
+        assert a.shape == b.shape, (l, a.shape, b.shape)
+        assert np.array_equal(a[:, :2], b[:, :2]), l
+        if exact_scores:
+            assert np.array_equal(a[:, 2], b[:, 2]), (l, np.abs(a[:, 2] - b[:, 2]).max())
+        else:
+            assert np.allclose(a[:, 2], b[:, 2], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_connections_and_grouping_synth8(engine, seed):
+    g = load_golden("synth8_post_seed%d.npz" % seed)
+    paf, heat, _ = pkg("synthetic").eight_person_maps(seed=seed)
+    conns = engine.connections(paf, g["all_peaks"], 576)
+    _check_conns(conns, split_conns(g["conn_lens"], g["conn_flat"]))
+    subsets = engine.group(conns, g["all_peaks"])
+    assert np.array_equal(subsets, g["subsets"])
+    assert len(subsets) == 8
+
+
+def test_connections_dense_noise_frame(engine):
+    """~5 800 peaks, 2.1 M candidate pairs, up to 102 k accepted candidates per limb."""
+    g = load_golden("fast_368x656_he0_img0.npz")
+    paf = R.resize_bilinear_align_corners(g["paf_lo_0"][None], (320, 576))[0]
+    conns = engine.connections(paf, g["all_peaks"], 576)
+    _check_conns(conns, split_conns(g["conn_lens"], g["conn_flat"]))
+    subsets = engine.group(conns, g["all_peaks"])
+    assert np.array_equal(subsets, g["subsets"])
+
+
+def test_connections_webcam_shape(engine):
+    g = load_golden("fast_480x640_he0.npz")
+    paf = R.resize_bilinear_align_corners(g["paf_lo_0"][None], (320, 432))[0]
+    conns = engine.connections(paf, g["all_peaks"], float(g["img_len"]))
+    _check_conns(conns, split_conns(g["conn_lens"], g["conn_flat"]))
+    assert np.array_equal(engine.group(conns, g["all_peaks"]), g["subsets"])
+
+
+def test_connections_empty_and_degenerate(engine):
+    paf = np.zeros((38, 64, 64), np.float32)
+    # no peaks at all
+    conns = engine.connections(paf, np.zeros((0, 5)), 64)
+    assert all(c.shape == (0, 3) for c in conns)
+    assert engine.group(conns, np.zeros((0, 5))).shape == (0, 20)
+    # coincident peaks (norm == 0 is skipped, pose_detector.py:141) and a type with no partner
+    peaks = np.array([[1, 10, 10, 0.9, 0], [8, 10, 10, 0.8, 1], [8, 30, 10, 0.7, 2], [4, 5, 5, 0.5, 3]], np.float64)
+    paf[0] = 1.0   # limb 0 = (1 -> 8), x component
+    ref = R.compute_connections(paf, peaks, 64)
+    _check_conns(engine.connections(paf, peaks, 64), ref)
+
+
+def test_grouping_quirks_random_graphs(engine):
+    """Random connection lists exercise the merge (count += score quirk, :217), the
+    two-subset non-merge branch and np.delete reordering; compare with the oracle exactly."""
+    rs = np.random.RandomState(7)
+    for trial in range(30):
+        n_per_type = rs.randint(1, 6)
+        types = np.repeat(np.arange(18), n_per_type)
+        n = len(types)
+        peaks = np.zeros((n, 5))
+        peaks[:, 0] = types
+        peaks[:, 1] = rs.randint(0, 300, n)
+        peaks[:, 2] = rs.randint(0, 300, n)
+        peaks[:, 3] = rs.uniform(0.06, 1.0, n).astype(np.float32)
+        peaks[:, 4] = np.arange(n)
+        conns = []
+        for (ja, jb) in R.LIMBS:
+            ia = np.nonzero(types == ja)[0]; ib = np.nonzero(types == jb)[0]
+            k = rs.randint(0, min(len(ia), len(ib)) + 1)
+            a = rs.permutation(ia)[:k]; b = rs.permutation(ib)[:k]
+            sc = np.sort(rs.uniform(0.05, 1.2, k))[::-1]
+            conns.append(np.stack([a, b, sc], axis=1).reshape(-1, 3))
+        try:
+            ref = R.grouping_key_points(conns, peaks)
+        except IndexError:
+            with pytest.raises(IndexError):
+                engine.group(conns, peaks)
+            continue
+        got = engine.group(conns, peaks)
+        assert np.array_equal(got, ref), trial
+
+
+def test_grouping_third_match_raises_index_error(engine):
+    # three different subsets claim the ends of one connection -> the reference raises IndexError (:197)
+    peaks = np.zeros((12, 5)); peaks[:, 4] = np.arange(12); peaks[:, 3] = 1.0
+    peaks[:, 0] = [1, 8, 1, 8, 1, 11, 2, 16, 5, 17, 0, 0]
+    conns = [np.zeros((0, 3)) for _ in range(19)]
+    conns[0] = np.array([[0., 1., 1.], [2., 3., 1.]])   # limb 0 (1->8): subsets A(neck0), B(neck2)
+    conns[3] = np.array([[4., 5., 1.]])                 # limb 3 (1->11): subset C(neck4)
+    # limb 6 (1->2): neck 0 -> shoulder 6 extends A; limb 9 (2->16) cannot create
+    conns[6] = np.array([[0., 6., 1.]])
+    # make B and C also hold shoulder 6 / ... craft: limb 10 (1->5): necks 2,4 share shoulder 8?  not allowed (unique b)
+    # direct construction: put the same right-shoulder id into three subsets through limb 6 with duplicate b ids
+    conns[6] = np.array([[0., 6., 1.], [2., 6., 0.9], [4., 6., 0.8]])
+    conns[7] = np.array([[6., 9., 1.]])                 # limb 7 (2->3): joint_a=2 id 6 is in A, B and C
+    with pytest.raises(IndexError):
+        R.grouping_key_points(conns, peaks)
+    with pytest.raises(IndexError):
+        engine.group(conns, peaks)
+
+
+def test_public_stage_methods_chain(engine):
+    """The reference-facing methods on PoseDetector reproduce the oracle's intermediate arrays."""
+    PD = pkg("pose_detector")
+    det = PD.PoseDetector.__new__(PD.PoseDetector)
+    det.engine = engine
+    paf, heat, _ = pkg("synthetic").eight_person_maps(seed=0)
+    g = load_golden("synth8_post_seed0.npz")
+    peaks = det.compute_peaks_from_heatmaps(heat)
+    conns = det.compute_connections(paf, peaks, 576, PD.params)
+    subsets = det.grouping_key_points(conns, peaks, PD.params)
+    poses = det.subsets_to_pose_array(subsets, peaks)
+    assert np.array_equal(peaks, g["all_peaks"]) and np.array_equal(subsets, g["subsets"])
+    assert np.array_equal(poses, g["poses"])
+    assert det.compute_peaks_from_heatmaps(np.zeros((19, 32, 32), np.float32)).shape == (0,)

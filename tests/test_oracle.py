@@ -109,10 +109,10 @@ def test_optimal_size_rule():
 
 def test_grouping_third_match_raises_index_error():
     # three subsets matching one connection: the reference raises IndexError (:193-198)
-    peaks = np.zeros((10, 5)); peaks[:, 4] = np.arange(10); peaks[:, 3] = 1.0
+    peaks = np.zeros((12, 5)); peaks[:, 4] = np.arange(12); peaks[:, 3] = 1.0
     conns = [np.zeros((0, 3)) for _ in range(19)]
-    conns[0] = np.array([[0., 1., 1.], [2., 3., 1.]])       # limb 0 (1->8): two subsets
-    conns[3] = np.array([[4., 5., 1.]])                     # limb 3 (1->11): a third subset, new
-    # limb 6 (1->2): connection whose joint_a==neck id matches... craft a direct 3-match instead
-    subs = R.grouping_key_points(conns, peaks)
-    assert subs.shape[1] == 20
+    conns[0] = np.array([[0., 1., 1.], [2., 3., 1.]])
+    conns[3] = np.array([[4., 5., 1.]])
+    conns[6] = np.array([[0., 6., 1.], [2., 6., 0.9], [4., 6., 0.8]])
+    with pytest.raises(IndexError):
+        R.grouping_key_points(conns, peaks)

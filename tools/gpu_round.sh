@@ -1,0 +1,22 @@
+#!/bin/bash
+# One GPU-box session: build check, probes, tests, bench.  Everything is logged to gpurun_out/.
+# usage: tools/gpu_round.sh [stage ...]   stages: probe post conv pipe smoke bench ncu
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+STAGES="${*:-probe post conv pipe smoke bench}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+for s in $STAGES; do
+  echo "=== stage $s $(date +%T)"
+  case $s in
+    probe) timeout 900 python tools/conv_probe.py > gpurun_out/probe.log 2>&1; tail -n 60 gpurun_out/probe.log ;;
+    post)  timeout 900 python -m pytest tests/test_gpu_postprocess.py -m gpu -q --timeout 600 > gpurun_out/post.log 2>&1; tail -n 30 gpurun_out/post.log ;;
+    conv)  timeout 900 python -m pytest tests/test_gpu_conv.py -m gpu -q --timeout 300 > gpurun_out/conv.log 2>&1; tail -n 30 gpurun_out/conv.log ;;
+    pipe)  timeout 1500 python -m pytest tests/test_gpu_pipeline.py -m gpu -q -s --timeout 900 > gpurun_out/pipe.log 2>&1; tail -n 40 gpurun_out/pipe.log ;;
+    smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -n 5 gpurun_out/smoke.log ;;
+    bench) timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; tail -n 3 gpurun_out/bench.log ;;
+    benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -n 2 gpurun_out/bench_ref.log ;;
+    ncu)   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -n 3 gpurun_out/ncu_bench.log ;;
+  esac
+done
+echo "=== done $(date +%T)"
