@@ -60,6 +60,7 @@ struct Op {
   std::string tag;
   // OP_CONV
   int ks = 0, bn = 0, mt = 1;
+  bool drain = false;
   CUtensorMap tmA[2], tmB[2];
   ConvParams P;
   int grid = 0;
@@ -190,10 +191,10 @@ int make_w_map(opb_ctx* ctx, CUtensorMap* tm, const PackedW& w, int bn) {
 }
 
 // ------------------------------------------------------------------ conv launch
-template <int KS, int BN, int MT, int NSA, int NSB, int ACC>
+template <int KS, int BN, int MT, int NSA, int NSB, int ACC, bool DRAIN = false>
 int launch_conv_t(opb_ctx* ctx, const Op& op) {
   using Cfg = ConvCfg<KS, BN, MT, NSA, NSB, ACC>;
-  auto kern = conv_tcgen05_kernel<KS, BN, MT, NSA, NSB, ACC>;
+  auto kern = conv_tcgen05_kernel<KS, BN, MT, NSA, NSB, ACC, DRAIN>;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     OPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -207,6 +208,20 @@ int launch_conv_t(opb_ctx* ctx, const Op& op) {
 
 int launch_conv(opb_ctx* ctx, const Op& op) {
   const int key = op.ks * 10000 + op.bn * 10 + op.mt;
+  if (op.drain) {   // parity precision: two-level accumulation variants (BN <= 128, MT = 1)
+    switch (key) {
+      case 7 * 10000 + 128 * 10 + 1: return launch_conv_t<7, 128, 1, 3, 6, 2, true>(ctx, op);
+      case 7 * 10000 + 64 * 10 + 1: return launch_conv_t<7, 64, 1, 3, 6, 2, true>(ctx, op);
+      case 7 * 10000 + 48 * 10 + 1: return launch_conv_t<7, 48, 1, 3, 6, 2, true>(ctx, op);
+      case 3 * 10000 + 128 * 10 + 1: return launch_conv_t<3, 128, 1, 3, 6, 2, true>(ctx, op);
+      case 3 * 10000 + 64 * 10 + 1: return launch_conv_t<3, 64, 1, 3, 6, 2, true>(ctx, op);
+      case 3 * 10000 + 48 * 10 + 1: return launch_conv_t<3, 48, 1, 3, 6, 2, true>(ctx, op);
+      case 1 * 10000 + 128 * 10 + 1: return launch_conv_t<1, 128, 1, 4, 6, 2, true>(ctx, op);
+      case 1 * 10000 + 64 * 10 + 1: return launch_conv_t<1, 64, 1, 4, 6, 2, true>(ctx, op);
+      case 1 * 10000 + 48 * 10 + 1: return launch_conv_t<1, 48, 1, 4, 6, 2, true>(ctx, op);
+      default: OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "no drain-mode conv variant for key " + std::to_string(key));
+    }
+  }
   switch (key) {
     case 7 * 10000 + 128 * 10 + 1: return launch_conv_t<7, 128, 1, 3, 6, 2>(ctx, op);
     case 7 * 10000 + 128 * 10 + 2: return launch_conv_t<7, 128, 2, 3, 5, 2>(ctx, op);
@@ -324,7 +339,8 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
   const bool split = ctx->precision == OPB_PRECISION_PARITY;
   op.ks = w0.ks;
   const int per_problem_cout_pad = w0.cout_pad;
-  op.bn = std::min(per_problem_cout_pad, 256);
+  op.drain = split;
+  op.bn = std::min(per_problem_cout_pad, split ? 128 : 256);
   op.mt = 1;
   const Act& a0 = *s.in[0];
   if (a0.H < 16 + op.ks - 1 || a0.W < 8)

@@ -16,7 +16,7 @@ from oracle import restate as R
 pytestmark = pytest.mark.gpu
 
 MAP_TOL = 1e-3
-TIE_EPS = 2e-4
+TIE_FACTOR = 4.0      # a peak may flip only if its oracle margin is below TIE_FACTOR x the measured map error
 
 
 @pytest.fixture(scope="module")
@@ -29,7 +29,7 @@ def weights_model():
 @pytest.fixture(scope="module")
 def det_parity(weights_model):
     return pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="parity",
-                                             max_candidates=131072)
+                                             max_candidates=131072, max_persons=4096)
 
 
 def _oracle_margins(heat):
@@ -40,14 +40,14 @@ def _oracle_margins(heat):
     return np.minimum(g - R.HEATMAP_PEAK_THRESH, g - nb)
 
 
-def _peak_sets_match(got_peaks, ref_peaks, heat_oracle):
+def _peak_sets_match(got_peaks, ref_peaks, heat_oracle, tie_eps):
     margin = _oracle_margins(heat_oracle)
     key = lambda p: set(map(tuple, p[:, :3].astype(int))) if len(p) else set()
     G, Rf = key(got_peaks), key(ref_peaks)
     sym = G ^ Rf
     for (c, x, y) in sym:
-        assert abs(margin[c, y, x]) < TIE_EPS, "peak (%d,%d,%d) differs with oracle margin %.3e" % (
-            c, x, y, margin[c, y, x])
+        assert abs(margin[c, y, x]) < tie_eps, "peak (%d,%d,%d) differs with oracle margin %.3e (eps %.1e)" % (
+            c, x, y, margin[c, y, x], tie_eps)
     return len(sym)
 
 
@@ -87,8 +87,12 @@ def _check_call(det, name, img):
     map_w, map_h = R.compute_optimal_size(img, 320)
     heat_or = R.resize_bilinear_align_corners(g["heat_lo_0"][None], (map_h, map_w))[0]
     peaks, conns, subsets = det.engine.image_detail(0)
-    n_ties = _peak_sets_match(peaks, g["all_peaks"], heat_or)
-    print(name, "peaks", len(peaks), "ref", len(g["all_peaks"]), "near-tie flips", n_ties)
+    import cv2
+    paf_lo, heat_lo = det.engine.forward(cv2.resize(img, (in_w, in_h))[None])
+    map_err = max(np.abs(paf_lo[0] - g["paf_lo_0"]).max(), np.abs(heat_lo[0] - g["heat_lo_0"]).max())
+    assert map_err <= MAP_TOL
+    n_ties = _peak_sets_match(peaks, g["all_peaks"], heat_or, max(TIE_FACTOR * map_err, 1e-4))
+    print(name, "map err %.2e" % map_err, "peaks", len(peaks), "ref", len(g["all_peaks"]), "near-tie flips", n_ties)
     assert n_ties <= max(2, len(g["all_peaks"]) // 500)
     if n_ties == 0:
         assert np.array_equal(peaks[:, :3], g["all_peaks"][:, :3])
@@ -166,7 +170,7 @@ def test_injected_synthetic_eight_person_maps(det_parity):
 
 def test_precise_path_480(weights_model):
     det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precise=True, precision="parity",
-                                            max_candidates=131072)
+                                            max_candidates=131072, max_persons=4096)
     g = load_golden("precise_480_he0.npz")
     img = pkg("synthetic").procedural_image(480, 480, seed=3)
     poses, scores = det(img)
@@ -177,6 +181,7 @@ def test_precise_path_480(weights_model):
     assert e1 <= MAP_TOL and e2 <= MAP_TOL
     G = set(map(tuple, det.all_peaks[:, :3].astype(int)))
     Rf = set(map(tuple, g["all_peaks"][:, :3].astype(int)))
+    print("precise peak-set symmetric difference:", len(G ^ Rf))
     assert len(G ^ Rf) <= max(2, len(Rf) // 500)
     if G == Rf and poses.shape == g["poses"].shape:
         assert np.array_equal(poses, g["poses"])       # OKS = 1.0 vs the reference

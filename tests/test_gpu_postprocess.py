@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def engine():
     native = pkg("_native")
-    prm = pkg("pose_detector").make_opb_params(max_peaks=8192, max_candidates=131072, max_persons=1024)
+    prm = pkg("pose_detector").make_opb_params(max_peaks=16384, max_candidates=131072, max_persons=4096)
     return native.Engine(0, prm)
 
 
