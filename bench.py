@@ -238,19 +238,26 @@ def run_ours(args):
     # CPU baseline: the oracle port on this box's host cores, bounded sample
     cpu = None
     if not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count())
         wd = syn.he_weights(0)
         weights = {k[:-2]: (wd[k], wd[k[:-2] + "/b"]) for k in wd if k.endswith("/W")}
         fr = imgs_host[0].numpy()
-        cpu_reference_step(weights, fr, paf_lo, heat_lo)
-        n_s = 3
-        t0 = time.perf_counter()
-        for _ in range(n_s):
+        # oneDNN does not scale to every logical core of a big host: use the best of a few
+        # thread counts (each: 1 warm-up + 1 timed frame), bounded to ~30 s of CPU work
+        best, t_budget = None, time.perf_counter()
+        for nt in sorted({min(os.cpu_count(), t) for t in (16, 32, 64, os.cpu_count())}):
+            torch.set_num_threads(nt)
             cpu_reference_step(weights, fr, paf_lo, heat_lo)
-        dt = time.perf_counter() - t0
-        cpu = {"value": n_s / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "%d single frames (reference is batch-1) after 1 warm-up; torch-CPU fp32 conv + NumPy/SciPy "
-                         "post-process" % n_s}
+            t0 = time.perf_counter()
+            cpu_reference_step(weights, fr, paf_lo, heat_lo)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, nt)
+            if time.perf_counter() - t_budget > 30:
+                break
+        cpu = {"value": 1.0 / best[0], "unit": "frames/s", "cores": best[1], "kind": "port",
+               "sample": "1 timed frame after 1 warm-up per thread setting (reference is batch-1), best of the "
+                         "settings tried within 30 s; host has %d logical cores; torch-CPU fp32 conv + NumPy/SciPy "
+                         "post-process" % os.cpu_count()}
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -227,6 +227,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // ================================================================ MMA issuer
     if (lane == 0) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+      const uint64_t a_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemA), 1024);
+      const uint64_t b_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemB), 1024);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int rem = tile % m_tiles;
         rem %= (P.tiles_y * P.tiles_x);
@@ -246,21 +248,21 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               accumulate = 0;
             }
             ptx::tc_fence_after();
-            const uint32_t a_base = ptx::smem_u32(smemA + sa * Cfg::A_STAGE_BYTES);
+            // descriptors differ from the stage-0 descriptor only in the 14-bit address field
+            const uint64_t a_st = a_desc0 + static_cast<uint64_t>((sa * Cfg::A_STAGE_BYTES) >> 4);
+#pragma unroll
             for (int r = 0; r < KS; ++r) {
               ptx::mbar_wait(&b_full[sb], pb);
               ptx::tc_fence_after();
-              const uint32_t b_base = ptx::smem_u32(smemB + sb * Cfg::B_STAGE_BYTES);
+              const uint64_t b_st = b_desc0 + static_cast<uint64_t>((sb * Cfg::B_STAGE_BYTES) >> 4);
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
                 if (mt < n_sub) {
                   const uint32_t d = tmem_base + (acc * MT + mt) * BN;
+                  const uint64_t ad0 = a_st + static_cast<uint64_t>((mt * Cfg::A_SUB_BYTES + r * 1024) >> 4);
+                  ptx::mma_f16_ss(d, ad0, b_st, IDESC, accumulate);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const uint64_t ad = ptx::umma_desc_sw128(a_base + mt * Cfg::A_SUB_BYTES + r * 1024 + k * 32, 1024);
-                    const uint64_t bd = ptx::umma_desc_sw128(b_base + k * 32, 1024);
-                    ptx::mma_f16_ss(d, ad, bd, IDESC, accumulate | (uint32_t)k);
-                  }
+                  for (int k = 1; k < 4; ++k) ptx::mma_f16_ss_acc(d, ad0 + (k * 32 >> 4), b_st + (k * 32 >> 4), IDESC);
                 }
               }
               accumulate = 1;

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -78,6 +79,7 @@ struct Chain {            // everything cached for one (N, H, W)
   float* heat_lo = nullptr;  // [N][19][h][w]
   uint8_t* img_u8 = nullptr;
   float* img_f32 = nullptr;
+  const uint8_t* img_u8_src = nullptr;   // where conv1_1 reads uint8 frames (img_u8, or the caller's device buffer)
 };
 
 struct PostWs {           // post-process workspace for (N, map_h, map_w)
@@ -85,6 +87,7 @@ struct PostWs {           // post-process workspace for (N, map_h, map_w)
   float* pafs = nullptr;      // [N][38][H][W]
   float* heat = nullptr;      // [N][19][H][W]
   PeakKey* keys = nullptr;    // [N][max_peaks]
+  float* tile_max = nullptr;  // [N*18][tiles_y][tiles_x]
   int* peak_counts = nullptr; // [N]
   PeakD* peaks = nullptr;     // [N][max_peaks]
   int* idx_list = nullptr;
@@ -125,6 +128,8 @@ struct opb_ctx {
   std::map<long long, PostWs*> posts;
   PostWs* last_post = nullptr;
   int conn_cap = kAssignMaxType;
+  bool profile = false;                       // OPB_PROFILE=1: cudaEvent after every launch of a batch
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
 };
 
 namespace {
@@ -146,6 +151,35 @@ namespace {
   } while (0)
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+void prof_mark(opb_ctx* ctx, const std::string& name) {
+  if (!ctx->profile) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, ctx->stream);
+  ctx->marks.emplace_back(name, e);
+}
+
+void prof_report(opb_ctx* ctx) {
+  if (!ctx->profile || ctx->marks.size() < 2) return;
+  cudaStreamSynchronize(ctx->stream);
+  std::map<std::string, std::pair<int, float>> agg;
+  std::vector<std::string> order;
+  float total = 0.f;
+  for (size_t i = 1; i < ctx->marks.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->marks[i - 1].second, ctx->marks[i].second);
+    auto& a = agg[ctx->marks[i].first];
+    if (a.first == 0) order.push_back(ctx->marks[i].first);
+    a.first++;
+    a.second += ms;
+    total += ms;
+  }
+  fprintf(stderr, "[opb profile] total %.3f ms\n", total);
+  for (auto& k : order) fprintf(stderr, "[opb profile] %-16s n=%3d %9.3f ms %5.1f%%\n", k.c_str(), agg[k].first, agg[k].second, 100.f * agg[k].second / total);
+  for (auto& m : ctx->marks) cudaEventDestroy(m.second);
+  ctx->marks.clear();
+}
 
 template <typename T>
 int dev_alloc(opb_ctx* ctx, T** p, size_t count, std::vector<void*>& owner, bool zero = true) {
@@ -252,9 +286,9 @@ int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
     return OPB_OK;
   }
   // OP_FIRST
-  const size_t total = static_cast<size_t>(op.N) * op.H * op.W;
-  const int grid = static_cast<int>(std::min<size_t>((total + 63) / 64, static_cast<size_t>(ctx->num_sms) * 32));
-  conv_first_kernel<<<grid, 256, 0, ctx->stream>>>(ch->img_u8 && op.C == 1 ? ch->img_u8 : nullptr,
+  const int tiles = op.N * ((op.H + CF_TH - 1) / CF_TH) * ((op.W + CF_TW - 1) / CF_TW);
+  const int grid = std::min(tiles, ctx->num_sms * 8);
+  conv_first_kernel<<<grid, 256, 0, ctx->stream>>>(op.C == 1 ? (ch->img_u8_src ? ch->img_u8_src : ch->img_u8) : nullptr,
                                                    op.C == 1 ? nullptr : ch->img_f32, ctx->w_first, ctx->b_first,
                                                    op.out, op.N, op.H, op.W, op.cstride, op.lo_off);
   ctx->launches++;
@@ -342,6 +376,11 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
   op.drain = split;
   op.bn = std::min(per_problem_cout_pad, split ? 128 : 256);
   op.mt = 1;
+  {  // MT=2: two 8-column sub-tiles share every weight stage (7x7/3x3, BN=128); OPB_MT=1 disables
+    const char* e = getenv("OPB_MT");
+    const int want = e ? atoi(e) : 2;   // measured: 7x7 128->128 grouped launch 10.1 -> 7.9 ms with MT=2
+    if (want == 2 && !split && op.bn == 128 && (op.ks == 7 || op.ks == 3)) op.mt = 2;
+  }
   const Act& a0 = *s.in[0];
   if (a0.H < 16 + op.ks - 1 || a0.W < 8)
     OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "feature map smaller than one TMA box (min 22 x 8); image too small");
@@ -522,6 +561,7 @@ int run_chain(opb_ctx* ctx, Chain* ch, bool u8_input) {
     if (op.kind == OP_FIRST) op.C = u8_input ? 1 : 0;
     int rc = launch_op(ctx, ch, op);
     if (rc) return rc;
+    prof_mark(ctx, op.tag);
   }
   return OPB_OK;
 }
@@ -545,6 +585,7 @@ int get_post(opb_ctx* ctx, int n, int H, int W, PostWs** out) {
   RC(dev_alloc(ctx, &ws->pafs, static_cast<size_t>(n) * 38 * H * W, ws->allocs, false));
   RC(dev_alloc(ctx, &ws->heat, static_cast<size_t>(n) * 19 * H * W, ws->allocs, false));
   RC(dev_alloc(ctx, &ws->keys, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
+  RC(dev_alloc(ctx, &ws->tile_max, static_cast<size_t>(n) * 18 * ((H + PK_TY - 1) / PK_TY) * ((W + PK_TX - 1) / PK_TX), ws->allocs));
   RC(dev_alloc(ctx, &ws->peak_counts, n, ws->allocs));
   RC(dev_alloc(ctx, &ws->peaks, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
   RC(dev_alloc(ctx, &ws->idx_list, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
@@ -566,7 +607,7 @@ int get_post(opb_ctx* ctx, int n, int H, int W, PostWs** out) {
 }
 
 int launch_upsample(opb_ctx* ctx, const float* in, int planes, int h, int w, float* out, int H, int W) {
-  const int ppb = 8;
+  const int ppb = 19;
   dim3 grid((W + 31) / 32, (H + 7) / 8, (planes + ppb - 1) / ppb), block(32, 8);
   if (grid.z > 65535) OPB_FAIL(ctx, OPB_ERR_ARG, "too many planes");
   upsample_bilinear_ac_kernel<<<grid, block, 0, ctx->stream>>>(in, planes, h, w, out, H, W, ppb);
@@ -589,11 +630,15 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
   }
   dim3 grid((W + PK_TX - 1) / PK_TX, (H + PK_TY - 1) / PK_TY, n * c_use);
   if (grid.z > 65535) OPB_FAIL(ctx, OPB_ERR_ARG, "batch too large for the peaks grid");
+  tile_max_kernel<<<grid, 256, 0, ctx->stream>>>(heat, c_total, c_use, H, W, ws->tile_max);
+  ctx->launches++;
+  prof_mark(ctx, "tile_max");
   smooth_nms_kernel<<<grid, 256, smem, ctx->stream>>>(heat, c_total, c_use, H, W, ctx->taps,
                                                       static_cast<float>(p.heatmap_peak_thresh), ws->keys,
-                                                      ws->peak_counts, p.max_peaks);
+                                                      ws->peak_counts, p.max_peaks, ws->tile_max);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
+  prof_mark(ctx, "smooth_nms");
   int npow = 1;
   while (npow < p.max_peaks) npow <<= 1;
   const size_t smem2 = static_cast<size_t>(npow) * 8;
@@ -617,6 +662,7 @@ int launch_connections(opb_ctx* ctx, PostWs* ws, const float* pafs, int n, int H
                                                      p.max_candidates);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
+  prof_mark(ctx, "paf_candidates");
   dim3 g2(19, n);
   limb_assign_kernel<<<g2, 256, 0, ctx->stream>>>(ws->peaks, ws->idx_list, ws->type_start, p.max_peaks, 18, ctx->pc,
                                                   ws->cands, ws->cand_counts, p.max_candidates, ws->conns,
@@ -734,6 +780,7 @@ int opb_create(opb_ctx** out, int device, const opb_params* params) {
   ctx->taps.radius = params->gauss_radius;
   for (int i = 0; i < 2 * params->gauss_radius + 1; ++i) ctx->taps.w[i] = params->gauss_taps[i];
   ctx->conn_cap = kAssignMaxType;
+  ctx->profile = getenv("OPB_PROFILE") && atoi(getenv("OPB_PROFILE")) > 0;
   *out = ctx;
   return OPB_OK;
 }
@@ -857,6 +904,7 @@ int opb_forward(opb_ctx* ctx, const void* x, int x_format, int x_loc, int n, int
   int rc = get_chain(ctx, n, h, w, &ch);
   if (rc) return rc;
   const size_t px = static_cast<size_t>(n) * h * w * 3;
+  ch->img_u8_src = nullptr;
   if (x_format == OPB_U8_NHWC_BGR) {
     if ((rc = copy_in(ctx, ch->img_u8, x, px, x_loc))) return rc;
   } else if (x_format == OPB_F32_NCHW) {
@@ -1039,19 +1087,33 @@ int opb_detect_batch(opb_ctx* ctx, const uint8_t* imgs, int imgs_loc, int n, int
   int rc;
   if ((rc = get_chain(ctx, n, h, w, &ch))) return rc;
   if ((rc = get_post(ctx, n, map_h, map_w, &ws))) return rc;
-  if ((rc = copy_in(ctx, ch->img_u8, imgs, static_cast<size_t>(n) * h * w * 3, imgs_loc))) return rc;
+  prof_mark(ctx, "begin");
+  if (imgs_loc == OPB_DEVICE) {
+    ch->img_u8_src = imgs;            // frames already resident in HBM: conv1_1 reads them in place
+  } else {
+    ch->img_u8_src = nullptr;
+    if ((rc = copy_in(ctx, ch->img_u8, imgs, static_cast<size_t>(n) * h * w * 3, imgs_loc))) return rc;
+  }
+  prof_mark(ctx, "copy_in");
   if ((rc = run_chain(ctx, ch, true))) return rc;
   const int h8 = h / 8, w8 = w / 8;
   const float* paf_lo = inject_paf ? inject_paf : ch->paf_lo;
   const float* heat_lo = inject_heat ? inject_heat : ch->heat_lo;
   if ((rc = launch_upsample(ctx, paf_lo, n * 38, h8, w8, ws->pafs, map_h, map_w))) return rc;
+  prof_mark(ctx, "upsample_paf");
   if ((rc = launch_upsample(ctx, heat_lo, n * 19, h8, w8, ws->heat, map_h, map_w))) return rc;
+  prof_mark(ctx, "upsample_heat");
   if ((rc = launch_peaks(ctx, ws, ws->heat, n, 19, map_h, map_w))) return rc;
+  prof_mark(ctx, "peaks");
   if ((rc = launch_connections(ctx, ws, ws->pafs, n, map_h, map_w, img_len))) return rc;
+  prof_mark(ctx, "connections");
   if ((rc = launch_group(ctx, ws, n, true))) return rc;
+  prof_mark(ctx, "group");
   if ((rc = copy_out(ctx, headers_out, ws->headers, sizeof(ImageHeader) * n, out_loc))) return rc;
   if ((rc = copy_out(ctx, persons_out, ws->persons, sizeof(PersonOut) * n * ctx->prm.max_persons, out_loc))) return rc;
+  prof_mark(ctx, "copy_out");
   OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  prof_report(ctx);
   return OPB_OK;
 }
 
@@ -1110,6 +1172,7 @@ int opb_precise_add_scale(opb_ctx* ctx, const uint8_t* img, int img_loc, int ph,
   Chain* ch = nullptr;
   int rc = get_chain(ctx, 1, ph, pw, &ch);
   if (rc) return rc;
+  ch->img_u8_src = nullptr;
   if ((rc = copy_in(ctx, ch->img_u8, img, static_cast<size_t>(ph) * pw * 3, img_loc))) return rc;
   if ((rc = run_chain(ctx, ch, true))) return rc;
   const int h8 = ph / 8, w8 = pw / 8;
@@ -1201,7 +1264,15 @@ int opb_time_stage(opb_ctx* ctx, const char* stage, int reps, float* ms) {
       if (s == "upsample_paf") { ++n_launch; return launch_upsample(ctx, ch->paf_lo, n * 38, h8, w8, ws->pafs, ws->H, ws->W); }
       if (s == "upsample_heat") { ++n_launch; return launch_upsample(ctx, ch->heat_lo, n * 19, h8, w8, ws->heat, ws->H, ws->W); }
       if (s == "peaks") { n_launch += 2; return launch_peaks(ctx, ws, ws->heat, n, 19, ws->H, ws->W); }
-      if (s == "paf_integral" || s == "limb_assign") { n_launch += 2; return launch_connections(ctx, ws, ws->pafs, n, ws->H, ws->W, ws->W); }
+      if (s == "paf_integral") { n_launch += 2; return launch_connections(ctx, ws, ws->pafs, n, ws->H, ws->W, ws->W); }
+      if (s == "limb_assign") {
+        ++n_launch;
+        dim3 g2(19, n);
+        limb_assign_kernel<<<g2, 256, 0, ctx->stream>>>(ws->peaks, ws->idx_list, ws->type_start, ctx->prm.max_peaks, 18,
+                                                        ctx->pc, ws->cands, ws->cand_counts, ctx->prm.max_candidates,
+                                                        ws->conns, ws->conn_counts, ctx->conn_cap, ws->status);
+        return OPB_OK;
+      }
       ++n_launch;
       return launch_group(ctx, ws, n, true);
     }

@@ -102,6 +102,15 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, accumulate always enabled (no runtime predicate computation on the issue path)
+__device__ __forceinline__ void mma_f16_ss_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

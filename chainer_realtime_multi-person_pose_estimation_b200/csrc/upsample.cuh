@@ -28,25 +28,43 @@ __device__ __forceinline__ void ac_axis(int i, int n_in, int n_out, int& i0, dou
   f = u;
 }
 
-// in [planes][h][w] -> out [planes][H][W]; grid (ceil(W/32), ceil(H/8), plane_groups)
+// in [planes][h][w] -> out [planes][H][W]; grid (ceil(W/32), ceil(H/8), plane_groups).
+// The float64 grid values depend on x or y only: one warp computes them per block into shared
+// memory; each thread then forms its four float32 weights (4 DMUL) once and streams
+// `planes_per_block` output planes.
 __global__ void __launch_bounds__(256)
 upsample_bilinear_ac_kernel(const float* __restrict__ in, int planes, int h, int w, float* __restrict__ out, int H,
                             int W, int planes_per_block) {
+  __shared__ double s_du0[32], s_du1[32], s_dv0[8], s_dv1[8];
+  __shared__ int s_u0[32], s_v0[8];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < 32) {
+    const int xx = min(blockIdx.x * 32 + tid, W - 1);
+    int u0; double u;
+    ac_axis(xx, w, W, u0, u);
+    s_u0[tid] = u0;
+    s_du1[tid] = __dsub_rn(static_cast<double>(u0 + 1), u);
+    s_du0[tid] = __dsub_rn(u, static_cast<double>(u0));
+  } else if (tid < 40) {
+    const int yy = min(blockIdx.y * 8 + (tid - 32), H - 1);
+    int v0; double v;
+    ac_axis(yy, h, H, v0, v);
+    s_v0[tid - 32] = v0;
+    s_dv1[tid - 32] = __dsub_rn(static_cast<double>(v0 + 1), v);
+    s_dv0[tid - 32] = __dsub_rn(v, static_cast<double>(v0));
+  }
+  __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * 8 + threadIdx.y;
   if (x >= W || y >= H) return;
-  int u0, v0;
-  double u, v;
-  ac_axis(x, w, W, u0, u);
-  ac_axis(y, h, H, v0, v);
-  const int u1 = u0 + 1, v1 = v0 + 1;
-  const double du1 = __dsub_rn(static_cast<double>(u1), u), du0 = __dsub_rn(u, static_cast<double>(u0));
-  const double dv1 = __dsub_rn(static_cast<double>(v1), v), dv0 = __dsub_rn(v, static_cast<double>(v0));
+  const int u0 = s_u0[threadIdx.x], v0 = s_v0[threadIdx.y];
+  const double du1 = s_du1[threadIdx.x], du0 = s_du0[threadIdx.x];
+  const double dv1 = s_dv1[threadIdx.y], dv0 = s_dv0[threadIdx.y];
   const float w1 = static_cast<float>(__dmul_rn(du1, dv1));
   const float w2 = static_cast<float>(__dmul_rn(du0, dv1));
   const float w3 = static_cast<float>(__dmul_rn(du1, dv0));
   const float w4 = static_cast<float>(__dmul_rn(du0, dv0));
-  const int o00 = v0 * w + u0, o01 = v0 * w + u1, o10 = v1 * w + u0, o11 = v1 * w + u1;
+  const int o00 = v0 * w + u0, o01 = o00 + 1, o10 = o00 + w, o11 = o10 + 1;
   const int p_begin = blockIdx.z * planes_per_block;
   const int p_end = min(planes, p_begin + planes_per_block);
   const size_t in_plane = static_cast<size_t>(h) * w, out_plane = static_cast<size_t>(H) * W;
