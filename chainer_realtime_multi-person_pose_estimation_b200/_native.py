@@ -295,13 +295,13 @@ class Engine(object):
         self._check(self.lib.opb_time_stage(self.ctx, stage.encode(), reps, C.byref(ms)))
         return float(ms.value)
 
-    def test_conv(self, x, W, b, relu, precision):
+    def test_conv(self, x, W, b, relu, precision, pool=False):
         x = np.ascontiguousarray(x, np.float32)
         W = np.ascontiguousarray(W, np.float32)
         b = np.ascontiguousarray(b, np.float32)
         n, h, w, cin = x.shape
         cout, _, ks, _ = W.shape
-        y = np.empty((n, h, w, cout), np.float32)
-        self._check(self.lib.opb_test_conv(self.ctx, _ptr(x), n, h, w, cin, _ptr(W), _ptr(b), cout, ks, int(relu),
-                                           int(precision), _ptr(y)))
+        y = np.empty((n, h // 2, w // 2, cout) if pool else (n, h, w, cout), np.float32)
+        self._check(self.lib.opb_test_conv(self.ctx, _ptr(x), n, h, w, cin, _ptr(W), _ptr(b), cout, ks,
+                                           int(bool(relu)) | (2 if pool else 0), int(precision), _ptr(y)))
         return y

@@ -18,7 +18,7 @@ constexpr int CF_TH = 8, CF_TW = 32;
 
 // wt: [27][64] fp32 (k = (r*3+s)*3 + c), bias [64].
 // x_u8: [N][H][W][3] uint8 BGR, or x_f32: [N][3][H][W] float32 (already preprocessed).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv_first_kernel(const uint8_t* __restrict__ x_u8, const float* __restrict__ x_f32, const float* __restrict__ wt,
                   const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W, int cstride,
                   int lo_off) {
@@ -31,28 +31,54 @@ conv_first_kernel(const uint8_t* __restrict__ x_u8, const float* __restrict__ x_
   if (tid < 64) s_b[tid] = bias[tid];
   s_lut[tid] = __fsub_rn(__fdiv_rn(static_cast<float>(tid), 255.f), 0.5f);
   const int tiles_x = (W + CF_TW - 1) / CF_TW, tiles_y = (H + CF_TH - 1) / CF_TH;
-  const int half = tid & 1;            // output channels half*32 .. +31
-  const int pair = tid >> 1;           // 0..127
+  const int half = tid >> 7;           // output channels half*32 .. +31; warp-uniform so that every
+                                       // weight LDS.128 is a single broadcast wavefront
+  const int pair = tid & 127;          // 0..127
   const int py = pair >> 4;            // 0..7
   const int px = (pair & 15) * 2;      // 0,2,..,30
   const int total_tiles = N * tiles_y * tiles_x;
+  constexpr int IN_ELEMS = (CF_TH + 2) * (CF_TW + 2) * 3;
+  constexpr int PER_THREAD = (IN_ELEMS + 255) / 256;
+  float pre[PER_THREAD];   // next tile's (normalised) inputs, in flight while this tile computes
+  auto prefetch = [&](int tile) {
+    const int n = tile / (tiles_y * tiles_x);
+    const int rem = tile - n * (tiles_y * tiles_x);
+    const int y0 = (rem / tiles_x) * CF_TH, x0 = (rem % tiles_x) * CF_TW;
+#pragma unroll
+    for (int e = 0; e < PER_THREAD; ++e) {
+      const int i = tid + e * 256;
+      float v = 0.f;
+      if (i < IN_ELEMS) {
+        const int c = i % 3;
+        const int q = i / 3;
+        const int xx = x0 - 1 + q % (CF_TW + 2), yy = y0 - 1 + q / (CF_TW + 2);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          if (x_u8) v = __int_as_float(static_cast<int>(x_u8[((static_cast<size_t>(n) * H + yy) * W + xx) * 3 + c]));
+          else v = x_f32[((static_cast<size_t>(n) * 3 + c) * H + yy) * W + xx];
+        } else {
+          v = x_u8 ? __int_as_float(-1) : 0.f;   // -1 marks zero padding on the uint8 path
+        }
+      }
+      pre[e] = v;
+    }
+  };
+  if (static_cast<int>(blockIdx.x) < total_tiles) prefetch(blockIdx.x);
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int n = tile / (tiles_y * tiles_x);
     const int rem = tile - n * (tiles_y * tiles_x);
     const int y0 = (rem / tiles_x) * CF_TH, x0 = (rem % tiles_x) * CF_TW;
     __syncthreads();   // LUT / weights ready; previous tile's s_in consumed
-    for (int i = tid; i < (CF_TH + 2) * (CF_TW + 2) * 3; i += 256) {
-      const int c = i % 3;
-      const int q = i / 3;
-      const int xx = x0 - 1 + q % (CF_TW + 2), yy = y0 - 1 + q / (CF_TW + 2);
-      float v = 0.f;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        if (x_u8) v = s_lut[x_u8[((static_cast<size_t>(n) * H + yy) * W + xx) * 3 + c]];
-        else v = x_f32[((static_cast<size_t>(n) * 3 + c) * H + yy) * W + xx];
+#pragma unroll
+    for (int e = 0; e < PER_THREAD; ++e) {
+      const int i = tid + e * 256;
+      if (i < IN_ELEMS) {
+        float v = pre[e];
+        if (x_u8) { const int b = __float_as_int(v); v = (b < 0) ? 0.f : s_lut[b]; }
+        s_in[i] = v;
       }
-      s_in[i] = v;
     }
     __syncthreads();
+    if (tile + static_cast<int>(gridDim.x) < total_tiles) prefetch(tile + gridDim.x);
     float in[3][4][3];   // rows py..py+2, cols px..px+3 of the halo tile
 #pragma unroll
     for (int r = 0; r < 3; ++r)

@@ -48,7 +48,7 @@ struct ConvProblem {
   int out_lo_off;       // parity mode: distance (channels) from the hi plane to the lo plane, else 0
   int cout_valid;       // real number of output channels
   int relu;
-  int pad_;
+  int pool;             // 1: fuse F.max_pooling_2d(2,2) -- `out` is the [N][H/2][W/2] pooled tensor
 };
 
 struct ConvParams {
@@ -77,24 +77,37 @@ struct ConvCfg {
 };
 
 
-// bias + ReLU + fp16 (hi[/lo]) store of CW consecutive output channels of one pixel
+// bias + ReLU (+ fused 2x2 max-pool) + fp16 (hi[/lo]) store of CW consecutive output channels of
+// one pixel.  Must be called by all 32 lanes of the warp (the pool uses shuffles): lane =
+// (y%4)*8 + x%8 of a 4-row x 8-column patch, so the 2x2 partners are lane^1 and lane^8.
 template <int CW>
 __device__ __forceinline__ void epilogue_store_group(const ConvProblem& pr, const float (&acc)[CW], int ch0, int n,
-                                                     int y, int x, int H, int W) {
-  if (ch0 >= pr.cout_valid) return;
+                                                     int y, int x, int H, int W, bool valid) {
+  if (ch0 >= pr.cout_valid) return;   // warp-uniform
   float f[CW];
 #pragma unroll
   for (int i = 0; i < CW; ++i) {
     const float t = acc[i] + __ldg(pr.bias + ch0 + i);
     f[i] = pr.relu ? fmaxf(t, 0.f) : t;
   }
+  int oy = y, ox = x, oH = H, oW = W;
+  if (pr.pool) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
+      f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 8));
+    }
+    valid = valid && ((y & 1) == 0) && ((x & 1) == 0);
+    oy = y >> 1; ox = x >> 1; oH = H >> 1; oW = W >> 1;
+  }
+  if (!valid) return;
   const int nvalid = min(CW, pr.cout_valid - ch0);
   if (pr.out32) {
     for (int i = 0; i < nvalid; ++i)
-      pr.out32[((static_cast<size_t>(n) * pr.cout_valid + ch0 + i) * H + y) * W + x] = f[i];
+      pr.out32[((static_cast<size_t>(n) * pr.cout_valid + ch0 + i) * oH + oy) * oW + ox] = f[i];
   }
   if (pr.out) {
-    const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
+    const size_t pix = (static_cast<size_t>(n) * oH + oy) * oW + ox;
     __half* o = pr.out + pix * pr.out_cstride + pr.out_coff + ch0;
     const bool vec = (nvalid == CW) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) && ((pr.out_lo_off & 7) == 0);
     if (vec) {
@@ -313,7 +326,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           for (int cc = 0; cc < BN; cc += CW) {
             float f[CW];
             tmem_load_group<CW>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * MT + mt) * BN + cc, f);
-            if (valid) epilogue_store_group<CW>(pr, f, nb * BN + cc, n, y, x, P.H, P.W);
+            epilogue_store_group<CW>(pr, f, nb * BN + cc, n, y, x, P.H, P.W, valid);
           }
         }
         ptx::tc_fence_before();
@@ -344,14 +357,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
         }
         const int x = x0 + wl;
-        if ((y < P.H) && (x < P.W)) {
+        const bool valid = (y < P.H) && (x < P.W);
 #pragma unroll
-          for (int cc = 0; cc < BN; cc += CW) {
-            float f[CW];
+        for (int cc = 0; cc < BN; cc += CW) {
+          float f[CW];
 #pragma unroll
-            for (int i = 0; i < CW; ++i) f[i] = sum[cc + i];
-            epilogue_store_group<CW>(pr, f, nb * BN + cc, n, y, x, P.H, P.W);
-          }
+          for (int i = 0; i < CW; ++i) f[i] = sum[cc + i];
+          epilogue_store_group<CW>(pr, f, nb * BN + cc, n, y, x, P.H, P.W, valid);
         }
       }
     }

@@ -101,6 +101,9 @@ struct PostWs {           // post-process workspace for (N, map_h, map_w)
   double* subsets_out = nullptr;
   ImageHeader* headers = nullptr;
   PersonOut* persons = nullptr;
+  const float* last_paf_lo = nullptr;   // low-res maps the last opb_detect_batch upsampled (network or injected)
+  const float* last_heat_lo = nullptr;
+  double last_img_len = 0;
   std::vector<void*> allocs;
 };
 
@@ -261,6 +264,8 @@ int launch_conv(opb_ctx* ctx, const Op& op) {
     case 7 * 10000 + 128 * 10 + 2: return launch_conv_t<7, 128, 2, 3, 5, 2>(ctx, op);
     case 7 * 10000 + 256 * 10 + 1: return launch_conv_t<7, 256, 1, 3, 4, 2>(ctx, op);
     case 3 * 10000 + 64 * 10 + 1: return launch_conv_t<3, 64, 1, 3, 6, 2>(ctx, op);
+    case 3 * 10000 + 64 * 10 + 2: return launch_conv_t<3, 64, 2, 3, 6, 2>(ctx, op);
+    case 7 * 10000 + 64 * 10 + 2: return launch_conv_t<7, 64, 2, 3, 6, 2>(ctx, op);
     case 3 * 10000 + 128 * 10 + 1: return launch_conv_t<3, 128, 1, 3, 6, 2>(ctx, op);
     case 3 * 10000 + 128 * 10 + 2: return launch_conv_t<3, 128, 2, 3, 6, 2>(ctx, op);
     case 3 * 10000 + 256 * 10 + 1: return launch_conv_t<3, 256, 1, 3, 4, 2>(ctx, op);
@@ -363,6 +368,7 @@ struct ConvSpec {
   float* out32[2];
   int n_problems;
   int relu;
+  int pool;
 };
 
 int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s) {
@@ -379,7 +385,7 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
   {  // MT=2: two 8-column sub-tiles share every weight stage (7x7/3x3, BN=128); OPB_MT=1 disables
     const char* e = getenv("OPB_MT");
     const int want = e ? atoi(e) : 2;   // measured: 7x7 128->128 grouped launch 10.1 -> 7.9 ms with MT=2
-    if (want == 2 && !split && op.bn == 128 && (op.ks == 7 || op.ks == 3)) op.mt = 2;
+    if (want == 2 && !split && (op.bn == 128 || op.bn == 64) && (op.ks == 7 || op.ks == 3)) op.mt = 2;
   }
   const Act& a0 = *s.in[0];
   if (a0.H < 16 + op.ks - 1 || a0.W < 8)
@@ -421,6 +427,7 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     pr.out_lo_off = (split && s.out[p]) ? s.out[p]->C : 0;
     pr.cout_valid = s.cout_valid[p];
     pr.relu = s.relu;
+    pr.pool = s.pool;
   }
   if (s.n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; P.prob[1] = P.prob[0]; }
   const int total_tiles = P.n_problems * P.n_blocks * P.N * P.tiles_y * P.tiles_x;
@@ -476,12 +483,14 @@ int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
     if (split) op.C = in.C;
     ch->ops.push_back(op);
   };
-  auto conv1 = [&](const std::string& layer, const Act& in, const Act& out, int out_coff, int cout) -> int {
+  auto conv1 = [&](const std::string& layer, const Act& in, const Act& out, int out_coff, int cout,
+                   int fuse_pool = 0) -> int {
     ConvSpec s{};
     s.in[0] = &in; s.in_coff[0] = 0; s.wkey[0] = layer; s.out[0] = &out; s.out_coff[0] = out_coff;
-    s.cout_valid[0] = cout; s.out32[0] = nullptr; s.n_problems = 1; s.relu = 1;
+    s.cout_valid[0] = cout; s.out32[0] = nullptr; s.n_problems = 1; s.relu = 1; s.pool = fuse_pool;
     return add_conv(ctx, ch, layer, s);
   };
+  const bool fuse = !(getenv("OPB_NO_POOL_FUSION") && atoi(getenv("OPB_NO_POOL_FUSION")));   // debug knob
   auto conv2 = [&](const std::string& tag, const std::string& l1, const std::string& l2, const Act& in, int ic1,
                    int ic2, const Act& out, int oc1, int oc2, int cv1, int cv2, int relu, float* o32a,
                    float* o32b) -> int {
@@ -493,16 +502,14 @@ int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
   };
 
   first();
-  RC(conv1("conv1_2", B0, B1, 0, 64));
-  pool("pool1", B1, P1);
+  // F.max_pooling_2d(2,2) (models/CocoPoseNet.py:138,141,146) is fused into the producing conv's epilogue
+  if (fuse) { RC(conv1("conv1_2", B0, P1, 0, 64, 1)); } else { RC(conv1("conv1_2", B0, B1, 0, 64)); pool("pool1", B1, P1); }
   RC(conv1("conv2_1", P1, B2, 0, 128));
-  RC(conv1("conv2_2", B2, B3, 0, 128));
-  pool("pool2", B3, P2);
+  if (fuse) { RC(conv1("conv2_2", B2, P2, 0, 128, 1)); } else { RC(conv1("conv2_2", B2, B3, 0, 128)); pool("pool2", B3, P2); }
   RC(conv1("conv3_1", P2, B4, 0, 256));
   RC(conv1("conv3_2", B4, B5, 0, 256));
   RC(conv1("conv3_3", B5, B4, 0, 256));
-  RC(conv1("conv3_4", B4, B5, 0, 256));
-  pool("pool3", B5, P3);
+  if (fuse) { RC(conv1("conv3_4", B4, P3, 0, 256, 1)); } else { RC(conv1("conv3_4", B4, B5, 0, 256)); pool("pool3", B5, P3); }
   RC(conv1("conv4_1", P3, B6, 0, 512));
   RC(conv1("conv4_2", B6, B7, 0, 512));
   RC(conv1("conv4_3_CPM", B7, B8, 0, 256));
@@ -625,7 +632,8 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
   const size_t smem = smooth_nms_smem_bytes(ctx->taps.radius);
   static bool attr1 = false, attr2 = false;
   if (!attr1) {
-    OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_kernel<PK_R_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr1 = true;
   }
   dim3 grid((W + PK_TX - 1) / PK_TX, (H + PK_TY - 1) / PK_TY, n * c_use);
@@ -633,9 +641,14 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
   tile_max_kernel<<<grid, 256, 0, ctx->stream>>>(heat, c_total, c_use, H, W, ws->tile_max);
   ctx->launches++;
   prof_mark(ctx, "tile_max");
-  smooth_nms_kernel<<<grid, 256, smem, ctx->stream>>>(heat, c_total, c_use, H, W, ctx->taps,
-                                                      static_cast<float>(p.heatmap_peak_thresh), ws->keys,
-                                                      ws->peak_counts, p.max_peaks, ws->tile_max);
+  if (ctx->taps.radius == PK_R_FAST)
+    smooth_nms_kernel<PK_R_FAST><<<grid, 256, smem, ctx->stream>>>(heat, c_total, c_use, H, W, ctx->taps,
+                                                                   static_cast<float>(p.heatmap_peak_thresh), ws->keys,
+                                                                   ws->peak_counts, p.max_peaks, ws->tile_max);
+  else
+    smooth_nms_kernel<0><<<grid, 256, smem, ctx->stream>>>(heat, c_total, c_use, H, W, ctx->taps,
+                                                           static_cast<float>(p.heatmap_peak_thresh), ws->keys,
+                                                           ws->peak_counts, p.max_peaks, ws->tile_max);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   prof_mark(ctx, "smooth_nms");
@@ -1099,6 +1112,7 @@ int opb_detect_batch(opb_ctx* ctx, const uint8_t* imgs, int imgs_loc, int n, int
   const int h8 = h / 8, w8 = w / 8;
   const float* paf_lo = inject_paf ? inject_paf : ch->paf_lo;
   const float* heat_lo = inject_heat ? inject_heat : ch->heat_lo;
+  ws->last_paf_lo = paf_lo; ws->last_heat_lo = heat_lo; ws->last_img_len = img_len;
   if ((rc = launch_upsample(ctx, paf_lo, n * 38, h8, w8, ws->pafs, map_h, map_w))) return rc;
   prof_mark(ctx, "upsample_paf");
   if ((rc = launch_upsample(ctx, heat_lo, n * 19, h8, w8, ws->heat, map_h, map_w))) return rc;
@@ -1261,10 +1275,13 @@ int opb_time_stage(opb_ctx* ctx, const char* stage, int reps, float* ms) {
         s == "group") {
       if (!ws || !ch) { ctx->err = "no cached pipeline to time"; return OPB_ERR_STATE; }
       const int n = ws->N, h8 = ch->H / 8, w8 = ch->W / 8;
-      if (s == "upsample_paf") { ++n_launch; return launch_upsample(ctx, ch->paf_lo, n * 38, h8, w8, ws->pafs, ws->H, ws->W); }
-      if (s == "upsample_heat") { ++n_launch; return launch_upsample(ctx, ch->heat_lo, n * 19, h8, w8, ws->heat, ws->H, ws->W); }
-      if (s == "peaks") { n_launch += 2; return launch_peaks(ctx, ws, ws->heat, n, 19, ws->H, ws->W); }
-      if (s == "paf_integral") { n_launch += 2; return launch_connections(ctx, ws, ws->pafs, n, ws->H, ws->W, ws->W); }
+      const float* plo = ws->last_paf_lo ? ws->last_paf_lo : ch->paf_lo;     // same maps as the last batch
+      const float* hlo = ws->last_heat_lo ? ws->last_heat_lo : ch->heat_lo;
+      const double ilen = ws->last_img_len > 0 ? ws->last_img_len : ws->W;
+      if (s == "upsample_paf") { ++n_launch; return launch_upsample(ctx, plo, n * 38, h8, w8, ws->pafs, ws->H, ws->W); }
+      if (s == "upsample_heat") { ++n_launch; return launch_upsample(ctx, hlo, n * 19, h8, w8, ws->heat, ws->H, ws->W); }
+      if (s == "peaks") { n_launch += 3; return launch_peaks(ctx, ws, ws->heat, n, 19, ws->H, ws->W); }
+      if (s == "paf_integral") { n_launch += 2; return launch_connections(ctx, ws, ws->pafs, n, ws->H, ws->W, ilen); }
       if (s == "limb_assign") {
         ++n_launch;
         dim3 g2(19, n);
@@ -1313,6 +1330,10 @@ int opb_test_conv(opb_ctx* ctx, const float* x, int n, int h, int w, int cin, co
   const bool split = precision_mode == OPB_PRECISION_PARITY;
   const int saved_precision = ctx->precision;
   ctx->precision = precision_mode;
+  const int pool = (relu >> 1) & 1;   // bit 1 of `relu`: fuse the 2x2 max-pool (y is then [N,H/2,W/2,Cout])
+  relu &= 1;
+  if (pool && ((h | w) & 1)) { ctx->precision = saved_precision; OPB_FAIL(ctx, OPB_ERR_ARG, "pooled test conv needs even H, W"); }
+  const int oh = pool ? h / 2 : h, ow = pool ? w / 2 : w;
   Chain tmp;
   int rc = OPB_OK;
   const int cin_pad = round_up(cin, 64);
@@ -1329,7 +1350,7 @@ int opb_test_conv(opb_ctx* ctx, const float* x, int n, int h, int w, int cin, co
   do {
     if ((rc = pack_weights(ctx, "__test__", {{"__test__", cout_pad}}, identity_map(cin, cin_pad), ksize, split))) break;
     if ((rc = alloc_act(ctx, &tmp, &in, n, h, w, cin_pad))) break;
-    if ((rc = alloc_act(ctx, &tmp, &out, n, h, w, cout_pad))) break;
+    if ((rc = alloc_act(ctx, &tmp, &out, n, oh, ow, cout_pad))) break;
     hx.assign(static_cast<size_t>(n) * h * w * in.Ctot, __float2half(0.f));
     for (size_t pix = 0; pix < static_cast<size_t>(n) * h * w; ++pix)
       for (int c = 0; c < cin; ++c) {
@@ -1342,14 +1363,14 @@ int opb_test_conv(opb_ctx* ctx, const float* x, int n, int h, int w, int cin, co
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = OPB_ERR_CUDA; break; }
     ConvSpec s{};
     s.in[0] = &in; s.in_coff[0] = 0; s.wkey[0] = "__test__"; s.out[0] = &out; s.out_coff[0] = 0;
-    s.cout_valid[0] = cout; s.n_problems = 1; s.relu = relu;
+    s.cout_valid[0] = cout; s.n_problems = 1; s.relu = relu; s.pool = pool;
     if ((rc = add_conv(ctx, &tmp, "__test__", s))) break;
     if ((rc = launch_op(ctx, &tmp, tmp.ops[0]))) break;
-    hy.resize(static_cast<size_t>(n) * h * w * out.Ctot);
+    hy.resize(static_cast<size_t>(n) * oh * ow * out.Ctot);
     e = cudaMemcpyAsync(hy.data(), out.p, hy.size() * 2, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { ctx->err = std::string("test conv: ") + cudaGetErrorString(e); rc = OPB_ERR_CUDA; break; }
-    for (size_t pix = 0; pix < static_cast<size_t>(n) * h * w; ++pix)
+    for (size_t pix = 0; pix < static_cast<size_t>(n) * oh * ow; ++pix)
       for (int c = 0; c < cout; ++c) {
         float v = __half2float(hy[pix * out.Ctot + c]);
         if (split) v += __half2float(hy[pix * out.Ctot + out.C + c]);

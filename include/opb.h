@@ -192,7 +192,8 @@ int opb_time_stage(opb_ctx* ctx, const char* stage, int reps, float* ms);
 /* -- test hooks (tests/ only) ---------------------------------------------------------------
  * single conv layer through the tcgen05 kernel: x [N,H,W,Cin] fp32 host, W [Cout,Cin,k,k],
  * b [Cout] -> y [N,H,W,Cout] fp32 host (activations are converted to fp16 / split-fp16 on the
- * device exactly as in the chain).                                                           */
+ * device exactly as in the chain).  relu: bit 0 = ReLU, bit 1 = fuse the 2x2/2 max-pool (y is
+ * then [N,H/2,W/2,Cout]).                                                                    */
 int opb_test_conv(opb_ctx* ctx, const float* x, int n, int h, int w, int cin, const float* W,
                   const float* b, int cout, int ksize, int relu, int precision_mode, float* y);
 

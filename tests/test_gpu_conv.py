@@ -76,3 +76,24 @@ def test_conv_zero_padding_borders(engine):
         y = engine.test_conv(x, W, b, 0, native.PRECISION_FAST)
         ref = _ref_conv(x, W, b, 0, quantize=True)
         assert np.array_equal(y, ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("mode", ["fast", "parity"])
+@pytest.mark.parametrize("case", [(2, 24, 40, 64, 64, 3), (1, 32, 18, 128, 128, 3), (1, 46, 82, 256, 256, 3)],
+                         ids=lambda c: "n%d_%dx%d_c%d_o%d_k%d" % c)
+def test_conv_fused_maxpool(engine, case, mode):
+    """conv + ReLU + F.max_pooling_2d(2,2) fused in the epilogue (conv1_2 / conv2_2 / conv3_4)."""
+    n, h, w, cin, cout, ks = case
+    native = pkg("_native")
+    rs = np.random.RandomState(11)
+    x = rs.standard_normal((n, h, w, cin)).astype(np.float32)
+    W = (rs.standard_normal((cout, cin, ks, ks)) * np.sqrt(2.0 / (cin * ks * ks))).astype(np.float32)
+    b = (rs.standard_normal(cout) * 0.1).astype(np.float32)
+    prec = native.PRECISION_FAST if mode == "fast" else native.PRECISION_PARITY
+    y = engine.test_conv(x, W, b, 1, prec, pool=True)
+    ref = _ref_conv(x, W, b, 1, quantize=(mode == "fast"))
+    ref = torch.nn.functional.max_pool2d(torch.from_numpy(ref).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).numpy()
+    scale = np.abs(ref).max()
+    err = np.abs(y - ref).max()
+    assert y.shape == ref.shape
+    assert err <= (2e-3 if mode == "fast" else 1e-4) * scale, "max abs err %.3e (scale %.3f)" % (err, scale)
