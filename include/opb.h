@@ -115,11 +115,11 @@ int opb_finalize_weights(opb_ctx* ctx, int precision_mode);
 int opb_forward(opb_ctx* ctx, const void* x, int x_format, int x_loc, int n, int h, int w,
                 float* paf_out, float* heat_out, int out_loc);
 
-/* -- upsample: replaces F.resize_images (pose_detector.py:501-502, bilinear align-corners)
- *    and cv2.resize(INTER_CUBIC) of float maps (pose_detector.py:461-467).
- *    in [planes,h,w] -> out [planes,H,W] float32.  For BICUBIC, out is cropped to
- *    [crop_h, crop_w] of the (H,W) result when crop_* > 0 (pose_detector.py:462,466) and
- *    `accumulate` != 0 adds into out instead of overwriting (pafs_sum +=, :463).            */
+/* -- upsample: replaces F.resize_images (pose_detector.py:501-502, OPB_UPSAMPLE_BILINEAR_AC:
+ *    align-corners bilinear, bit-exact restatement of Chainer's ResizeImages.forward) and one
+ *    cv2.resize(INTER_CUBIC) of float maps (pose_detector.py:461-467, OPB_UPSAMPLE_BICUBIC).
+ *    in [planes,h,w] -> out [planes,out_h,out_w] float32.  The crop / accumulate / average
+ *    steps of detect_precise are inside opb_precise_add_scale.                              */
 int opb_upsample(opb_ctx* ctx, int mode, const float* in, int in_loc, int planes, int h, int w,
                  float* out, int out_loc, int out_h, int out_w);
 

@@ -188,3 +188,18 @@ def test_public_stage_methods_chain(engine):
     assert np.array_equal(peaks, g["all_peaks"]) and np.array_equal(subsets, g["subsets"])
     assert np.array_equal(poses, g["poses"])
     assert det.compute_peaks_from_heatmaps(np.zeros((19, 32, 32), np.float32)).shape == (0,)
+
+
+def test_upsample_bicubic_vs_cv2(engine):
+    """cv2.resize(INTER_CUBIC) on float32 maps (pose_detector.py:461-467): Keys cubic A=-0.75, half-pixel
+    centres, replicate border.  cv2 evaluates the 4x4 sum with SIMD FMAs, so this is a tolerance
+    check (1e-5 absolute on O(1) data), not bit-exactness."""
+    import cv2
+    native = pkg("_native")
+    rs = np.random.RandomState(5)
+    for (h, w, H, W) in ((23, 23, 184, 184), (46, 46, 368, 368), (60, 60, 480, 480), (46, 82, 368, 656), (31, 17, 100, 90)):
+        x = rs.standard_normal((6, h, w)).astype(np.float32)
+        got = engine.upsample(x, H, W, mode=native.UPSAMPLE_BICUBIC)
+        ref = cv2.resize(np.ascontiguousarray(x.transpose(1, 2, 0)), (W, H), interpolation=cv2.INTER_CUBIC)
+        ref = ref.transpose(2, 0, 1)
+        assert np.abs(got - ref).max() <= 1e-5, (h, w, H, W, np.abs(got - ref).max())
