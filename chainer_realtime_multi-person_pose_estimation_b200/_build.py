@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "opb_api.cu")
-LIB = os.path.join(HERE, "libopb.so")
+LIB = os.path.join(HERE, os.environ.get("OPB_LIB_NAME", "libopb.so"))
 DEPS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [
     os.path.join(os.path.dirname(HERE), "include", "opb.h")]
 
@@ -24,7 +24,7 @@ def build_native(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-           "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3", "-o", LIB, SRC]
+           "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3", "-o", LIB, SRC] + os.environ.get("OPB_NVCC_FLAGS", "").split()
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libopb.so")
+LIB_PATH = os.environ.get("OPB_LIB_PATH", os.path.join(HERE, "libopb.so"))   # OPB_LIB_PATH: A/B builds only
 
 OPB_HOST, OPB_DEVICE = 0, 1
 F32_NCHW, U8_NHWC_BGR = 0, 1

@@ -36,7 +36,14 @@
 
 namespace opb {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 192;    // 2 + 4 epilogue warps (parity / two-level accumulation kernels)
+#ifndef OPB_EPI_SETS
+#define OPB_EPI_SETS 1
+#endif
+#ifndef OPB_ROLE_REORDER
+#define OPB_ROLE_REORDER 0
+#endif
+constexpr int kConvThreads2 = 64 + 128 * OPB_EPI_SETS;   // 2 + 8 epilogue warps (fast kernels): the epilogue is latency bound with one warp per SMSP
 constexpr int kMaxPairs = 24;
 
 struct ConvProblem {
@@ -73,66 +80,138 @@ struct ConvCfg {
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static_assert(TMEM_COLS_RAW <= 512, "accumulators do not fit TMEM");
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NSA * A_STAGE_BYTES + NSB * B_STAGE_BYTES + 512;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NSA * A_STAGE_BYTES + NSB * B_STAGE_BYTES + 512 + 8 * BN * 4;
 };
 
 
 // bias + ReLU (+ fused 2x2 max-pool) + fp16 (hi[/lo]) store of CW consecutive output channels of
 // one pixel.  Must be called by all 32 lanes of the warp (the pool uses shuffles): lane =
 // (y%4)*8 + x%8 of a 4-row x 8-column patch, so the 2x2 partners are lane^1 and lane^8.
-template <int CW>
-__device__ __forceinline__ void epilogue_store_group(const ConvProblem& pr, const float (&acc)[CW], int ch0, int n,
-                                                     int y, int x, int H, int W, bool valid) {
+// `bias` points at this group's CW biases (shared memory, 16-byte aligned).
+// SPLIT = parity precision (hi + lo planes, pooling on the fp32 value); otherwise the values are
+// packed to half2 first and pooled with HMNMX2 (rounding is monotonic, so max commutes with it).
+template <int CW, bool SPLIT>
+__device__ __forceinline__ void epilogue_store_group(const ConvProblem& pr, const float (&acc)[CW],
+                                                     const float* __restrict__ bias, int ch0, int n, int y, int x,
+                                                     int H, int W, bool valid) {
   if (ch0 >= pr.cout_valid) return;   // warp-uniform
   float f[CW];
 #pragma unroll
-  for (int i = 0; i < CW; ++i) {
-    const float t = acc[i] + __ldg(pr.bias + ch0 + i);
-    f[i] = pr.relu ? fmaxf(t, 0.f) : t;
+  for (int i = 0; i < CW / 4; ++i) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * i);
+    f[4 * i + 0] = acc[4 * i + 0] + b.x;
+    f[4 * i + 1] = acc[4 * i + 1] + b.y;
+    f[4 * i + 2] = acc[4 * i + 2] + b.z;
+    f[4 * i + 3] = acc[4 * i + 3] + b.w;
+  }
+  if (pr.relu) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) f[i] = fmaxf(f[i], 0.f);
   }
   int oy = y, ox = x, oH = H, oW = W;
-  if (pr.pool) {
-#pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
-      f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 8));
-    }
-    valid = valid && ((y & 1) == 0) && ((x & 1) == 0);
-    oy = y >> 1; ox = x >> 1; oH = H >> 1; oW = W >> 1;
-  }
-  if (!valid) return;
   const int nvalid = min(CW, pr.cout_valid - ch0);
-  if (pr.out32) {
-    for (int i = 0; i < nvalid; ++i)
-      pr.out32[((static_cast<size_t>(n) * pr.cout_valid + ch0 + i) * oH + oy) * oW + ox] = f[i];
+  if (pr.pool) {
+    oy = y >> 1; ox = x >> 1; oH = H >> 1; oW = W >> 1;
+    valid = valid && ((y & 1) == 0) && ((x & 1) == 0);
   }
-  if (pr.out) {
-    const size_t pix = (static_cast<size_t>(n) * oH + oy) * oW + ox;
-    __half* o = pr.out + pix * pr.out_cstride + pr.out_coff + ch0;
-    const bool vec = (nvalid == CW) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) && ((pr.out_lo_off & 7) == 0);
-    if (vec) {
+  if constexpr (SPLIT) {
+    if (pr.pool) {
 #pragma unroll
-      for (int g = 0; g < CW / 8; ++g) {
-        __align__(16) __half2 h[4];
-        __align__(16) __half2 l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float a = f[g * 8 + 2 * i], b = f[g * 8 + 2 * i + 1];
-          const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-          h[i] = __halves2half2(ha, hb);
-          l[i] = __halves2half2(__float2half_rn(a - __half2float(ha)), __float2half_rn(b - __half2float(hb)));
-        }
-        *reinterpret_cast<uint4*>(o + g * 8) = *reinterpret_cast<const uint4*>(h);
-        if (pr.out_lo_off) *reinterpret_cast<uint4*>(o + pr.out_lo_off + g * 8) = *reinterpret_cast<const uint4*>(l);
+      for (int i = 0; i < CW; ++i) {
+        f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
+        f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 8));
       }
-    } else {
-      for (int i = 0; i < nvalid; ++i) {
-        const __half hi = __float2half_rn(f[i]);
-        o[i] = hi;
-        if (pr.out_lo_off) o[pr.out_lo_off + i] = __float2half_rn(f[i] - __half2float(hi));
+    }
+    if (!valid) return;
+    if (pr.out32) {
+      // constant trip count + predicate: a runtime-indexed f[] would be demoted to local memory
+#pragma unroll
+      for (int i = 0; i < CW; ++i)
+        if (i < nvalid) pr.out32[((static_cast<size_t>(n) * pr.cout_valid + ch0 + i) * oH + oy) * oW + ox] = f[i];
+    }
+    if (pr.out) {
+      const size_t pix = (static_cast<size_t>(n) * oH + oy) * oW + ox;
+      __half* o = pr.out + pix * pr.out_cstride + pr.out_coff + ch0;
+      const bool vec = (nvalid == CW) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) && ((pr.out_lo_off & 7) == 0);
+      if (vec) {
+#pragma unroll
+        for (int g = 0; g < CW / 8; ++g) {
+          __align__(16) __half2 h[4];
+          __align__(16) __half2 l[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = f[g * 8 + 2 * i], b = f[g * 8 + 2 * i + 1];
+            const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+            h[i] = __halves2half2(ha, hb);
+            l[i] = __halves2half2(__float2half_rn(a - __half2float(ha)), __float2half_rn(b - __half2float(hb)));
+          }
+          *reinterpret_cast<uint4*>(o + g * 8) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(o + pr.out_lo_off + g * 8) = *reinterpret_cast<const uint4*>(l);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+          if (i < nvalid) {
+            const __half hi = __float2half_rn(f[i]);
+            o[i] = hi;
+            o[pr.out_lo_off + i] = __float2half_rn(f[i] - __half2float(hi));
+          }
+        }
+      }
+    }
+  } else {
+    if (pr.out32 && valid) {   // network heads: fp32 planar maps for the post-process (never pooled)
+#pragma unroll
+      for (int i = 0; i < CW; ++i)
+        if (i < nvalid) pr.out32[((static_cast<size_t>(n) * pr.cout_valid + ch0 + i) * oH + oy) * oW + ox] = f[i];
+    }
+    if (pr.out) {
+      uint32_t h[CW / 2];        // packed half2, kept in registers (no address-taken arrays)
+#pragma unroll
+      for (int i = 0; i < CW / 2; ++i) {
+        const __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        h[i] = *reinterpret_cast<const uint32_t*>(&t);
+      }
+      if (pr.pool) {
+#pragma unroll
+        for (int i = 0; i < CW / 2; ++i) {
+          uint32_t o1 = __shfl_xor_sync(0xffffffffu, h[i], 1);
+          __half2 m = __hmax2(*reinterpret_cast<__half2*>(&h[i]), *reinterpret_cast<__half2*>(&o1));
+          h[i] = *reinterpret_cast<uint32_t*>(&m);
+          uint32_t o2 = __shfl_xor_sync(0xffffffffu, h[i], 8);
+          m = __hmax2(*reinterpret_cast<__half2*>(&h[i]), *reinterpret_cast<__half2*>(&o2));
+          h[i] = *reinterpret_cast<uint32_t*>(&m);
+        }
+      }
+      if (!valid) return;
+      const size_t pix = (static_cast<size_t>(n) * oH + oy) * oW + ox;
+      __half* o = pr.out + pix * pr.out_cstride + pr.out_coff + ch0;
+      const bool vec = (nvalid == CW) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+      if (vec) {
+#pragma unroll
+        for (int g = 0; g < CW / 8; ++g)
+          *reinterpret_cast<uint4*>(o + g * 8) = make_uint4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+          if (i < nvalid) {
+            const uint32_t w = h[i >> 1];
+            const unsigned short bits = (i & 1) ? static_cast<unsigned short>(w >> 16) : static_cast<unsigned short>(w & 0xffffu);
+            reinterpret_cast<unsigned short*>(o)[i] = bits;
+          }
+        }
       }
     }
   }
+}
+
+// each epilogue warp keeps its own copy of the current (problem, n-block) bias vector in shared memory
+template <int BN>
+__device__ __forceinline__ void epilogue_load_bias(float* s_bias_warp, const float* __restrict__ gbias, int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int i = lane; i < BN; i += 32) s_bias_warp[i] = __ldg(gbias + i);
+  __syncwarp();
 }
 
 template <int CW>
@@ -153,7 +232,7 @@ __device__ __forceinline__ void tmem_load_group(uint32_t taddr, float (&f)[CW]) 
 }
 
 template <int KS, int BN, int MT, int NSA, int NSB, int ACC_STAGES, bool DRAIN>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(DRAIN ? kConvThreads : kConvThreads2, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                     const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                     const __grid_constant__ ConvParams P) {
@@ -174,8 +253,18 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint64_t* t_full = b_empty + NSB;
   uint64_t* t_empty = t_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + ACC_STAGES);
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [8 warps][BN]
+  constexpr int EPI_SETS = DRAIN ? 1 : OPB_EPI_SETS;
 
-  const int warp = threadIdx.x >> 5;
+  // warp roles: 0..kEpiWarps-1 epilogue, then the TMA producer, then the MMA issuer.  The SMSP arbiter
+  // prefers the HIGHEST warp id, so the two latency-critical single-thread roles get the top ids.
+  constexpr int kEpiWarps = 4 * EPI_SETS;
+  const int warp_raw = threadIdx.x >> 5;
+#if OPB_ROLE_REORDER
+  const int warp = (warp_raw >= kEpiWarps) ? warp_raw - kEpiWarps : warp_raw + 2;   // logical: 0 TMA, 1 MMA, 2.. epilogue
+#else
+  const int warp = warp_raw;
+#endif
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -187,7 +276,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     for (int i = 0; i < NSA; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NSB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 128); }
+    for (int i = 0; i < ACC_STAGES; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 128 * EPI_SETS); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -297,10 +386,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
     }
   } else {
-    // ================================================================ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ================================================================ epilogue (warps 2..5 [, 6..9])
+    const int q = warp_raw & 3;  // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int eset = (warp - 2) >> 2;          // which set of four epilogue warps (fast kernels have two)
     const int row = q * 32 + lane;
     const int hl = row >> 3, wl = row & 7;
+    float* s_bias_w = s_bias + (warp - 2) * BN;
+    int bias_key = -1;
     uint32_t acc = 0, pacc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int p = tile / tiles_per_problem;
@@ -314,19 +406,26 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int x0 = tx * (8 * MT);
       const int n_sub = min(MT, (P.W - x0 + 7) >> 3);
       const ConvProblem& pr = P.prob[p];
+      if (bias_key != p * 1024 + nb) {         // (problem, n-block) changes a handful of times per launch
+        bias_key = p * 1024 + nb;
+        epilogue_load_bias<BN>(s_bias_w, pr.bias + nb * BN, lane);
+      }
 
       constexpr int CW = (BN % 32 == 0) ? 32 : 16;   // BN = 48: three groups of 16
       if constexpr (!DRAIN) {
         ptx::mbar_wait(&t_full[acc], pacc);
         ptx::tc_fence_after();
+        // the (sub-tile, channel-group) work items alternate between the two sets of epilogue warps
+        int item = 0;
         for (int mt = 0; mt < n_sub; ++mt) {
           const int x = x0 + mt * 8 + wl;
           const bool valid = (y < P.H) && (x < P.W);
 #pragma unroll 1
-          for (int cc = 0; cc < BN; cc += CW) {
+          for (int cc = 0; cc < BN; cc += CW, ++item) {
+            if ((item & (EPI_SETS - 1)) != eset) continue;
             float f[CW];
             tmem_load_group<CW>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * MT + mt) * BN + cc, f);
-            epilogue_store_group<CW>(pr, f, nb * BN + cc, n, y, x, P.H, P.W, valid);
+            epilogue_store_group<CW, false>(pr, f, s_bias_w + cc, nb * BN + cc, n, y, x, P.H, P.W, valid);
           }
         }
         ptx::tc_fence_before();
@@ -363,7 +462,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           float f[CW];
 #pragma unroll
           for (int i = 0; i < CW; ++i) f[i] = sum[cc + i];
-          epilogue_store_group<CW>(pr, f, nb * BN + cc, n, y, x, P.H, P.W, valid);
+          epilogue_store_group<CW, true>(pr, f, s_bias_w + cc, nb * BN + cc, n, y, x, P.H, P.W, valid);
         }
       }
     }

@@ -18,6 +18,7 @@
 #include "../../include/opb.h"
 #include "conv_first.cuh"
 #include "conv_tcgen05.cuh"
+#include "conv_tcgen05_pair.cuh"
 #include "paf.cuh"
 #include "peaks.cuh"
 #include "pool.cuh"
@@ -62,6 +63,7 @@ struct Op {
   // OP_CONV
   int ks = 0, bn = 0, mt = 1;
   bool drain = false;
+  bool pair = false;   // cta_group::2 kernel (cluster of 2 CTAs)
   CUtensorMap tmA[2], tmB[2];
   ConvParams P;
   int grid = 0;
@@ -237,7 +239,22 @@ int launch_conv_t(opb_ctx* ctx, const Op& op) {
     OPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set[ctx->device & 63] = true;
   }
-  kern<<<op.grid, kConvThreads, Cfg::SMEM_BYTES, ctx->stream>>>(op.tmA[0], op.tmB[0], op.tmA[1], op.tmB[1], op.P);
+  kern<<<op.grid, DRAIN ? kConvThreads : kConvThreads2, Cfg::SMEM_BYTES, ctx->stream>>>(op.tmA[0], op.tmB[0], op.tmA[1], op.tmB[1], op.P);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  return OPB_OK;
+}
+
+template <int KS, int BN, int MT, int NSA, int NSB, int ACC>
+int launch_conv_pair_t(opb_ctx* ctx, const Op& op) {
+  using Cfg = ConvPairCfg<KS, BN, MT, NSA, NSB, ACC>;
+  auto kern = conv_tcgen05_pair_kernel<KS, BN, MT, NSA, NSB, ACC>;
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    OPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[ctx->device & 63] = true;
+  }
+  kern<<<op.grid, kConvThreads2, Cfg::SMEM_BYTES, ctx->stream>>>(op.tmA[0], op.tmB[0], op.tmA[1], op.tmB[1], op.P);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   return OPB_OK;
@@ -245,6 +262,19 @@ int launch_conv_t(opb_ctx* ctx, const Op& op) {
 
 int launch_conv(opb_ctx* ctx, const Op& op) {
   const int key = op.ks * 10000 + op.bn * 10 + op.mt;
+  if (op.pair) {    // CTA-pair kernels (fast precision)
+    switch (key) {
+      case 7 * 10000 + 128 * 10 + 2: return launch_conv_pair_t<7, 128, 2, 3, 6, 2>(ctx, op);
+      case 7 * 10000 + 128 * 10 + 1: return launch_conv_pair_t<7, 128, 1, 4, 8, 2>(ctx, op);
+      case 7 * 10000 + 256 * 10 + 1: return launch_conv_pair_t<7, 256, 1, 4, 6, 2>(ctx, op);
+      case 3 * 10000 + 128 * 10 + 2: return launch_conv_pair_t<3, 128, 2, 3, 6, 2>(ctx, op);
+      case 3 * 10000 + 256 * 10 + 1: return launch_conv_pair_t<3, 256, 1, 4, 6, 2>(ctx, op);
+      case 3 * 10000 + 64 * 10 + 2: return launch_conv_pair_t<3, 64, 2, 3, 6, 2>(ctx, op);
+      case 1 * 10000 + 128 * 10 + 1: return launch_conv_pair_t<1, 128, 1, 4, 6, 2>(ctx, op);
+      case 1 * 10000 + 256 * 10 + 1: return launch_conv_pair_t<1, 256, 1, 4, 6, 2>(ctx, op);
+      default: OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "no pair-mode conv variant for key " + std::to_string(key));
+    }
+  }
   if (op.drain) {   // parity precision: two-level accumulation variants (BN <= 128, MT = 1)
     switch (key) {
       case 7 * 10000 + 128 * 10 + 1: return launch_conv_t<7, 128, 1, 3, 6, 2, true>(ctx, op);
@@ -264,10 +294,10 @@ int launch_conv(opb_ctx* ctx, const Op& op) {
     case 7 * 10000 + 128 * 10 + 2: return launch_conv_t<7, 128, 2, 3, 5, 2>(ctx, op);
     case 7 * 10000 + 256 * 10 + 1: return launch_conv_t<7, 256, 1, 3, 4, 2>(ctx, op);
     case 3 * 10000 + 64 * 10 + 1: return launch_conv_t<3, 64, 1, 3, 6, 2>(ctx, op);
-    case 3 * 10000 + 64 * 10 + 2: return launch_conv_t<3, 64, 2, 3, 6, 2>(ctx, op);
+    case 3 * 10000 + 64 * 10 + 2: return (getenv("OPB_K3") && atoi(getenv("OPB_K3"))) ? launch_conv_t<3, 64, 2, 5, 4, 2>(ctx, op) : launch_conv_t<3, 64, 2, 3, 6, 2>(ctx, op);
     case 7 * 10000 + 64 * 10 + 2: return launch_conv_t<7, 64, 2, 3, 6, 2>(ctx, op);
     case 3 * 10000 + 128 * 10 + 1: return launch_conv_t<3, 128, 1, 3, 6, 2>(ctx, op);
-    case 3 * 10000 + 128 * 10 + 2: return launch_conv_t<3, 128, 2, 3, 6, 2>(ctx, op);
+    case 3 * 10000 + 128 * 10 + 2: return (getenv("OPB_K3") && atoi(getenv("OPB_K3"))) ? launch_conv_t<3, 128, 2, 4, 4, 2>(ctx, op) : launch_conv_t<3, 128, 2, 3, 6, 2>(ctx, op);
     case 3 * 10000 + 256 * 10 + 1: return launch_conv_t<3, 256, 1, 3, 4, 2>(ctx, op);
     case 1 * 10000 + 128 * 10 + 1: return launch_conv_t<1, 128, 1, 4, 6, 2>(ctx, op);
     case 1 * 10000 + 256 * 10 + 1: return launch_conv_t<1, 256, 1, 4, 4, 2>(ctx, op);
@@ -390,10 +420,23 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
   const Act& a0 = *s.in[0];
   if (a0.H < 16 + op.ks - 1 || a0.W < 8)
     OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "feature map smaller than one TMA box (min 22 x 8); image too small");
+  {  // OPB_PAIR: bit mask of kernel families that run on CTA pairs (cta_group::2): 1 = 7x7, 2 = 3x3, 4 = 1x1
+    const char* e = getenv("OPB_PAIR");
+    const int mask = e ? atoi(e) : -1;
+    const int fam = op.ks == 7 ? 1 : op.ks == 3 ? 2 : 4;
+    // default (-1): only the fused Mconv1 launch (7x7, N=256): measured 2.07 -> 1.92 ms per 5 launches.
+    // The N=128 families lose more to the 16-column pair granularity (82 -> 96 columns) than they gain.
+    const bool use_pair = (mask < 0) ? (op.ks == 7 && op.bn == 256) : ((mask & fam) != 0);
+    if (!split && use_pair && op.bn >= 64 && op.bn != 48) {
+      op.pair = true;
+      if (op.bn == 256 || op.ks == 1) op.mt = 1;
+    }
+  }
   std::memset(&op.P, 0, sizeof(op.P));
   ConvParams& P = op.P;
   P.N = a0.N; P.H = a0.H; P.W = a0.W;
-  P.tiles_x = (a0.W + 8 * op.mt - 1) / (8 * op.mt);
+  const int tile_w = (op.pair ? 16 : 8) * op.mt;
+  P.tiles_x = (a0.W + tile_w - 1) / tile_w;
   P.tiles_y = (a0.H + 15) / 16;
   P.n_blocks = per_problem_cout_pad / op.bn;
   P.n_problems = s.n_problems;
@@ -416,7 +459,7 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     if (split && s.in[p]->C != a0.C) OPB_FAIL(ctx, OPB_ERR_ARG, "grouped problems must share the lo-plane offset");
     int rc = make_act_map(ctx, &op.tmA[p], *s.in[p], s.in_coff[p], op.ks);
     if (rc) return rc;
-    rc = make_w_map(ctx, &op.tmB[p], w, op.bn);
+    rc = make_w_map(ctx, &op.tmB[p], w, op.pair ? op.bn / 2 : op.bn);
     if (rc) return rc;
     ConvProblem& pr = P.prob[p];
     pr.out = s.out[p] ? s.out[p]->p : nullptr;
@@ -431,7 +474,7 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
   }
   if (s.n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; P.prob[1] = P.prob[0]; }
   const int total_tiles = P.n_problems * P.n_blocks * P.N * P.tiles_y * P.tiles_x;
-  op.grid = std::min(total_tiles, ctx->num_sms);
+  op.grid = op.pair ? 2 * std::min(total_tiles, ctx->num_sms / 2) : std::min(total_tiles, ctx->num_sms);
   ch->ops.push_back(op);
   return OPB_OK;
 }

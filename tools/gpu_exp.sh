@@ -1,12 +1,9 @@
 #!/bin/bash
-# full ncu capture of the dominant kernel (grouped 7x7 128->128) + 2-GPU bench
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-if [ "${1:-}" = "ncu" ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tcgen05_kernel -s 40 -c 2 -o gpurun_out/prof_conv7x7 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-  tail -n 3 gpurun_out/ncu_full.log | cut -c 1-300
-  ls -la gpurun_out/*.ncu-rep
-fi
-if [ "${1:-}" = "multi" ]; then
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -n 3 | cut -c 1-900
-fi
+P=chainer_realtime_multi-person_pose_estimation_b200
+for lib in r0e1 r0e2 r1e2; do
+  echo "== lib $lib"
+  OPB_LIB_PATH=$PWD/$P/libopb_$lib.so OPB_PROFILE=1 timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline 2> gpurun_out/profile_$lib.txt | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('fps', round(d['value']), 'conv7x7 TF', round(d['roofline']['achieved']), 'chain ms', round(d['extra']['conv_chain_ms'],2))"
+  tail -n 44 gpurun_out/profile_$lib.txt | grep -E "conv1_2|conv2_1|conv3_2|Mconv1 |Mconv7x7|Mconv6|total" | head -7
+done
