@@ -231,7 +231,7 @@ __device__ __forceinline__ void tmem_load_group(uint32_t taddr, float (&f)[CW]) 
   }
 }
 
-template <int KS, int BN, int MT, int NSA, int NSB, int ACC_STAGES, bool DRAIN>
+template <int KS, int BN, int MT, int NSA, int NSB, int ACC_STAGES, bool DRAIN, bool BRES = false>
 __global__ void __launch_bounds__(DRAIN ? kConvThreads : kConvThreads2, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                     const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -315,10 +315,14 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                                x0 + mt * 8 + s - PAD, y0 - PAD, n);
             if (++sa == NSA) { sa = 0; pa ^= 1; }
             for (int r = 0; r < KS; ++r) {
-              ptx::mbar_wait(&b_empty[sb], pb ^ 1);
-              ptx::mbar_expect_tx(&b_full[sb], Cfg::B_STAGE_BYTES);
-              ptx::tma_load_2d(smemB + sb * Cfg::B_STAGE_BYTES, tmB, &b_full[sb],
-                               (r * KS + s) * P.b_tap_stride + bk, nb * BN);
+              // BRES: the whole weight matrix (NSB = taps x chunks stages) stays resident in shared
+              // memory; it is fetched once, by the CTA's first tile
+              if (!BRES || tile == static_cast<int>(blockIdx.x)) {
+                ptx::mbar_wait(&b_empty[sb], pb ^ 1);
+                ptx::mbar_expect_tx(&b_full[sb], Cfg::B_STAGE_BYTES);
+                ptx::tma_load_2d(smemB + sb * Cfg::B_STAGE_BYTES, tmB, &b_full[sb],
+                                 (r * KS + s) * P.b_tap_stride + bk, nb * BN);
+              }
               if (++sb == NSB) { sb = 0; pb ^= 1; }
             }
           }
@@ -354,8 +358,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const uint64_t a_st = a_desc0 + static_cast<uint64_t>((sa * Cfg::A_STAGE_BYTES) >> 4);
 #pragma unroll
             for (int r = 0; r < KS; ++r) {
-              ptx::mbar_wait(&b_full[sb], pb);
-              ptx::tc_fence_after();
+              if (!BRES || tile == static_cast<int>(blockIdx.x)) {
+                ptx::mbar_wait(&b_full[sb], pb);
+                ptx::tc_fence_after();
+              }
               const uint64_t b_st = b_desc0 + static_cast<uint64_t>((sb * Cfg::B_STAGE_BYTES) >> 4);
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
@@ -368,7 +374,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 }
               }
               accumulate = 1;
-              ptx::mma_commit(&b_empty[sb]);
+              if (!BRES) ptx::mma_commit(&b_empty[sb]);
               if (++sb == NSB) { sb = 0; pb ^= 1; }
             }
             ptx::mma_commit(&a_empty[sa]);

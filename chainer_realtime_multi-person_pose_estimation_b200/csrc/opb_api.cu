@@ -230,10 +230,10 @@ int make_w_map(opb_ctx* ctx, CUtensorMap* tm, const PackedW& w, int bn) {
 }
 
 // ------------------------------------------------------------------ conv launch
-template <int KS, int BN, int MT, int NSA, int NSB, int ACC, bool DRAIN = false>
+template <int KS, int BN, int MT, int NSA, int NSB, int ACC, bool DRAIN = false, bool BRES = false>
 int launch_conv_t(opb_ctx* ctx, const Op& op) {
   using Cfg = ConvCfg<KS, BN, MT, NSA, NSB, ACC>;
-  auto kern = conv_tcgen05_kernel<KS, BN, MT, NSA, NSB, ACC, DRAIN>;
+  auto kern = conv_tcgen05_kernel<KS, BN, MT, NSA, NSB, ACC, DRAIN, BRES>;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     OPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -294,10 +294,14 @@ int launch_conv(opb_ctx* ctx, const Op& op) {
     case 7 * 10000 + 128 * 10 + 2: return launch_conv_t<7, 128, 2, 3, 5, 2>(ctx, op);
     case 7 * 10000 + 256 * 10 + 1: return launch_conv_t<7, 256, 1, 3, 4, 2>(ctx, op);
     case 3 * 10000 + 64 * 10 + 1: return launch_conv_t<3, 64, 1, 3, 6, 2>(ctx, op);
-    case 3 * 10000 + 64 * 10 + 2: return (getenv("OPB_K3") && atoi(getenv("OPB_K3"))) ? launch_conv_t<3, 64, 2, 5, 4, 2>(ctx, op) : launch_conv_t<3, 64, 2, 3, 6, 2>(ctx, op);
+    case 3 * 10000 + 64 * 10 + 2:
+      // conv1_2 (64->64): the 72 KB weight matrix stays resident in shared memory (9 stages, one per tap)
+      if (op.P.n_pairs == 1 && op.P.n_problems == 1 && op.P.n_blocks == 1 && !(getenv("OPB_NO_BRES") && atoi(getenv("OPB_NO_BRES"))))
+        return launch_conv_t<3, 64, 2, 3, 9, 2, false, true>(ctx, op);
+      return launch_conv_t<3, 64, 2, 3, 6, 2>(ctx, op);
     case 7 * 10000 + 64 * 10 + 2: return launch_conv_t<7, 64, 2, 3, 6, 2>(ctx, op);
     case 3 * 10000 + 128 * 10 + 1: return launch_conv_t<3, 128, 1, 3, 6, 2>(ctx, op);
-    case 3 * 10000 + 128 * 10 + 2: return (getenv("OPB_K3") && atoi(getenv("OPB_K3"))) ? launch_conv_t<3, 128, 2, 4, 4, 2>(ctx, op) : launch_conv_t<3, 128, 2, 3, 6, 2>(ctx, op);
+    case 3 * 10000 + 128 * 10 + 2: return launch_conv_t<3, 128, 2, 3, 6, 2>(ctx, op);
     case 3 * 10000 + 256 * 10 + 1: return launch_conv_t<3, 256, 1, 3, 4, 2>(ctx, op);
     case 1 * 10000 + 128 * 10 + 1: return launch_conv_t<1, 128, 1, 4, 6, 2>(ctx, op);
     case 1 * 10000 + 256 * 10 + 1: return launch_conv_t<1, 256, 1, 4, 4, 2>(ctx, op);
@@ -658,9 +662,12 @@ int get_post(opb_ctx* ctx, int n, int H, int W, PostWs** out) {
 
 int launch_upsample(opb_ctx* ctx, const float* in, int planes, int h, int w, float* out, int H, int W) {
   const int ppb = 19;
-  dim3 grid((W + 31) / 32, (H + 7) / 8, (planes + ppb - 1) / ppb), block(32, 8);
+  dim3 block(32, 8);
+  const bool v4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  dim3 grid(v4 ? (W + 127) / 128 : (W + 31) / 32, (H + 7) / 8, (planes + ppb - 1) / ppb);
   if (grid.z > 65535) OPB_FAIL(ctx, OPB_ERR_ARG, "too many planes");
-  upsample_bilinear_ac_kernel<<<grid, block, 0, ctx->stream>>>(in, planes, h, w, out, H, W, ppb);
+  if (v4) upsample_bilinear_ac_v4_kernel<<<grid, block, 0, ctx->stream>>>(in, planes, h, w, out, H, W, ppb);
+  else upsample_bilinear_ac_kernel<<<grid, block, 0, ctx->stream>>>(in, planes, h, w, out, H, W, ppb);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   return OPB_OK;

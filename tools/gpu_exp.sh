@@ -1,9 +1,9 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-P=chainer_realtime_multi-person_pose_estimation_b200
-for lib in r0e1 r0e2 r1e2; do
-  echo "== lib $lib"
-  OPB_LIB_PATH=$PWD/$P/libopb_$lib.so OPB_PROFILE=1 timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline 2> gpurun_out/profile_$lib.txt | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('fps', round(d['value']), 'conv7x7 TF', round(d['roofline']['achieved']), 'chain ms', round(d['extra']['conv_chain_ms'],2))"
-  tail -n 44 gpurun_out/profile_$lib.txt | grep -E "conv1_2|conv2_1|conv3_2|Mconv1 |Mconv7x7|Mconv6|total" | head -7
+timeout 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_postprocess.py -m gpu -q --timeout 120 -k "conv or upsample" 2>&1 | tail -n 3
+for cfg in "OPB_NO_BRES=1" "OPB_NO_BRES=0"; do
+  echo "== bench $cfg"
+  env $cfg OPB_PROFILE=1 timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline 2> gpurun_out/profile.txt | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('fps', round(d['value']), 'e2e', round(d['e2e']['value']), 'chain ms', round(d['extra']['conv_chain_ms'],2), 'paf_up', d['extra']['paf_upsample_integrate']['frac'])"
+  tail -n 44 gpurun_out/profile.txt | grep -E "conv1_1|conv1_2|conv2_1|upsample|total" | head -7
 done
