@@ -50,6 +50,8 @@ _SIGNATURES = {
                             C.POINTER(C.c_int)]),
     "opb_connections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                   C.c_double, C.c_void_p, C.c_int, C.c_void_p]),
+    "opb_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "opb_group": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                             C.POINTER(C.c_int)]),
     "opb_detect_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -210,6 +212,18 @@ class Engine(object):
             res.append(out[o:o + c].copy() if c else np.zeros((0, 3)))
             o += int(c)
         return res
+
+    def candidates(self, paf, cand_a, cand_b, img_len):
+        paf = np.ascontiguousarray(paf, np.float32)
+        _, h, w = paf.shape
+        a = np.ascontiguousarray(cand_a, np.float64).reshape(-1, 4)
+        b = np.ascontiguousarray(cand_b, np.float64).reshape(-1, 4)
+        cap = max(len(a) * len(b), 1)
+        out = np.empty((cap, 3), np.float64)
+        n = C.c_int(0)
+        self._check(self.lib.opb_candidates(self.ctx, _ptr(paf), h, w, _ptr(a), len(a), _ptr(b), len(b), float(img_len),
+                                            _ptr(out), cap, C.byref(n)))
+        return out[:n.value].copy()
 
     def group(self, all_connections, peaks):
         pk = np.ascontiguousarray(peaks, np.float64).reshape(-1, 5)

@@ -65,6 +65,7 @@ struct ConvParams {
   int n_pairs;           // number of 64-channel K chunk pairs
   int n_problems;        // 1 or 2 (grouped launch: the L1 / L2 branches of one stage)
   int b_tap_stride;      // K elements per filter tap in the packed weights
+  int pad_edge8;         // swap kernel: the last tile of a row is 8 (not 16) pixels wide
   int a_off[kMaxPairs];  // activation channel offset of chunk pair j
   int b_off[kMaxPairs];  // weight k offset (inside one tap) of chunk pair j
   ConvProblem prob[2];

@@ -1,0 +1,210 @@
+// conv_tcgen05_swap.cuh -- the implicit-GEMM conv with the operand ROLES SWAPPED, for layers whose
+// output-channel count is only 128 (the 7x7 128->128 refinement layers, 50 % of all FLOPs).
+//
+// Measured (profiles/): a tcgen05.mma of M=128 x N=128 x K=16 (64 tensor cycles) sustains ~69 % of
+// the cuBLAS peak in this pipeline, one of N=256 (128 cycles) ~83 %: the per-instruction issue /
+// operand-fetch overhead is amortised over twice the work.  Cout = 128 caps N at 128 when the
+// pixels are the M operand, so here the WEIGHTS are the M operand (A: 128 output channels) and a
+// 16 x 16 PIXEL tile is the N operand (B: 256 rows):   D[cout, pixel] += W[cout, k] * X[pixel, k]^T.
+//
+//   pixel operand  one TMA box {64 ch, 16 px, 16+k-1 rows}: shared-memory row index = row*16 + px,
+//                  i.e. 8-pixel groups (1024-byte swizzle atoms) follow each other with a constant
+//                  1024-byte stride, so the 256 pixels of filter row r are one contiguous K-major
+//                  operand starting r*2048 bytes into the box (the same trick as the A boxes of
+//                  conv_tcgen05.cuh).  The last tile of an image row uses an 8-pixel box (N = 128)
+//                  when <= 8 columns remain, so the column padding stays at 8-pixel granularity.
+//   weight operand box {64, 128 rows} per (tap, chunk), as before.
+//   accumulator    TMEM lane = output channel, column = pixel of the tile; 2 x 256 columns.
+//   epilogue       thread = one output channel; a warp holds 32 consecutive channels of one pixel,
+//                  so each store instruction writes 64 contiguous bytes of the NHWC row.
+#pragma once
+#include "conv_tcgen05.cuh"
+
+namespace opb {
+
+template <int KS, int NSP, int NSW>
+struct ConvSwapCfg {
+  static constexpr int RH = 16 + KS - 1;
+  static constexpr int P_STAGE_BYTES = RH * 16 * 128;      // 16-pixel-wide box
+  static constexpr int W_STAGE_BYTES = 128 * 128;
+  static constexpr int SMEM_BYTES = 1024 + NSP * P_STAGE_BYTES + NSW * W_STAGE_BYTES + 512;
+};
+
+template <int KS, int NSP, int NSW>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __grid_constant__ CUtensorMap tmP8_0,
+                         const __grid_constant__ CUtensorMap tmW_0, const __grid_constant__ CUtensorMap tmP16_1,
+                         const __grid_constant__ CUtensorMap tmP8_1, const __grid_constant__ CUtensorMap tmW_1,
+                         const __grid_constant__ ConvParams P) {
+  using Cfg = ConvSwapCfg<KS, NSP, NSW>;
+  constexpr int PAD = (KS - 1) / 2;
+  constexpr int ACC_STAGES = 2;
+  constexpr uint32_t IDESC256 = ptx::umma_idesc_f16(128, 256);
+  constexpr uint32_t IDESC128 = ptx::umma_idesc_f16(128, 128);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smemP = smem;
+  uint8_t* smemW = smem + NSP * Cfg::P_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemW + NSW * Cfg::W_STAGE_BYTES);
+  uint64_t* p_full = bars;
+  uint64_t* p_empty = p_full + NSP;
+  uint64_t* w_full = p_empty + NSP;
+  uint64_t* w_empty = w_full + NSW;
+  uint64_t* t_full = w_empty + NSW;
+  uint64_t* t_empty = t_full + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmP16_0);
+    ptx::prefetch_tensormap(&tmP8_0);
+    ptx::prefetch_tensormap(&tmW_0);
+    if (P.n_problems > 1) {
+      ptx::prefetch_tensormap(&tmP16_1);
+      ptx::prefetch_tensormap(&tmP8_1);
+      ptx::prefetch_tensormap(&tmW_1);
+    }
+    for (int i = 0; i < NSP; ++i) { ptx::mbar_init(&p_full[i], 1); ptx::mbar_init(&p_empty[i], 1); }
+    for (int i = 0; i < NSW; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 128); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // P.tiles_x counts 16-wide tiles plus (if P.pad_edge8) one trailing 8-wide tile
+  const int m_tiles = P.N * P.tiles_y * P.tiles_x;
+  const int tiles_per_problem = P.n_blocks * m_tiles;
+  const int total_tiles = P.n_problems * tiles_per_problem;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      uint32_t sp = 0, pp = 0, sw = 0, pw = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int p = tile / tiles_per_problem;
+        int rem = tile - p * tiles_per_problem;
+        const int nb = rem / m_tiles;
+        rem -= nb * m_tiles;
+        const int n = rem / (P.tiles_y * P.tiles_x);
+        rem -= n * (P.tiles_y * P.tiles_x);
+        const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+        const int y0 = ty * 16, x0 = tx * 16;
+        const bool narrow = P.pad_edge8 && (tx == P.tiles_x - 1);
+        const CUtensorMap* tmP = narrow ? (p ? &tmP8_1 : &tmP8_0) : (p ? &tmP16_1 : &tmP16_0);
+        const CUtensorMap* tmW = p ? &tmW_1 : &tmW_0;
+        const uint32_t p_bytes = narrow ? Cfg::P_STAGE_BYTES / 2 : Cfg::P_STAGE_BYTES;
+        for (int j = 0; j < P.n_pairs; ++j) {
+          const int ac = P.a_off[j], bk = P.b_off[j];
+          for (int s = 0; s < KS; ++s) {
+            ptx::mbar_wait(&p_empty[sp], pp ^ 1);
+            ptx::mbar_expect_tx(&p_full[sp], p_bytes);
+            ptx::tma_load_4d(smemP + sp * Cfg::P_STAGE_BYTES, tmP, &p_full[sp], ac, x0 + s - PAD, y0 - PAD, n);
+            if (++sp == NSP) { sp = 0; pp ^= 1; }
+            for (int r = 0; r < KS; ++r) {
+              ptx::mbar_wait(&w_empty[sw], pw ^ 1);
+              ptx::mbar_expect_tx(&w_full[sw], Cfg::W_STAGE_BYTES);
+              ptx::tma_load_2d(smemW + sw * Cfg::W_STAGE_BYTES, tmW, &w_full[sw], (r * KS + s) * P.b_tap_stride + bk,
+                               nb * 128);
+              if (++sw == NSW) { sw = 0; pw ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      uint32_t sp = 0, pp = 0, sw = 0, pw = 0, acc = 0, pacc = 0;
+      const uint64_t p_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemP), 1024);
+      const uint64_t w_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemW), 1024);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tx = (tile % m_tiles) % (P.tiles_y * P.tiles_x) % P.tiles_x;
+        const bool narrow = P.pad_edge8 && (tx == P.tiles_x - 1);
+        const uint32_t idesc = narrow ? IDESC128 : IDESC256;
+        const uint32_t row_pitch16 = narrow ? (1024 >> 4) : (2048 >> 4);   // bytes per image row of the box, >> 4
+        ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d = tmem_base + acc * 256;
+        uint32_t accumulate = 0;
+        for (int j = 0; j < P.n_pairs; ++j) {
+          for (int s = 0; s < KS; ++s) {
+            ptx::mbar_wait(&p_full[sp], pp);
+            ptx::tc_fence_after();
+            const uint64_t p_st = p_desc0 + static_cast<uint64_t>((sp * Cfg::P_STAGE_BYTES) >> 4);
+#pragma unroll
+            for (int r = 0; r < KS; ++r) {
+              ptx::mbar_wait(&w_full[sw], pw);
+              ptx::tc_fence_after();
+              const uint64_t w_st = w_desc0 + static_cast<uint64_t>((sw * Cfg::W_STAGE_BYTES) >> 4);
+              const uint64_t pd0 = p_st + static_cast<uint64_t>(r * row_pitch16);
+              ptx::mma_f16_ss(d, w_st, pd0, idesc, accumulate);
+#pragma unroll
+              for (int k = 1; k < 4; ++k) ptx::mma_f16_ss_acc(d, w_st + (k * 32 >> 4), pd0 + (k * 32 >> 4), idesc);
+              accumulate = 1;
+              ptx::mma_commit(&w_empty[sw]);
+              if (++sw == NSW) { sw = 0; pw ^= 1; }
+            }
+            ptx::mma_commit(&p_empty[sp]);
+            if (++sp == NSP) { sp = 0; pp ^= 1; }
+          }
+        }
+        ptx::mma_commit(&t_full[acc]);
+        if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================ epilogue: thread = output channel
+    const int q = warp & 3;
+    uint32_t acc = 0, pacc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int p = tile / tiles_per_problem;
+      int rem = tile - p * tiles_per_problem;
+      const int nb = rem / m_tiles;
+      rem -= nb * m_tiles;
+      const int n = rem / (P.tiles_y * P.tiles_x);
+      rem -= n * (P.tiles_y * P.tiles_x);
+      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+      const int y0 = ty * 16, x0 = tx * 16;
+      const bool narrow = P.pad_edge8 && (tx == P.tiles_x - 1);
+      const int wshift = narrow ? 3 : 4;                 // pixels per tile row = 8 or 16
+      const int n_pix = narrow ? 128 : 256;
+      const ConvProblem& pr = P.prob[p];
+      const int ch = nb * 128 + q * 32 + lane;           // this thread's output channel
+      const bool ch_ok = ch < pr.cout_valid;
+      const float bias = ch_ok ? __ldg(pr.bias + ch) : 0.f;
+      __half* out_c = pr.out + pr.out_coff + ch;
+      ptx::mbar_wait(&t_full[acc], pacc);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < n_pix; c0 += 32) {
+        float f[32];
+        tmem_load_group<32>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + c0, f);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int pix = c0 + i;
+          const int y = y0 + (pix >> wshift), x = x0 + (pix & ((1 << wshift) - 1));
+          float v = f[i] + bias;
+          v = pr.relu ? fmaxf(v, 0.f) : v;
+          if (ch_ok && y < P.H && x < P.W)
+            out_c[((static_cast<size_t>(n) * P.H + y) * P.W + x) * pr.out_cstride] = __float2half_rn(v);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&t_empty[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace opb

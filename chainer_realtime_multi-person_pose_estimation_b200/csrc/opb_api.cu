@@ -19,6 +19,7 @@
 #include "conv_first.cuh"
 #include "conv_tcgen05.cuh"
 #include "conv_tcgen05_pair.cuh"
+#include "conv_tcgen05_swap.cuh"
 #include "paf.cuh"
 #include "peaks.cuh"
 #include "pool.cuh"
@@ -64,6 +65,8 @@ struct Op {
   int ks = 0, bn = 0, mt = 1;
   bool drain = false;
   bool pair = false;   // cta_group::2 kernel (cluster of 2 CTAs)
+  bool swap = false;   // weights-as-A kernel (16x16 pixel tiles as the N=256 operand)
+  CUtensorMap tmP16[2];
   CUtensorMap tmA[2], tmB[2];
   ConvParams P;
   int grid = 0;
@@ -202,12 +205,12 @@ void free_all(std::vector<void*>& v) {
 }
 
 // ------------------------------------------------------------------ tensor maps
-int make_act_map(opb_ctx* ctx, CUtensorMap* tm, const Act& a, int coff, int ks) {
+int make_act_map(opb_ctx* ctx, CUtensorMap* tm, const Act& a, int coff, int ks, int box_w = 8) {
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.Ctot - coff), static_cast<cuuint64_t>(a.W),
                         static_cast<cuuint64_t>(a.H), static_cast<cuuint64_t>(a.N)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(a.Ctot) * 2, static_cast<cuuint64_t>(a.W) * a.Ctot * 2,
                            static_cast<cuuint64_t>(a.H) * a.W * a.Ctot * 2};
-  cuuint32_t box[4] = {64, 8, static_cast<cuuint32_t>(16 + ks - 1), 1};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(16 + ks - 1), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.p + coff, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -260,8 +263,29 @@ int launch_conv_pair_t(opb_ctx* ctx, const Op& op) {
   return OPB_OK;
 }
 
+template <int KS, int NSP, int NSW>
+int launch_conv_swap_t(opb_ctx* ctx, const Op& op) {
+  using Cfg = ConvSwapCfg<KS, NSP, NSW>;
+  auto kern = conv_tcgen05_swap_kernel<KS, NSP, NSW>;
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    OPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[ctx->device & 63] = true;
+  }
+  kern<<<op.grid, kConvThreads, Cfg::SMEM_BYTES, ctx->stream>>>(op.tmP16[0], op.tmA[0], op.tmB[0], op.tmP16[1], op.tmA[1],
+                                                                op.tmB[1], op.P);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  return OPB_OK;
+}
+
 int launch_conv(opb_ctx* ctx, const Op& op) {
   const int key = op.ks * 10000 + op.bn * 10 + op.mt;
+  if (op.swap) {
+    if (op.ks == 7) return launch_conv_swap_t<7, 3, 5>(ctx, op);
+    if (op.ks == 3) return launch_conv_swap_t<3, 3, 6>(ctx, op);
+    OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "no swap-mode conv variant");
+  }
   if (op.pair) {    // CTA-pair kernels (fast precision)
     switch (key) {
       case 7 * 10000 + 128 * 10 + 2: return launch_conv_pair_t<7, 128, 2, 3, 6, 2>(ctx, op);
@@ -436,11 +460,27 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
       if (op.bn == 256 || op.ks == 1) op.mt = 1;
     }
   }
+  {  // weights-as-A kernel (N = 256-pixel tiles) for the Cout=128 7x7 layers: measured 6.63 -> 5.23 ms on the
+     // 20 grouped launches (1452 TFLOP/s).  OPB_SWAP=0 disables, bit 1 also enables it for 3x3 (slower there:
+     // with K = 1152 the channel-per-thread epilogue dominates).
+    const char* e = getenv("OPB_SWAP");
+    const int want = e ? atoi(e) : 1;
+    if (want && !split && !op.pair && per_problem_cout_pad % 128 == 0 && op.bn == 128 &&
+        (op.ks == 7 || (op.ks == 3 && (want & 2))) && !s.pool && !s.out32[0] && a0.W >= 16) {
+      op.swap = true;
+      op.mt = 1;
+    }
+  }
   std::memset(&op.P, 0, sizeof(op.P));
   ConvParams& P = op.P;
   P.N = a0.N; P.H = a0.H; P.W = a0.W;
   const int tile_w = (op.pair ? 16 : 8) * op.mt;
   P.tiles_x = (a0.W + tile_w - 1) / tile_w;
+  if (op.swap) {
+    const int rem = a0.W % 16;
+    P.pad_edge8 = (rem >= 1 && rem <= 8) ? 1 : 0;
+    P.tiles_x = a0.W / 16 + (rem ? 1 : 0);
+  }
   P.tiles_y = (a0.H + 15) / 16;
   P.n_blocks = per_problem_cout_pad / op.bn;
   P.n_problems = s.n_problems;
@@ -463,6 +503,10 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     if (split && s.in[p]->C != a0.C) OPB_FAIL(ctx, OPB_ERR_ARG, "grouped problems must share the lo-plane offset");
     int rc = make_act_map(ctx, &op.tmA[p], *s.in[p], s.in_coff[p], op.ks);
     if (rc) return rc;
+    if (op.swap) {
+      rc = make_act_map(ctx, &op.tmP16[p], *s.in[p], s.in_coff[p], op.ks, 16);
+      if (rc) return rc;
+    }
     rc = make_w_map(ctx, &op.tmB[p], w, op.pair ? op.bn / 2 : op.bn);
     if (rc) return rc;
     ConvProblem& pr = P.prob[p];
@@ -476,7 +520,7 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     pr.relu = s.relu;
     pr.pool = s.pool;
   }
-  if (s.n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; P.prob[1] = P.prob[0]; }
+  if (s.n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; op.tmP16[1] = op.tmP16[0]; P.prob[1] = P.prob[0]; }
   const int total_tiles = P.n_problems * P.n_blocks * P.N * P.tiles_y * P.tiles_x;
   op.grid = op.pair ? 2 * std::min(total_tiles, ctx->num_sms / 2) : std::min(total_tiles, ctx->num_sms);
   ch->ops.push_back(op);
@@ -1100,6 +1144,58 @@ int opb_connections(opb_ctx* ctx, const float* paf, int paf_loc, int h, int w, c
   if (st) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "candidate / per-type capacity exceeded (status " + std::to_string(st) +
                                               "); raise opb_params.max_candidates");
   return download_connections(ctx, ws, 0, conn_out, conn_cap, conn_counts);
+}
+
+int opb_candidates(opb_ctx* ctx, const float* paf, int h, int w, const double* cand_a, int n_a, const double* cand_b,
+                   int n_b, double img_len, double* out, int out_cap, int* n_out) {
+  if (!ctx || !paf || !out || !n_out || (n_a > 0 && !cand_a) || (n_b > 0 && !cand_b)) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  PostWs* ws;
+  int rc = get_post(ctx, 1, h, w, &ws);
+  if (rc) return rc;
+  *n_out = 0;
+  if (n_a == 0 || n_b == 0) return OPB_OK;
+  // limb 0 of the table joins joint types limbs[0][0] -> limbs[0][1]; its PAF channels are 0 and 1
+  const int ja = ctx->pc.limbs[0][0], jb = ctx->pc.limbs[0][1];
+  std::vector<double> pk(static_cast<size_t>(n_a + n_b) * 5);
+  for (int i = 0; i < n_a + n_b; ++i) {
+    const double* src = (i < n_a) ? cand_a + i * 4 : cand_b + (i - n_a) * 4;
+    pk[i * 5 + 0] = (i < n_a) ? ja : jb;
+    pk[i * 5 + 1] = src[0]; pk[i * 5 + 2] = src[1]; pk[i * 5 + 3] = src[2]; pk[i * 5 + 4] = i;
+  }
+  if ((rc = upload_peaks(ctx, ws, pk.data(), n_a + n_b))) return rc;
+  OPB_CUDA(ctx, cudaMemsetAsync(ws->pafs, 0, sizeof(float) * 38 * static_cast<size_t>(h) * w, ctx->stream));
+  if ((rc = copy_in(ctx, ws->pafs, paf, sizeof(float) * 2 * static_cast<size_t>(h) * w, OPB_HOST))) return rc;
+  OPB_CUDA(ctx, cudaMemsetAsync(ws->cand_counts, 0, sizeof(int) * 19, ctx->stream));
+  dim3 g1(8, 1, 1);
+  paf_candidates_kernel<<<g1, 128, 0, ctx->stream>>>(ws->pafs, h, w, ws->peaks, ws->idx_list, ws->type_start,
+                                                     ctx->prm.max_peaks, 18, ctx->pc, img_len, ws->cands,
+                                                     ws->cand_counts, ctx->prm.max_candidates);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  int cnt = 0;
+  OPB_CUDA(ctx, cudaMemcpyAsync(&cnt, ws->cand_counts, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (cnt > ctx->prm.max_candidates) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "more candidates than opb_params.max_candidates");
+  if (cnt > out_cap) OPB_FAIL(ctx, OPB_ERR_CAPACITY, "out too small");
+  std::vector<Candidate> cd(cnt);
+  if (cnt) {
+    OPB_CUDA(ctx, cudaMemcpyAsync(cd.data(), ws->cands, sizeof(Candidate) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  // presentation order only (the scores were computed on the device): descending score, ties in
+  // generation order (a-major, b-minor) = Python's stable sorted(..., reverse=True)
+  std::sort(cd.begin(), cd.end(), [](const Candidate& x, const Candidate& y) {
+    return x.score > y.score || (x.score == y.score && x.pair < y.pair);
+  });
+  for (int i = 0; i < cnt; ++i) {
+    const int a = cd[i].pair / n_b, b = cd[i].pair % n_b;
+    out[i * 3 + 0] = static_cast<double>(static_cast<int>(cand_a[a * 4 + 3]));
+    out[i * 3 + 1] = static_cast<double>(static_cast<int>(cand_b[b * 4 + 3]));
+    out[i * 3 + 2] = cd[i].score;
+  }
+  *n_out = cnt;
+  return OPB_OK;
 }
 
 int opb_group(opb_ctx* ctx, const double* conns, const int* conn_counts, const double* peaks, int n_peaks,

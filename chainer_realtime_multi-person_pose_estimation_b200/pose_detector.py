@@ -131,10 +131,10 @@ class PoseDetector(object):
         return self.engine.connections(np.asarray(pafs), all_peaks, img_len)
 
     def compute_candidate_connections(self, paf, cand_a, cand_b, img_len, params):
-        """The reference's per-limb helper (pose_detector.py:135-159).  On the device the PAF
-        scoring is fused with the greedy assignment inside compute_connections, so the
-        intermediate sorted candidate list is not exposed."""
-        raise NotImplementedError("fused into compute_connections on the device (opb_connections)")
+        """Sorted candidate list of ONE limb, [[id_a, id_b, score], ...] (pose_detector.py:135-159);
+        the PAF line integrals run on the device (opb_candidates)."""
+        rows = self.engine.candidates(np.asarray(paf), cand_a, cand_b, img_len)
+        return [[int(r[0]), int(r[1]), r[2]] for r in rows]
 
     def grouping_key_points(self, all_connections, candidate_peaks, params):
         return self.engine.group(all_connections, candidate_peaks)

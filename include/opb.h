@@ -135,6 +135,12 @@ int opb_peaks(opb_ctx* ctx, const float* heat, int heat_loc, int c_plus_1, int h
 int opb_connections(opb_ctx* ctx, const float* paf, int paf_loc, int h, int w, const double* peaks,
                     int n_peaks, double img_len, double* conn_out, int conn_cap, int* conn_counts);
 
+/* -- candidates of ONE limb: replaces compute_candidate_connections, pose_detector.py:135-159.
+ *    paf [2,H,W] float32 host; cand_a [n_a,4], cand_b [n_b,4] float64 rows (x, y, score, id).
+ *    out rows (id_a, id_b, score) float64, sorted by descending score (stable, :158).          */
+int opb_candidates(opb_ctx* ctx, const float* paf, int h, int w, const double* cand_a, int n_a,
+                   const double* cand_b, int n_b, double img_len, double* out, int out_cap, int* n_out);
+
 /* -- grouping: replaces grouping_key_points, pose_detector.py:183-250.
  *    subsets_out rows of 20 float64 (18 ids, score, count).                                  */
 int opb_group(opb_ctx* ctx, const double* conns, const int* conn_counts, const double* peaks,

@@ -203,3 +203,37 @@ def test_upsample_bicubic_vs_cv2(engine):
         ref = cv2.resize(np.ascontiguousarray(x.transpose(1, 2, 0)), (W, H), interpolation=cv2.INTER_CUBIC)
         ref = ref.transpose(2, 0, 1)
         assert np.abs(got - ref).max() <= 1e-5, (h, w, H, W, np.abs(got - ref).max())
+
+
+def test_candidate_connections_single_limb(engine):
+    """compute_candidate_connections (pose_detector.py:135-159) for one limb vs the oracle."""
+    g = load_golden("synth8_post_seed0.npz")
+    paf, heat, _ = pkg("synthetic").eight_person_maps(seed=0)
+    peaks = g["all_peaks"]
+    PD = pkg("pose_detector")
+    det = PD.PoseDetector.__new__(PD.PoseDetector)
+    det.engine = engine
+    for l in (0, 7, 14):
+        ja, jb = R.LIMBS[l]
+        ca = peaks[peaks[:, 0] == ja][:, 1:]
+        cb = peaks[peaks[:, 0] == jb][:, 1:]
+        ref = R.candidate_connections(paf[2 * l:2 * l + 2], ca, cb, 576)
+        got = det.compute_candidate_connections(paf[2 * l:2 * l + 2], ca, cb, 576, PD.params)
+        assert len(got) == len(ref)
+        assert np.array_equal(np.array(got, np.float64).reshape(-1, 3), ref)
+
+
+def test_capacity_errors_are_loud():
+    """Overflowing a device-side list raises (never truncates silently)."""
+    native = pkg("_native")
+    small = native.Engine(0, pkg("pose_detector").make_opb_params(max_peaks=32, max_candidates=64, max_persons=2))
+    rs = np.random.RandomState(0)
+    heat = (rs.standard_normal((19, 200, 200)) * 0.5).astype(np.float32)
+    with pytest.raises(native.OpbError):
+        small.peaks(heat)                               # > 32 peaks
+    paf, hm, _ = pkg("synthetic").eight_person_maps(seed=0)
+    g = load_golden("synth8_post_seed0.npz")
+    big = native.Engine(0, pkg("pose_detector").make_opb_params(max_peaks=8192, max_candidates=64, max_persons=2))
+    conns = big.connections(paf, g["all_peaks"], 576)    # 8 persons: <= 64 candidates per limb is enough
+    with pytest.raises(native.OpbError):
+        big.group(conns, g["all_peaks"])                # 8 persons do not fit max_persons = 2
