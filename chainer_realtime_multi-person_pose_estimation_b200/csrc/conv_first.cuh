@@ -136,3 +136,127 @@ conv_first_kernel(const uint8_t* __restrict__ x_u8, const float* __restrict__ x_
 }
 
 }  // namespace opb
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core variant (fast precision, uint8 frames): the 27-tap im2col row of every pixel is built
+// by its own thread (look-up table -> fp16) directly in the canonical K-major SWIZZLE_128B layout,
+// so conv1_1 becomes two tcgen05.mma (M = 128 pixels, N = 64 channels, K = 2 x 16) per 16 x 8
+// tile instead of 1728 FMAs per pixel; the kernel is then bound by its 128 B/pixel store.
+// One CTA = 128 threads, 64 TMEM columns, ~26 KB shared memory -> up to 8 CTAs per SM hide the
+// (synchronous) build -> MMA -> epilogue latency of each tile.
+#include "conv_tcgen05.cuh"
+
+namespace opb {
+
+// wth: [64][32] fp16 (row = output channel, k = (r*3+s)*3 + c, k >= 27 zero); bias [64] fp32
+__global__ void __launch_bounds__(128)
+conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict__ wth, const float* __restrict__ bias,
+                     __half* __restrict__ out, int N, int H, int W, int cstride) {
+  __shared__ __align__(1024) uint8_t sA[128 * 128];
+  __shared__ __align__(1024) uint8_t sB[64 * 128];
+  __shared__ __half s_lut[260];
+  __shared__ uint16_t s_idx[18 * 10 * 3];
+  __shared__ float s_bias[64];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // one-time setup
+  for (int i = tid; i < 257; i += 128)
+    s_lut[i] = (i < 256) ? __float2half_rn(__fsub_rn(__fdiv_rn(static_cast<float>(i), 255.f), 0.5f)) : __float2half(0.f);
+  if (tid < 64) {
+    s_bias[tid] = bias[tid];
+    // weight row `tid`: 4 chunks of 8 halfs, physical chunk = logical ^ (row & 7)
+    const uint4* src = reinterpret_cast<const uint4*>(wth + tid * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(sB + tid * 128 + ((j ^ (tid & 7)) * 16)) = src[j];
+#pragma unroll
+    for (int j = 4; j < 8; ++j) *reinterpret_cast<uint4*>(sB + tid * 128 + ((j ^ (tid & 7)) * 16)) = make_uint4(0, 0, 0, 0);
+  }
+  {  // the chunks 4..7 of A are never read (only k-steps 0 and 1 are issued) but keep them finite
+#pragma unroll
+    for (int j = 4; j < 8; ++j) *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) * 16)) = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) { ptx::mbar_init(&s_bar, 1); ptx::fence_barrier_init(); }
+  if (warp == 0) ptx::tmem_alloc<64>(&s_tmem);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(sA), 1024);
+  const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(sB), 1024);
+  constexpr uint32_t IDESC = ptx::umma_idesc_f16(128, 64);
+
+  const int tiles_x = (W + 7) >> 3, tiles_y = (H + 15) >> 4;
+  const int total = N * tiles_y * tiles_x;
+  const int hl = tid >> 3, wl = tid & 7;
+  uint32_t parity = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int n = tile / (tiles_y * tiles_x);
+    const int rem = tile - n * (tiles_y * tiles_x);
+    const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
+    // (1) halo tile of byte indices (256 = zero padding)
+    for (int i = tid; i < 18 * 10 * 3; i += 128) {
+      const int c = i % 3, q = i / 3;
+      const int xx = x0 - 1 + q % 10, yy = y0 - 1 + q / 10;
+      uint16_t v = 256;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x_u8[((static_cast<size_t>(n) * H + yy) * W + xx) * 3 + c];
+      s_idx[i] = v;
+    }
+    __syncthreads();
+    // (2) this thread's im2col row: k = (r*3+s)*3 + c  ->  27 consecutive idx of each halo row segment
+    {
+      uint32_t pk[16];                  // 32 halfs packed in registers (27 taps + 5 zeros)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k0 = 2 * i, k1 = 2 * i + 1;
+        const __half lo = (k0 < 27) ? s_lut[s_idx[((hl + k0 / 9) * 10 + wl) * 3 + k0 % 9]] : __float2half(0.f);
+        const __half hi = (k1 < 27) ? s_lut[s_idx[((hl + k1 / 9) * 10 + wl) * 3 + k1 % 9]] : __float2half(0.f);
+        const __half2 t = __halves2half2(lo, hi);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&t);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) * 16)) =
+            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+    ptx::fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core (async proxy)
+    ptx::tc_fence_before();
+    __syncthreads();
+    // (3) two MMAs, one elected thread
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      ptx::mma_f16_ss(tmem, a_desc, b_desc, IDESC, 0u);
+      ptx::mma_f16_ss_acc(tmem, a_desc + 2, b_desc + 2, IDESC);
+      ptx::mma_commit(&s_bar);
+    }
+    ptx::mbar_wait(&s_bar, parity);
+    parity ^= 1;
+    ptx::tc_fence_after();
+    // (4) epilogue: bias + ReLU + fp16, 128 contiguous bytes per pixel
+    const int y = y0 + hl, x = x0 + wl;
+    const bool valid = (y < H) && (x < W);
+    __half* o = out + ((static_cast<size_t>(n) * H + y) * W + x) * cstride;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      float f[32];
+      tmem_load_group<32>(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, f);
+      uint32_t h[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const __half2 t = __floats2half2_rn(fmaxf(f[2 * i] + s_bias[c0 + 2 * i], 0.f),
+                                            fmaxf(f[2 * i + 1] + s_bias[c0 + 2 * i + 1], 0.f));
+        h[i] = *reinterpret_cast<const uint32_t*>(&t);
+      }
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(o + c0 + g * 8) = make_uint4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();                   // s_idx / sA / TMEM are free for the next tile
+  }
+  if (warp == 0) ptx::tmem_dealloc<64>(tmem);
+}
+
+}  // namespace opb

@@ -92,7 +92,7 @@ struct PostWs {           // post-process workspace for (N, map_h, map_w)
   float* pafs = nullptr;      // [N][38][H][W]
   float* heat = nullptr;      // [N][19][H][W]
   PeakKey* keys = nullptr;    // [N][max_peaks]
-  float* tile_max = nullptr;  // [N*18][tiles_y][tiles_x]
+  float* tile_max = nullptr;  // cell maxima [N*18][ceil(H/8)][ceil(W/8)]
   int* peak_counts = nullptr; // [N]
   PeakD* peaks = nullptr;     // [N][max_peaks]
   int* idx_list = nullptr;
@@ -129,6 +129,7 @@ struct opb_ctx {
   std::map<std::string, HostLayer> host_layers;
   std::map<std::string, PackedW> packed;
   float* w_first = nullptr;  // conv1_1 [27][64] fp32
+  __half* w_first_h = nullptr;  // conv1_1 [64][32] fp16 (tensor-core variant)
   float* b_first = nullptr;
   std::vector<void*> weight_allocs;
   std::map<long long, Chain*> chains;
@@ -349,6 +350,15 @@ int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
     return OPB_OK;
   }
   // OP_FIRST
+  if (op.C == 1 && ctx->precision == OPB_PRECISION_FAST && !(getenv("OPB_NO_TC_FIRST") && atoi(getenv("OPB_NO_TC_FIRST")))) {
+    const int tiles = op.N * ((op.H + 15) / 16) * ((op.W + 7) / 8);
+    const int grid = std::min(tiles, ctx->num_sms * 8);
+    conv_first_tc_kernel<<<grid, 128, 0, ctx->stream>>>(ch->img_u8_src ? ch->img_u8_src : ch->img_u8, ctx->w_first_h,
+                                                        ctx->b_first, op.out, op.N, op.H, op.W, op.cstride);
+    ctx->launches++;
+    OPB_CUDA(ctx, cudaGetLastError());
+    return OPB_OK;
+  }
   const int tiles = op.N * ((op.H + CF_TH - 1) / CF_TH) * ((op.W + CF_TW - 1) / CF_TW);
   const int grid = std::min(tiles, ctx->num_sms * 8);
   conv_first_kernel<<<grid, 256, 0, ctx->stream>>>(op.C == 1 ? (ch->img_u8_src ? ch->img_u8_src : ch->img_u8) : nullptr,
@@ -683,7 +693,7 @@ int get_post(opb_ctx* ctx, int n, int H, int W, PostWs** out) {
   RC(dev_alloc(ctx, &ws->pafs, static_cast<size_t>(n) * 38 * H * W, ws->allocs, false));
   RC(dev_alloc(ctx, &ws->heat, static_cast<size_t>(n) * 19 * H * W, ws->allocs, false));
   RC(dev_alloc(ctx, &ws->keys, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
-  RC(dev_alloc(ctx, &ws->tile_max, static_cast<size_t>(n) * 18 * ((H + PK_TY - 1) / PK_TY) * ((W + PK_TX - 1) / PK_TX), ws->allocs));
+  RC(dev_alloc(ctx, &ws->tile_max, static_cast<size_t>(n) * 18 * ((H + PK_CELL - 1) / PK_CELL) * ((W + PK_CELL - 1) / PK_CELL), ws->allocs));
   RC(dev_alloc(ctx, &ws->peak_counts, n, ws->allocs));
   RC(dev_alloc(ctx, &ws->peaks, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
   RC(dev_alloc(ctx, &ws->idx_list, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
@@ -732,7 +742,8 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
   }
   dim3 grid((W + PK_TX - 1) / PK_TX, (H + PK_TY - 1) / PK_TY, n * c_use);
   if (grid.z > 65535) OPB_FAIL(ctx, OPB_ERR_ARG, "batch too large for the peaks grid");
-  tile_max_kernel<<<grid, 256, 0, ctx->stream>>>(heat, c_total, c_use, H, W, ws->tile_max);
+  cell_max_kernel<<<grid, 256, 0, ctx->stream>>>(heat, c_total, c_use, H, W, ws->tile_max, (H + PK_CELL - 1) / PK_CELL,
+                                                 (W + PK_CELL - 1) / PK_CELL);
   ctx->launches++;
   prof_mark(ctx, "tile_max");
   if (ctx->taps.radius == PK_R_FAST)
@@ -957,6 +968,13 @@ int opb_finalize_weights(opb_ctx* ctx, int precision_mode) {
     for (int o = 0; o < 64; ++o)
       for (int c = 0; c < 3; ++c)
         for (int t = 0; t < 9; ++t) wt[(t * 3 + c) * 64 + o] = L.W[(static_cast<size_t>(o) * 3 + c) * 9 + t];
+    std::vector<__half> wh(64 * 32, __float2half(0.f));
+    for (int o = 0; o < 64; ++o)
+      for (int c = 0; c < 3; ++c)
+        for (int t = 0; t < 9; ++t) wh[o * 32 + t * 3 + c] = __float2half_rn(L.W[(static_cast<size_t>(o) * 3 + c) * 9 + t]);
+    if ((rc = dev_alloc(ctx, &ctx->w_first_h, wh.size(), ctx->weight_allocs, false))) return rc;
+    OPB_CUDA(ctx, cudaMemcpyAsync(ctx->w_first_h, wh.data(), wh.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+    OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if ((rc = dev_alloc(ctx, &ctx->w_first, wt.size(), ctx->weight_allocs, false))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->b_first, 64, ctx->weight_allocs, false))) return rc;
     OPB_CUDA(ctx, cudaMemcpyAsync(ctx->w_first, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice, ctx->stream));

@@ -45,29 +45,32 @@ struct GaussTaps {
   int radius;
 };
 
-// Per-tile maxima of the raw heat maps: tile_max[(img*c_use + c)][ty][tx] over PK_TY x PK_TX pixels.
-// One coalesced pass (each pixel read once); lets smooth_nms_kernel drop inactive tiles before
-// it touches memory.
+// Maxima of the raw heat maps over PK_CELL x PK_CELL pixel cells: cell_max[plane][cy][cx].
+// One coalesced pass (each pixel read once); smooth_nms_kernel tests the cells overlapping its
+// input window BEFORE loading it, so tiles far from every blob cost nothing.
+constexpr int PK_CELL = 8;
 __global__ void __launch_bounds__(256)
-tile_max_kernel(const float* __restrict__ heat, int c_total, int c_use, int H, int W, float* __restrict__ tile_max) {
+cell_max_kernel(const float* __restrict__ heat, int c_total, int c_use, int H, int W, float* __restrict__ cell_max,
+                int cells_y, int cells_x) {
   const int plane = blockIdx.z;
   const int img = plane / c_use, c = plane - img * c_use;
   const int x0 = blockIdx.x * PK_TX, y0 = blockIdx.y * PK_TY;
   const float* src = heat + (static_cast<size_t>(img) * c_total + c) * H * W;
+  // thread t -> cell (t / 8 % .. ): 16 x 64 pixels = 2 x 8 cells of 64 pixels; 16 threads per cell
+  const int cell = threadIdx.x >> 4, sub = threadIdx.x & 15;          // 16 cells, 16 threads each
+  const int cy = cell >> 3, cx = cell & 7;
   float m = -3.0e38f;
-  for (int i = threadIdx.x; i < PK_TY * PK_TX; i += blockDim.x) {
-    const int y = y0 + i / PK_TX, x = x0 + i % PK_TX;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int e = sub * 4 + k;                                         // 64 pixels of the cell
+    const int y = y0 + cy * PK_CELL + (e >> 3), x = x0 + cx * PK_CELL + (e & 7);
     if (y < H && x < W) m = fmaxf(m, __ldg(src + static_cast<size_t>(y) * W + x));
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  __shared__ float s_m[8];
-  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, s_m[i]);
-    tile_max[(static_cast<size_t>(plane) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = m;
-  }
+  for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const int gy = blockIdx.y * (PK_TY / PK_CELL) + cy, gx = blockIdx.x * (PK_TX / PK_CELL) + cx;
+  if (sub == 0 && gy < cells_y && gx < cells_x)
+    cell_max[(static_cast<size_t>(plane) * cells_y + gy) * cells_x + gx] = m;
 }
 
 // heat: [n_img][c_total][H][W] f32, only the first `c_use` channels of each image are processed.
@@ -89,16 +92,19 @@ smooth_nms_kernel(const float* __restrict__ heat, int c_total, int c_use, int H,
                   const float* __restrict__ tile_max) {
   const int R = (RT > 0) ? RT : taps.radius;
   const float skip_below = (thresh > 0.f) ? thresh * 0.999f : thresh * 1.001f - 1e-30f;
-  if (tile_max != nullptr && R + 1 <= PK_TY) {
-    const float* tm = tile_max + static_cast<size_t>(blockIdx.z) * gridDim.y * gridDim.x;
+  if (tile_max != nullptr) {
+    // cells overlapping the (clamped) input window [y0-1-R, y0+PK_TY+R] x [x0-1-R, x0+PK_TX+R]; reflected
+    // border samples are copies of in-image pixels within R of the border, i.e. inside the clamped window
+    const int cells_y = (H + PK_CELL - 1) / PK_CELL, cells_x = (W + PK_CELL - 1) / PK_CELL;
+    const int wy0 = max(static_cast<int>(blockIdx.y) * PK_TY - 1 - R, 0), wy1 = min(static_cast<int>(blockIdx.y) * PK_TY + PK_TY + R, H - 1);
+    const int wx0 = max(static_cast<int>(blockIdx.x) * PK_TX - 1 - R, 0), wx1 = min(static_cast<int>(blockIdx.x) * PK_TX + PK_TX + R, W - 1);
+    const int cy0 = wy0 / PK_CELL, cy1 = wy1 / PK_CELL, cx0 = wx0 / PK_CELL, cx1 = wx1 / PK_CELL;
+    const int ncx = cx1 - cx0 + 1, ncell = (cy1 - cy0 + 1) * ncx;
+    const float* cm = tile_max + static_cast<size_t>(blockIdx.z) * cells_y * cells_x;
     float m = -3.0e38f;
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int ty = min(max(static_cast<int>(blockIdx.y) + dy, 0), static_cast<int>(gridDim.y) - 1);
-        const int tx = min(max(static_cast<int>(blockIdx.x) + dx, 0), static_cast<int>(gridDim.x) - 1);
-        m = fmaxf(m, __ldg(tm + ty * gridDim.x + tx));
-      }
-    if (!(m > skip_below)) return;
+    for (int i = threadIdx.x; i < ncell; i += blockDim.x)
+      m = fmaxf(m, __ldg(cm + (cy0 + i / ncx) * cells_x + cx0 + i % ncx));
+    if (!__syncthreads_or(m > skip_below)) return;
   }
   const int IN_W = PK_TX + 2 + 2 * R, IN_H = PK_TY + 2 + 2 * R;
   const int O_H = PK_TY + 2, O_W = PK_TX + 2;
