@@ -747,11 +747,11 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
   ctx->launches++;
   prof_mark(ctx, "tile_max");
   if (ctx->taps.radius == PK_R_FAST)
-    smooth_nms_kernel<PK_R_FAST><<<grid, 256, smem, ctx->stream>>>(heat, c_total, c_use, H, W, ctx->taps,
+    smooth_nms_kernel<PK_R_FAST><<<grid, PK_THREADS, smem, ctx->stream>>>(heat, c_total, c_use, H, W, ctx->taps,
                                                                    static_cast<float>(p.heatmap_peak_thresh), ws->keys,
                                                                    ws->peak_counts, p.max_peaks, ws->tile_max);
   else
-    smooth_nms_kernel<0><<<grid, 256, smem, ctx->stream>>>(heat, c_total, c_use, H, W, ctx->taps,
+    smooth_nms_kernel<0><<<grid, PK_THREADS, smem, ctx->stream>>>(heat, c_total, c_use, H, W, ctx->taps,
                                                            static_cast<float>(p.heatmap_peak_thresh), ws->keys,
                                                            ws->peak_counts, p.max_peaks, ws->tile_max);
   ctx->launches++;

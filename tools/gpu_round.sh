@@ -17,7 +17,7 @@ for s in $STAGES; do
     bench) timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; tail -n 3 gpurun_out/bench.log ;;
     benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -n 2 gpurun_out/bench_ref.log ;;
     sanitize) timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python tools/conv_probe.py r3 > gpurun_out/sanitize.log 2>&1; echo "memcheck conv rc=$?"; tail -n 4 gpurun_out/sanitize.log; timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_postprocess.py -m gpu -q -k 'synth8 or edges or upsample' >> gpurun_out/sanitize.log 2>&1; echo "memcheck post rc=$?"; tail -n 4 gpurun_out/sanitize.log ;;
-    ncu)   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -n 3 gpurun_out/ncu_bench.log ;;
+    ncu)   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-stage-timing > gpurun_out/ncu_bench.log 2>&1; tail -n 3 gpurun_out/ncu_bench.log ;;
   esac
 done
 echo "=== done $(date +%T)"
