@@ -98,3 +98,26 @@ def test_pose_array_and_unit_length_helpers():
     joints = [j if j[2] > 0 else None for j in pose]
     lens, limbs = det.compute_limbs_length(joints)
     assert lens.shape == (19,) and det.compute_unit_length(lens) > 0
+
+
+def test_camera_demo_import_flow_and_drawing():
+    """What camera_pose_demo.py does before its capture loop (reference :1-14), flat imports:
+    `import chainer`, `from pose_detector import PoseDetector, draw_person_pose`, then the
+    drawing helper on a poses array (no GPU needed up to the constructor)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import chainer\n"
+        "from pose_detector import PoseDetector, draw_person_pose\n"
+        "chainer.using_config('enable_backprop', False)\n"
+        "img = np.zeros((120, 160, 3), np.uint8)\n"
+        "poses = np.zeros((1, 18, 3)); poses[0, :, 0] = np.linspace(10, 150, 18); poses[0, :, 1] = 60; poses[0, :, 2] = 2\n"
+        "out = draw_person_pose(img, poses)\n"
+        "assert out.shape == img.shape and out.any() and not img.any()\n"
+        "assert draw_person_pose(img, np.empty((0, 18, 3))) is img\n"
+        "print('ok')\n") % (os.path.join(ROOT, "chainer_realtime_multi-person_pose_estimation_b200"),
+                             os.path.join(ROOT, "chainer_realtime_multi-person_pose_estimation_b200", "compat"))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout
