@@ -96,19 +96,37 @@ def cpu_reference_step(weights, img, paf_lo, heat_lo):
     return R.postprocess_fast(pafs, heat, MAP_W, W, H, MAP_H)
 
 
+def pick_cpu_threads(weights, frame, paf_lo, heat_lo, budget_s=30.0):
+    """oneDNN does not scale to every logical core of a big host (128 threads: 30 s/frame, 16 threads: <1 s):
+    try a few thread counts (1 warm-up + 1 timed frame each) within `budget_s` and keep the fastest."""
+    import torch
+    best, t_start = None, time.perf_counter()
+    for nt in sorted({min(os.cpu_count(), t) for t in (16, 32, 64, os.cpu_count())}):
+        torch.set_num_threads(nt)
+        cpu_reference_step(weights, frame, paf_lo, heat_lo)
+        t0 = time.perf_counter()
+        cpu_reference_step(weights, frame, paf_lo, heat_lo)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    torch.set_num_threads(best[1])
+    return best
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port) on the host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
     syn = pkg("synthetic")
     wd = syn.he_weights(0)
     weights = {k[:-2]: (wd[k], wd[k[:-2] + "/b"]) for k in wd if k.endswith("/W")}
     imgs = syn.random_images(2, H, W, seed=0)
     paf_lo, heat_lo = syn.eight_person_lowres(H // 8, W // 8, seed=0)
+    _, cores = pick_cpu_threads(weights, imgs[0], paf_lo, heat_lo)      # threads actually used
     for i in range(max(args.warmup, 1)):
         cpu_reference_step(weights, imgs[i % 2], paf_lo, heat_lo)
     t0 = time.perf_counter()
@@ -117,7 +135,8 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     assert len(scores) == 8
     value = args.steps / dt
-    sample = "1 frame per step (the reference is batch-1), %d steps" % args.steps
+    sample = ("1 frame per step (the reference is batch-1), %d steps, %d torch threads (fastest of 16/32/64/all on a "
+              "%d-core host)" % (args.steps, cores, os.cpu_count()))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -251,19 +270,7 @@ def run_ours(args):
         wd = syn.he_weights(0)
         weights = {k[:-2]: (wd[k], wd[k[:-2] + "/b"]) for k in wd if k.endswith("/W")}
         fr = imgs_host[0].numpy()
-        # oneDNN does not scale to every logical core of a big host: use the best of a few
-        # thread counts (each: 1 warm-up + 1 timed frame), bounded to ~30 s of CPU work
-        best, t_budget = None, time.perf_counter()
-        for nt in sorted({min(os.cpu_count(), t) for t in (16, 32, 64, os.cpu_count())}):
-            torch.set_num_threads(nt)
-            cpu_reference_step(weights, fr, paf_lo, heat_lo)
-            t0 = time.perf_counter()
-            cpu_reference_step(weights, fr, paf_lo, heat_lo)
-            dt = time.perf_counter() - t0
-            if best is None or dt < best[0]:
-                best = (dt, nt)
-            if time.perf_counter() - t_budget > 30:
-                break
+        best = pick_cpu_threads(weights, fr, paf_lo, heat_lo)
         cpu = {"value": 1.0 / best[0], "unit": "frames/s", "cores": best[1], "kind": "port",
                "sample": "1 timed frame after 1 warm-up per thread setting (reference is batch-1), best of the "
                          "settings tried within 30 s; host has %d logical cores; torch-CPU fp32 conv + NumPy/SciPy "
