@@ -133,6 +133,23 @@ def main():
     out["heatmaps_sample"] = detp.heatmaps[:, ::7, ::7].astype(np.float32)
     np.savez_compressed(os.path.join(GOLD, "precise_480_he0.npz"), **out)
     print("G5", time.time() - t0)
+    precise_padded(ref, he)
+
+
+def precise_padded(ref, he):
+    # G7: precise path on a 200x300 frame: the scaled images (184x276, 368x552, 552x828, 736x1104) need
+    # right-padding to a multiple of 8 at scales 0.5 and 1.5 -> exercises pad_image / crop (:445,:462,:466)
+    detp = ref.PoseDetector("posenet", he, precise=True)
+    img = syn.procedural_image(200, 300, seed=4)
+    rec = capture_fast(ref, detp, img)
+    out = pack(rec)
+    out["all_peaks"] = np.asarray(detp.all_peaks, np.float64)
+    out["pafs_sample"] = detp.pafs[:, ::5, ::5].astype(np.float32)
+    out["heatmaps_sample"] = detp.heatmaps[:, ::5, ::5].astype(np.float32)
+    for k in list(out):
+        if k.startswith("paf_lo_") or k.startswith("heat_lo_"):
+            del out[k]          # keep this fixture small: the low-res maps are already pinned by G5
+    np.savez_compressed(os.path.join(GOLD, "precise_200x300_he0.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -44,6 +44,11 @@ CASES = [
     (2, 30, 17, 512, 38, 1, 0),      # PAF head (N = 48 tile, 38 valid)
     (1, 46, 46, 128, 19, 1, 0),      # heat head
     (1, 40, 40, 128, 128, 1, 1),     # Mconv6
+    # tile-edge coverage of the weights-as-A (swap) 7x7 kernel: W % 16 == 3 / 0 / 8 / 12, two images
+    (2, 23, 35, 128, 128, 7, 1),
+    (1, 40, 16, 128, 128, 7, 0),
+    (1, 30, 24, 128, 128, 7, 1),
+    (1, 25, 28, 128, 256, 7, 1),     # Cout 256 in fast mode = the CTA-pair kernel, odd tile counts
 ]
 
 

@@ -185,3 +185,23 @@ def test_precise_path_480(weights_model):
     assert len(G ^ Rf) <= max(2, len(Rf) // 500)
     if G == Rf and poses.shape == g["poses"].shape:
         assert np.array_equal(poses, g["poses"])       # OKS = 1.0 vs the reference
+
+
+def test_precise_path_padded_200x300(weights_model):
+    """Precise path with padding: the scaled inputs 184x276 and 552x828 are padded to 280 / 832 columns
+    (pad_image, :445) and the x8 maps cropped again (:462,:466)."""
+    det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precise=True, precision="parity",
+                                            max_candidates=131072, max_persons=4096)
+    g = load_golden("precise_200x300_he0.npz")
+    img = pkg("synthetic").procedural_image(200, 300, seed=4)
+    poses, scores = det(img)
+    e1 = np.abs(det.pafs[:, ::5, ::5] - g["pafs_sample"]).max()
+    e2 = np.abs(det.heatmaps[:, ::5, ::5] - g["heatmaps_sample"]).max()
+    G = set(map(tuple, det.all_peaks[:, :3].astype(int)))
+    Rf = set(map(tuple, g["all_peaks"][:, :3].astype(int)))
+    print("precise 200x300 max abs err: paf %.3e heat %.3e; peaks %d ref %d symdiff %d" % (
+        e1, e2, len(G), len(Rf), len(G ^ Rf)))
+    assert e1 <= MAP_TOL and e2 <= MAP_TOL
+    assert len(G ^ Rf) <= max(2, len(Rf) // 500)
+    if G == Rf and poses.shape == g["poses"].shape:
+        assert np.array_equal(poses, g["poses"])

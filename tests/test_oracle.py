@@ -98,6 +98,18 @@ def test_precise_path_480(he_weights):
     assert np.array_equal(poses, g["poses"]) and np.array_equal(scores, g["scores"])
 
 
+def test_precise_path_padded_200x300(he_weights):
+    # scales 0.5 and 1.5 need right-padding to a multiple of 8: pad_image / crop of :445,:462,:466
+    g = load_golden("precise_200x300_he0.npz")
+    img = pkg("synthetic").procedural_image(200, 300, seed=4)
+    poses, scores, parts = R.detect_precise(he_weights, img, return_parts=True)
+    assert np.array_equal(parts["pafs"][:, ::5, ::5], g["pafs_sample"])
+    assert np.array_equal(parts["heatmaps"][:, ::5, ::5], g["heatmaps_sample"])
+    assert np.array_equal(parts["all_peaks"], g["all_peaks"])
+    assert np.array_equal(parts["subsets"], g["subsets"])
+    assert np.array_equal(poses, g["poses"]) and np.array_equal(scores, g["scores"])
+
+
 def test_optimal_size_rule():
     z = np.zeros
     assert R.compute_optimal_size(z((368, 656, 3)), 368) == (656, 368)
