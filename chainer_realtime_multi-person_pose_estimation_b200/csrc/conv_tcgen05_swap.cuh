@@ -39,8 +39,6 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
   using Cfg = ConvSwapCfg<KS, NSP, NSW>;
   constexpr int PAD = (KS - 1) / 2;
   constexpr int ACC_STAGES = 2;
-  constexpr uint32_t IDESC256 = ptx::umma_idesc_f16(128, 256);
-  constexpr uint32_t IDESC128 = ptx::umma_idesc_f16(128, 128);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -125,9 +123,12 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
       const uint64_t p_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemP), 1024);
       const uint64_t w_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemW), 1024);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int tx = (tile % m_tiles) % (P.tiles_y * P.tiles_x) % P.tiles_x;
+        const int rem_t = (tile % m_tiles) % (P.tiles_y * P.tiles_x);
+        const int ty = rem_t / P.tiles_x, tx = rem_t - ty * P.tiles_x;
         const bool narrow = P.pad_edge8 && (tx == P.tiles_x - 1);
-        const uint32_t idesc = narrow ? IDESC128 : IDESC256;
+        // the last tile row of an image only needs its valid rows (rounded to even): N = rows x 16 (or x 8)
+        const int rows = min(16, (P.H - ty * 16 + 1) & ~1);
+        const uint32_t idesc = ptx::umma_idesc_f16(128, rows * (narrow ? 8 : 16));
         const uint32_t row_pitch16 = narrow ? (1024 >> 4) : (2048 >> 4);   // bytes per image row of the box, >> 4
         ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
         ptx::tc_fence_after();
@@ -174,7 +175,8 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
       const int y0 = ty * 16, x0 = tx * 16;
       const bool narrow = P.pad_edge8 && (tx == P.tiles_x - 1);
       const int wshift = narrow ? 3 : 4;                 // pixels per tile row = 8 or 16
-      const int n_pix = narrow ? 128 : 256;
+      const int rows = min(16, (P.H - y0 + 1) & ~1);     // rows the MMA computed for this tile
+      const int n_pix = rows << wshift;
       const ConvProblem& pr = P.prob[p];
       const int ch = nb * 128 + q * 32 + lane;           // this thread's output channel
       const bool ch_ok = ch < pr.cout_valid;
