@@ -28,7 +28,7 @@ struct PeakKey {
   float score;
 };
 
-constexpr int PK_TX = 64, PK_TY = 16, PK_R_MAX = 16;
+constexpr int PK_TX = 64, PK_TY = 16, PK_R_MAX = 16;   // tile of the peak kernel (32-row tiles measured no faster)
 constexpr int PK_THREADS = 256;  // (128-thread blocks were measured slower: 1.03 vs 0.74 ms)
 constexpr int PK_R_FAST = 10;   // radius of sigma = 2.5 (entity.py:75): compile-time specialisation
 
@@ -57,18 +57,20 @@ cell_max_kernel(const float* __restrict__ heat, int c_total, int c_use, int H, i
   const int img = plane / c_use, c = plane - img * c_use;
   const int x0 = blockIdx.x * PK_TX, y0 = blockIdx.y * PK_TY;
   const float* src = heat + (static_cast<size_t>(img) * c_total + c) * H * W;
-  // thread t -> cell (t / 8 % .. ): 16 x 64 pixels = 2 x 8 cells of 64 pixels; 16 threads per cell
-  const int cell = threadIdx.x >> 4, sub = threadIdx.x & 15;          // 16 cells, 16 threads each
-  const int cy = cell >> 3, cx = cell & 7;
+  constexpr int CELLS = (PK_TY / PK_CELL) * (PK_TX / PK_CELL);       // cells per tile
+  constexpr int TPC = 256 / CELLS;                                    // threads per cell (power of two <= 32)
+  static_assert(CELLS * TPC == 256 && TPC >= 1 && TPC <= 32 && (64 % TPC) == 0, "cell mapping");
+  const int cell = threadIdx.x / TPC, sub = threadIdx.x % TPC;
+  const int cy = cell / (PK_TX / PK_CELL), cx = cell % (PK_TX / PK_CELL);
   float m = -3.0e38f;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int e = sub * 4 + k;                                         // 64 pixels of the cell
+  for (int k = 0; k < 64 / TPC; ++k) {
+    const int e = sub * (64 / TPC) + k;                                // 64 pixels of the cell
     const int y = y0 + cy * PK_CELL + (e >> 3), x = x0 + cx * PK_CELL + (e & 7);
     if (y < H && x < W) m = fmaxf(m, __ldg(src + static_cast<size_t>(y) * W + x));
   }
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  for (int o = TPC / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   const int gy = blockIdx.y * (PK_TY / PK_CELL) + cy, gx = blockIdx.x * (PK_TX / PK_CELL) + cx;
   if (sub == 0 && gy < cells_y && gx < cells_x)
     cell_max[(static_cast<size_t>(plane) * cells_y + gy) * cells_x + gx] = m;
