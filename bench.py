@@ -264,6 +264,24 @@ def run_ours(args):
                                    "ms": ms_up},
         "stage_ms": {s: eng.time_stage(s, reps=5) for s in ("upsample_heat", "peaks", "paf_integral", "group")},
     }
+    # camera-style latency: one 640x480 BGR frame through the public PoseDetector.__call__ (host resize,
+    # H2D, conv chain, post-process, D2H), the loop of camera_pose_demo.py:20-31
+    try:
+        det = pkg("pose_detector").PoseDetector(model=model, device=local_rank, precision=args.precision)
+        frame = syn.procedural_image(480, 640, seed=2)
+        for _ in range(3):
+            det(frame)
+        ts = []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            det(frame)
+            ts.append(time.perf_counter() - t0)
+        extra["single_frame_640x480_ms"] = {"median": 1e3 * float(np.median(ts)), "min": 1e3 * float(np.min(ts)),
+                                            "note": "wall clock of PoseDetector.__call__ (random-weight noise maps: "
+                                                    "~2000 peaks, so the post-process is far heavier than on real frames)"}
+        del det
+    except Exception as e:  # the headline numbers must not depend on this extra
+        extra["single_frame_640x480_ms"] = {"error": str(e)[:200]}
     # CPU baseline: the oracle port on this box's host cores, bounded sample
     cpu = None
     if not args.no_cpu_baseline:

@@ -56,6 +56,10 @@ _SIGNATURES = {
                             C.POINTER(C.c_int)]),
     "opb_detect_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "opb_resize_linear_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_int, C.c_int]),
+    "opb_detect_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "opb_get_image_detail": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p,
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "opb_precise_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -258,6 +262,28 @@ class Engine(object):
                                               C.c_void_p(int(inject_paf)) if inject_paf else None,
                                               C.c_void_p(int(inject_heat)) if inject_heat else None,
                                               _ptr(headers), _ptr(persons), OPB_HOST))
+        return headers, persons
+
+    def resize_linear_u8(self, imgs, out_h, out_w):
+        """cv2.resize(img, (out_w, out_h)) (INTER_LINEAR, uint8) on the device; imgs [N,H,W,3] or [H,W,3]."""
+        a = np.ascontiguousarray(imgs, np.uint8)
+        single = a.ndim == 3
+        if single:
+            a = a[None]
+        n, h0, w0, _ = a.shape
+        out = np.empty((n, out_h, out_w, 3), np.uint8)
+        self._check(self.lib.opb_resize_linear_u8(self.ctx, _ptr(a), OPB_HOST, n, h0, w0, _ptr(out), OPB_HOST, out_h, out_w))
+        return out[0] if single else out
+
+    def detect_image(self, img, in_h, in_w, map_h, map_w, img_len=None):
+        """One BGR frame of any size: upload, device resize, full pipeline (opb_detect_image)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        oh, ow, _ = img.shape
+        headers = np.empty(1, HEADER_DTYPE)
+        persons = np.empty((1, self.max_persons), PERSON_DTYPE)
+        self._check(self.lib.opb_detect_image(self.ctx, _ptr(img), OPB_HOST, oh, ow, in_h, in_w, map_h, map_w,
+                                              float(map_w if img_len is None else img_len), _ptr(headers),
+                                              _ptr(persons), OPB_HOST))
         return headers, persons
 
     def image_detail(self, img):

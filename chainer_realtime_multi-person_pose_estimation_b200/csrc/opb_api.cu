@@ -17,6 +17,7 @@
 
 #include "../../include/opb.h"
 #include "conv_first.cuh"
+#include "ingest.cuh"
 #include "conv_tcgen05.cuh"
 #include "conv_tcgen05_pair.cuh"
 #include "conv_tcgen05_swap.cuh"
@@ -136,6 +137,8 @@ struct opb_ctx {
   Chain* last_chain = nullptr;
   std::map<long long, PostWs*> posts;
   PostWs* last_post = nullptr;
+  uint8_t* ingest_buf = nullptr;   // staging for the original frame(s) of opb_detect_image
+  size_t ingest_bytes = 0;
   int conn_cap = kAssignMaxType;
   bool profile = false;                       // OPB_PROFILE=1: cudaEvent after every launch of a batch
   std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -910,6 +913,7 @@ void opb_destroy(opb_ctx* ctx) {
   for (auto& kv : ctx->chains) { free_all(kv.second->allocs); delete kv.second; }
   for (auto& kv : ctx->posts) { free_all(kv.second->allocs); delete kv.second; }
   free_all(ctx->weight_allocs);
+  if (ctx->ingest_buf) cudaFree(ctx->ingest_buf);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1405,6 +1409,67 @@ int opb_download_maps(opb_ctx* ctx, float* pafs_out, float* heat_out, int out_lo
   if (heat_out && (rc = copy_out(ctx, heat_out, ws->heat, plane * 19, out_loc))) return rc;
   OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return OPB_OK;
+}
+
+static int launch_resize_u8(opb_ctx* ctx, const uint8_t* d_src, int n, int h0, int w0, uint8_t* d_dst, int h, int w) {
+  if (h0 == h && w0 == w) {
+    OPB_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, static_cast<size_t>(n) * h * w * 3, cudaMemcpyDeviceToDevice, ctx->stream));
+    return OPB_OK;
+  }
+  const double sx = 1.0 / (static_cast<double>(w) / w0), sy = 1.0 / (static_cast<double>(h) / h0);
+  dim3 grid((w + 31) / 32, (h + 7) / 8, n), block(32, 8);
+  resize_linear_u8_kernel<<<grid, block, 0, ctx->stream>>>(d_src, h0, w0, d_dst, h, w, sx, sy);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  return OPB_OK;
+}
+
+static int ensure_ingest(opb_ctx* ctx, size_t bytes) {
+  if (ctx->ingest_bytes >= bytes) return OPB_OK;
+  if (ctx->ingest_buf) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->ingest_buf); ctx->ingest_buf = nullptr; }
+  OPB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->ingest_buf), bytes));
+  ctx->ingest_bytes = bytes;
+  return OPB_OK;
+}
+
+int opb_resize_linear_u8(opb_ctx* ctx, const uint8_t* src, int src_loc, int n, int h0, int w0, uint8_t* dst,
+                         int dst_loc, int h, int w) {
+  if (!ctx || !src || !dst || n <= 0 || h0 <= 0 || w0 <= 0 || h <= 0 || w <= 0) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const size_t in_b = static_cast<size_t>(n) * h0 * w0 * 3, out_b = static_cast<size_t>(n) * h * w * 3;
+  int rc = ensure_ingest(ctx, in_b + out_b + 512);
+  if (rc) return rc;
+  const uint8_t* d_src = src;
+  if (src_loc == OPB_HOST) {
+    if ((rc = copy_in(ctx, ctx->ingest_buf, src, in_b, OPB_HOST))) return rc;
+    d_src = ctx->ingest_buf;
+  }
+  uint8_t* d_dst = (dst_loc == OPB_HOST) ? ctx->ingest_buf + ((in_b + 255) & ~size_t(255)) : dst;
+  if ((rc = launch_resize_u8(ctx, d_src, n, h0, w0, d_dst, h, w))) return rc;
+  if (dst_loc == OPB_HOST && (rc = copy_out(ctx, dst, d_dst, out_b, OPB_HOST))) return rc;
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return OPB_OK;
+}
+
+int opb_detect_image(opb_ctx* ctx, const uint8_t* img, int img_loc, int orig_h, int orig_w, int in_h, int in_w,
+                     int map_h, int map_w, double img_len, opb_image_header* header_out, opb_person* persons_out,
+                     int out_loc) {
+  if (!ctx || !img || !header_out || !persons_out) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  Chain* ch = nullptr;
+  int rc = get_chain(ctx, 1, in_h, in_w, &ch);
+  if (rc) return rc;
+  const size_t in_b = static_cast<size_t>(orig_h) * orig_w * 3;
+  const uint8_t* d_src = img;
+  if (img_loc == OPB_HOST) {
+    if ((rc = ensure_ingest(ctx, in_b + 512))) return rc;
+    if ((rc = copy_in(ctx, ctx->ingest_buf, img, in_b, OPB_HOST))) return rc;
+    d_src = ctx->ingest_buf;
+  }
+  if ((rc = launch_resize_u8(ctx, d_src, 1, orig_h, orig_w, ch->img_u8, in_h, in_w))) return rc;
+  // frames are now resident at network-input size: reuse the batch path in place
+  return opb_detect_batch(ctx, ch->img_u8, OPB_DEVICE, 1, in_h, in_w, map_h, map_w, img_len, nullptr, nullptr, header_out,
+                          persons_out, out_loc);
 }
 
 void* opb_device_buffer(opb_ctx* ctx, int which) {

@@ -251,8 +251,9 @@ class PoseDetector(object):
         oh, ow = orig_img.shape[:2]
         in_w, in_h = self.compute_optimal_size(orig_img, params['inference_img_size'])
         map_w, map_h = self.compute_optimal_size(orig_img, params['heatmap_size'])
-        resized = cv2.resize(orig_img, (in_w, in_h))
-        headers, persons = self.engine.detect_batch(resized[None], map_h, map_w, img_len=map_w)
+        # cv2.resize(orig_img, (input_w, input_h)) of the reference (:493) runs on the device, bit-exact with
+        # OpenCV's 8-bit INTER_LINEAR (csrc/ingest.cuh); the frame is uploaded once at its original size
+        headers, persons = self.engine.detect_image(orig_img, in_h, in_w, map_h, map_w, img_len=map_w)
         return self._poses_from_records(headers[0], persons[0], ow / map_w, oh / map_h)
 
     def detect_batch(self, imgs, orig_sizes=None):

@@ -158,6 +158,18 @@ int opb_detect_batch(opb_ctx* ctx, const uint8_t* imgs, int imgs_loc, int n, int
                      int map_w, double img_len, const float* inject_paf, const float* inject_heat,
                      opb_image_header* headers_out, opb_person* persons_out, int out_loc);
 
+/* -- device-side ingest: replaces cv2.resize(orig_img, (input_w, input_h)) (default INTER_LINEAR on
+ *    uint8 BGR, pose_detector.py:493), bit-exact with OpenCV's 8-bit fixed-point path.
+ *    src [n,h0,w0,3] -> dst [n,h,w,3] uint8.                                                     */
+int opb_resize_linear_u8(opb_ctx* ctx, const uint8_t* src, int src_loc, int n, int h0, int w0,
+                         uint8_t* dst, int dst_loc, int h, int w);
+/* PoseDetector.__call__ for ONE frame of arbitrary size (pose_detector.py:484-517): uploads the
+ * original frame, resizes it on the device to (in_h, in_w), then runs the same pipeline as
+ * opb_detect_batch with n = 1.                                                                  */
+int opb_detect_image(opb_ctx* ctx, const uint8_t* img, int img_loc, int orig_h, int orig_w, int in_h,
+                     int in_w, int map_h, int map_w, double img_len, opb_image_header* header_out,
+                     opb_person* persons_out, int out_loc);
+
 /* device pointers of the last opb_detect_batch outputs/intermediates (valid until the next
  * call with a different shape): 0 paf_lo, 1 heat_lo, 2 pafs (full-res), 3 heatmaps (full-res),
  * 4 headers, 5 persons, 6 peak table ([N,max_peaks] of {int32 type,x,y; float score})       */

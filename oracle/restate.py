@@ -182,6 +182,40 @@ def pad_image(img, stride, pad_value):
     return out, [ph, pw]
 
 
+def cv2_resize_linear_u8(img, dsize):
+    """Restatement of cv2.resize(img_uint8, (W, H)) with the default INTER_LINEAR (pose_detector.py:493)
+    [3p OpenCV 4.13 imgproc/resize.cpp, 8-bit fixed-point path]: per axis fx = float((d+0.5)*scale-0.5),
+    s = floor(fx), fx -= s; COLUMNS clamp (s<0 -> s=0,fx=0; s>=w-1 -> s=w-1,fx=0), ROWS keep fx and clip the
+    two source rows separately; coefficients = rint(c*2048) as int16; horizontal pass in int32
+    D = S[s]*a0 + S[s+1]*a1; vertical pass ((b0*(D0>>4))>>16) + ((b1*(D1>>4))>>16) + 2) >> 2.
+    Verified bit-exact against cv2 in tests/test_oracle.py."""
+    W, H = int(dsize[0]), int(dsize[1])
+    h0, w0 = img.shape[:2]
+    if (W, H) == (w0, h0):
+        return img.copy()
+
+    def axis(dst_n, src_n, clamp):
+        scale = 1.0 / (float(dst_n) / src_n)
+        f = ((np.arange(dst_n, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        s0 = np.floor(f).astype(np.int32)
+        f = (f - s0.astype(np.float32)).astype(np.float32)
+        if clamp:
+            lo = s0 < 0
+            f[lo] = 0; s0[lo] = 0
+            hi = s0 >= src_n - 1
+            f[hi] = 0; s0[hi] = src_n - 1
+        c0 = np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int32)
+        c1 = np.rint(f * np.float32(2048)).astype(np.int32)
+        return np.clip(s0, 0, src_n - 1), np.clip(s0 + 1, 0, src_n - 1), c0, c1
+
+    sx, sx1, a0, a1 = axis(W, w0, True)
+    sy, sy1, b0, b1 = axis(H, h0, False)
+    S = img.astype(np.int32).reshape(h0, w0, -1)
+    D = S[:, sx] * a0[None, :, None] + S[:, sx1] * a1[None, :, None]
+    out = ((((b0[:, None, None] * (D[sy] >> 4)) >> 16) + ((b1[:, None, None] * (D[sy1] >> 4)) >> 16) + 2) >> 2)
+    return out.astype(np.uint8).reshape((H, W) + img.shape[2:])
+
+
 def resize_bilinear_align_corners(x, out_hw):
     """Chainer resize_images [3p] (pose_detector.py:501-502).  x: [B,C,H,W] f32."""
     B, C, H, W = x.shape

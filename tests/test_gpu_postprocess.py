@@ -237,3 +237,22 @@ def test_capacity_errors_are_loud():
     conns = big.connections(paf, g["all_peaks"], 576)    # 8 persons: <= 64 candidates per limb is enough
     with pytest.raises(native.OpbError):
         big.group(conns, g["all_peaks"])                # 8 persons do not fit max_persons = 2
+
+
+def test_device_resize_linear_u8_bit_exact_vs_cv2(engine):
+    """cv2.resize(img, (w, h)) with the default INTER_LINEAR on uint8 (pose_detector.py:493), on the device."""
+    import cv2
+    rs = np.random.RandomState(0)
+    shapes = [((480, 640), (496, 368)), ((584, 584), (368, 368)), ((1080, 1920), (656, 368)), ((100, 37), (368, 1000)),
+              ((240, 320), (496, 368)), ((736, 1312), (656, 368)), ((368, 656), (656, 368)), ((333, 517), (576, 368))]
+    for _ in range(8):
+        shapes.append(((rs.randint(40, 600), rs.randint(40, 600)), (rs.randint(40, 500), rs.randint(40, 500))))
+    for (h0, w0), (W, H) in shapes:
+        img = rs.randint(0, 256, (h0, w0, 3)).astype(np.uint8)
+        got = engine.resize_linear_u8(img, H, W)
+        assert np.array_equal(got, cv2.resize(img, (W, H))), ((h0, w0), (W, H))
+        assert np.array_equal(got, R.cv2_resize_linear_u8(img, (W, H)))
+    batch = rs.randint(0, 256, (3, 120, 160, 3)).astype(np.uint8)
+    got = engine.resize_linear_u8(batch, 96, 128)
+    for i in range(3):
+        assert np.array_equal(got[i], cv2.resize(batch[i], (128, 96)))

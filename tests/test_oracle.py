@@ -110,6 +110,18 @@ def test_precise_path_padded_200x300(he_weights):
     assert np.array_equal(poses, g["poses"]) and np.array_equal(scores, g["scores"])
 
 
+def test_cv2_linear_u8_restatement_bit_exact():
+    import cv2
+    rs = np.random.RandomState(0)
+    shapes = [((480, 640), (496, 368)), ((584, 584), (368, 368)), ((1080, 1920), (656, 368)), ((100, 37), (368, 1000)),
+              ((240, 320), (496, 368)), ((736, 1312), (656, 368)), ((368, 656), (656, 368)), ((333, 517), (576, 368))]
+    for _ in range(10):
+        shapes.append(((rs.randint(40, 600), rs.randint(40, 600)), (rs.randint(40, 500), rs.randint(40, 500))))
+    for (h0, w0), (W, H) in shapes:
+        img = rs.randint(0, 256, (h0, w0, 3)).astype(np.uint8)
+        assert np.array_equal(R.cv2_resize_linear_u8(img, (W, H)), cv2.resize(img, (W, H))), ((h0, w0), (W, H))
+
+
 def test_optimal_size_rule():
     z = np.zeros
     assert R.compute_optimal_size(z((368, 656, 3)), 368) == (656, 368)
