@@ -60,6 +60,9 @@ _SIGNATURES = {
                                        C.c_int, C.c_int]),
     "opb_detect_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
+    "opb_stream_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
+    "opb_stream_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "opb_get_image_detail": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p,
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "opb_precise_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -284,6 +287,33 @@ class Engine(object):
         self._check(self.lib.opb_detect_image(self.ctx, _ptr(img), OPB_HOST, oh, ow, in_h, in_w, map_h, map_w,
                                               float(map_w if img_len is None else img_len), _ptr(headers),
                                               _ptr(persons), OPB_HOST))
+        return headers, persons
+
+    def stream_submit(self, frames, in_h, in_w, map_h, map_w, slot, img_len=None, inject_paf=None, inject_heat=None):
+        """Enqueue one batch [N,H0,W0,3] uint8 (host) on `slot` (0/1) without waiting (opb_stream_submit)."""
+        if isinstance(frames, np.ndarray):
+            frames = np.ascontiguousarray(frames, np.uint8)
+            if frames.ndim == 3:
+                frames = frames[None]
+            n, oh, ow, _ = frames.shape
+            ptr = _ptr(frames)
+            self._stream_keep = getattr(self, "_stream_keep", {})
+            self._stream_keep[slot] = frames          # pinned buffers are read asynchronously: keep them alive
+        else:                                         # (data_ptr, n, h, w) of a pinned buffer owned by the caller
+            addr, n, oh, ow = frames
+            ptr = C.c_void_p(addr)
+        self._stream_n = getattr(self, "_stream_n", {})
+        self._stream_n[slot] = n
+        self._check(self.lib.opb_stream_submit(self.ctx, ptr, n, oh, ow, in_h, in_w, map_h, map_w,
+                                               float(map_w if img_len is None else img_len),
+                                               C.c_void_p(inject_paf or 0), C.c_void_p(inject_heat or 0), slot))
+
+    def stream_collect(self, slot):
+        """Block until the batch submitted on `slot` is done; returns (headers[N], persons[N, max_persons])."""
+        n = self._stream_n[slot]
+        headers = np.empty(n, HEADER_DTYPE)
+        persons = np.empty((n, self.max_persons), PERSON_DTYPE)
+        self._check(self.lib.opb_stream_collect(self.ctx, slot, _ptr(headers), _ptr(persons)))
         return headers, persons
 
     def image_detail(self, img):

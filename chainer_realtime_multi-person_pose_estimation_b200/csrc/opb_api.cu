@@ -139,6 +139,15 @@ struct opb_ctx {
   PostWs* last_post = nullptr;
   uint8_t* ingest_buf = nullptr;   // staging for the original frame(s) of opb_detect_image
   size_t ingest_bytes = 0;
+  // streaming mode (opb_stream_submit / opb_stream_collect): two slots, pinned staging, a copy stream
+  struct StreamSlot {
+    uint8_t* d_frames = nullptr; size_t d_bytes = 0;     // device copy of the submitted frames (original size)
+    uint8_t* h_frames = nullptr; size_t h_bytes = 0;     // pinned staging for pageable caller buffers
+    uint8_t* h_result = nullptr; size_t r_bytes = 0;     // pinned [headers | persons] of the slot
+    cudaEvent_t h2d_done = nullptr, done = nullptr;
+    int n = 0; bool busy = false;
+  } slots[2];
+  cudaStream_t copy_stream = nullptr;
   int conn_cap = kAssignMaxType;
   bool profile = false;                       // OPB_PROFILE=1: cudaEvent after every launch of a batch
   std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -914,6 +923,14 @@ void opb_destroy(opb_ctx* ctx) {
   for (auto& kv : ctx->posts) { free_all(kv.second->allocs); delete kv.second; }
   free_all(ctx->weight_allocs);
   if (ctx->ingest_buf) cudaFree(ctx->ingest_buf);
+  for (auto& sl : ctx->slots) {
+    if (sl.d_frames) cudaFree(sl.d_frames);
+    if (sl.h_frames) cudaFreeHost(sl.h_frames);
+    if (sl.h_result) cudaFreeHost(sl.h_result);
+    if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1258,6 +1275,29 @@ int opb_group(opb_ctx* ctx, const double* conns, const int* conn_counts, const d
   return OPB_OK;
 }
 
+// conv chain + upsample + peaks + connections + grouping for the frames ch->img_u8_src points at (all on ctx->stream,
+// no host synchronisation): the device-resident body of PoseDetector.__call__ (pose_detector.py:495-512)
+static int run_pipeline(opb_ctx* ctx, Chain* ch, PostWs* ws, int n, int h, int w, int map_h, int map_w, double img_len,
+                        const float* inject_paf, const float* inject_heat) {
+  int rc;
+  if ((rc = run_chain(ctx, ch, true))) return rc;
+  const int h8 = h / 8, w8 = w / 8;
+  const float* paf_lo = inject_paf ? inject_paf : ch->paf_lo;
+  const float* heat_lo = inject_heat ? inject_heat : ch->heat_lo;
+  ws->last_paf_lo = paf_lo; ws->last_heat_lo = heat_lo; ws->last_img_len = img_len;
+  if ((rc = launch_upsample(ctx, paf_lo, n * 38, h8, w8, ws->pafs, map_h, map_w))) return rc;
+  prof_mark(ctx, "upsample_paf");
+  if ((rc = launch_upsample(ctx, heat_lo, n * 19, h8, w8, ws->heat, map_h, map_w))) return rc;
+  prof_mark(ctx, "upsample_heat");
+  if ((rc = launch_peaks(ctx, ws, ws->heat, n, 19, map_h, map_w))) return rc;
+  prof_mark(ctx, "peaks");
+  if ((rc = launch_connections(ctx, ws, ws->pafs, n, map_h, map_w, img_len))) return rc;
+  prof_mark(ctx, "connections");
+  if ((rc = launch_group(ctx, ws, n, true))) return rc;
+  prof_mark(ctx, "group");
+  return OPB_OK;
+}
+
 int opb_detect_batch(opb_ctx* ctx, const uint8_t* imgs, int imgs_loc, int n, int h, int w, int map_h, int map_w,
                      double img_len, const float* inject_paf, const float* inject_heat, opb_image_header* headers_out,
                      opb_person* persons_out, int out_loc) {
@@ -1276,21 +1316,7 @@ int opb_detect_batch(opb_ctx* ctx, const uint8_t* imgs, int imgs_loc, int n, int
     if ((rc = copy_in(ctx, ch->img_u8, imgs, static_cast<size_t>(n) * h * w * 3, imgs_loc))) return rc;
   }
   prof_mark(ctx, "copy_in");
-  if ((rc = run_chain(ctx, ch, true))) return rc;
-  const int h8 = h / 8, w8 = w / 8;
-  const float* paf_lo = inject_paf ? inject_paf : ch->paf_lo;
-  const float* heat_lo = inject_heat ? inject_heat : ch->heat_lo;
-  ws->last_paf_lo = paf_lo; ws->last_heat_lo = heat_lo; ws->last_img_len = img_len;
-  if ((rc = launch_upsample(ctx, paf_lo, n * 38, h8, w8, ws->pafs, map_h, map_w))) return rc;
-  prof_mark(ctx, "upsample_paf");
-  if ((rc = launch_upsample(ctx, heat_lo, n * 19, h8, w8, ws->heat, map_h, map_w))) return rc;
-  prof_mark(ctx, "upsample_heat");
-  if ((rc = launch_peaks(ctx, ws, ws->heat, n, 19, map_h, map_w))) return rc;
-  prof_mark(ctx, "peaks");
-  if ((rc = launch_connections(ctx, ws, ws->pafs, n, map_h, map_w, img_len))) return rc;
-  prof_mark(ctx, "connections");
-  if ((rc = launch_group(ctx, ws, n, true))) return rc;
-  prof_mark(ctx, "group");
+  if ((rc = run_pipeline(ctx, ch, ws, n, h, w, map_h, map_w, img_len, inject_paf, inject_heat))) return rc;
   if ((rc = copy_out(ctx, headers_out, ws->headers, sizeof(ImageHeader) * n, out_loc))) return rc;
   if ((rc = copy_out(ctx, persons_out, ws->persons, sizeof(PersonOut) * n * ctx->prm.max_persons, out_loc))) return rc;
   prof_mark(ctx, "copy_out");
@@ -1470,6 +1496,80 @@ int opb_detect_image(opb_ctx* ctx, const uint8_t* img, int img_loc, int orig_h, 
   // frames are now resident at network-input size: reuse the batch path in place
   return opb_detect_batch(ctx, ch->img_u8, OPB_DEVICE, 1, in_h, in_w, map_h, map_w, img_len, nullptr, nullptr, header_out,
                           persons_out, out_loc);
+}
+
+int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, int orig_w, int in_h, int in_w, int map_h,
+                      int map_w, double img_len, const float* inject_paf, const float* inject_heat, int slot) {
+  if (!ctx || !frames || n <= 0 || slot < 0 || slot > 1) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  auto& sl = ctx->slots[slot];
+  if (sl.busy) OPB_FAIL(ctx, OPB_ERR_ARG, "opb_stream_submit: slot still holds an uncollected batch");
+  Chain* ch = nullptr;
+  PostWs* ws = nullptr;
+  int rc;
+  if ((rc = get_chain(ctx, n, in_h, in_w, &ch))) return rc;
+  if ((rc = get_post(ctx, n, map_h, map_w, &ws))) return rc;
+  if (!ctx->copy_stream) OPB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (!sl.done) {
+    OPB_CUDA(ctx, cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    OPB_CUDA(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  const size_t in_b = static_cast<size_t>(n) * orig_h * orig_w * 3;
+  const size_t res_b = n * (sizeof(ImageHeader) + sizeof(PersonOut) * static_cast<size_t>(ctx->prm.max_persons));
+  if (sl.d_bytes < in_b) {
+    if (sl.d_frames) { OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(sl.d_frames); sl.d_frames = nullptr; }
+    OPB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sl.d_frames), in_b));
+    sl.d_bytes = in_b;
+  }
+  if (sl.r_bytes < res_b) {
+    if (sl.h_result) cudaFreeHost(sl.h_result);
+    OPB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&sl.h_result), res_b));
+    sl.r_bytes = res_b;
+  }
+  // pageable caller memory goes through the slot's pinned staging buffer so the H2D copy is truly asynchronous
+  const uint8_t* h_src = frames;
+  cudaPointerAttributes at{};
+  const bool pinned = cudaPointerGetAttributes(&at, frames) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (!pinned) {
+    if (sl.h_bytes < in_b) {
+      if (sl.h_frames) cudaFreeHost(sl.h_frames);
+      OPB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&sl.h_frames), in_b));
+      sl.h_bytes = in_b;
+    }
+    memcpy(sl.h_frames, frames, in_b);
+    h_src = sl.h_frames;
+  }
+  // the slot's previous batch was collected (sl.done reached), so its device frames are free to overwrite
+  OPB_CUDA(ctx, cudaMemcpyAsync(sl.d_frames, h_src, in_b, cudaMemcpyHostToDevice, ctx->copy_stream));
+  OPB_CUDA(ctx, cudaEventRecord(sl.h2d_done, ctx->copy_stream));
+  OPB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
+  if (orig_h == in_h && orig_w == in_w) {
+    ch->img_u8_src = sl.d_frames;
+  } else {
+    if ((rc = launch_resize_u8(ctx, sl.d_frames, n, orig_h, orig_w, ch->img_u8, in_h, in_w))) return rc;
+    ch->img_u8_src = nullptr;
+  }
+  if ((rc = run_pipeline(ctx, ch, ws, n, in_h, in_w, map_h, map_w, img_len, inject_paf, inject_heat))) return rc;
+  if ((rc = copy_out(ctx, sl.h_result, ws->headers, sizeof(ImageHeader) * n, OPB_HOST))) return rc;
+  if ((rc = copy_out(ctx, sl.h_result + sizeof(ImageHeader) * n, ws->persons,
+                     sizeof(PersonOut) * n * static_cast<size_t>(ctx->prm.max_persons), OPB_HOST))) return rc;
+  OPB_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream));
+  sl.n = n;
+  sl.busy = true;
+  return OPB_OK;
+}
+
+int opb_stream_collect(opb_ctx* ctx, int slot, opb_image_header* headers_out, opb_person* persons_out) {
+  if (!ctx || slot < 0 || slot > 1 || !headers_out || !persons_out) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  auto& sl = ctx->slots[slot];
+  if (!sl.busy) OPB_FAIL(ctx, OPB_ERR_ARG, "opb_stream_collect: nothing submitted on this slot");
+  OPB_CUDA(ctx, cudaEventSynchronize(sl.done));
+  sl.busy = false;
+  memcpy(headers_out, sl.h_result, sizeof(ImageHeader) * sl.n);
+  memcpy(persons_out, sl.h_result + sizeof(ImageHeader) * sl.n, sizeof(PersonOut) * sl.n * static_cast<size_t>(ctx->prm.max_persons));
+  return OPB_OK;
 }
 
 void* opb_device_buffer(opb_ctx* ctx, int which) {

@@ -259,14 +259,41 @@ class PoseDetector(object):
     def detect_batch(self, imgs, orig_sizes=None):
         """Batched fast path for equally sized BGR frames [N,H,W,3] (no reference analogue: the
         reference is batch-1).  Returns a list of (poses, scores)."""
-        imgs = np.asarray(imgs)
+        imgs = np.ascontiguousarray(imgs, np.uint8)
         in_w, in_h = self.compute_optimal_size(imgs[0], params['inference_img_size'])
         map_w, map_h = self.compute_optimal_size(imgs[0], params['heatmap_size'])
         oh, ow = imgs.shape[1:3]
-        if (in_h, in_w) != (oh, ow):
-            imgs = np.stack([cv2.resize(im, (in_w, in_h)) for im in imgs])
-        headers, persons = self.engine.detect_batch(imgs, map_h, map_w, img_len=map_w)
+        # the per-frame cv2.resize of :493 runs on the device for the whole batch (csrc/ingest.cuh)
+        self.engine.stream_submit(imgs, in_h, in_w, map_h, map_w, slot=0, img_len=map_w)
+        headers, persons = self.engine.stream_collect(0)
         return [self._poses_from_records(headers[i], persons[i], ow / map_w, oh / map_h) for i in range(len(imgs))]
+
+    def detect_stream(self, frames):
+        """Pipelined camera loop (camera_pose_demo.py:20-31): `frames` is an iterable of BGR uint8 frames
+        [H,W,3] or equally sized batches [N,H,W,3]; yields (poses, scores) per frame (a list of them per batch)
+        in order, one item behind the input: the upload of item i+1 overlaps the kernels of item i."""
+        pending = None                                    # (slot, single, ow, oh, map_w, map_h, n)
+        slot = 0
+        for item in frames:
+            a = np.ascontiguousarray(item, np.uint8)
+            single = a.ndim == 3
+            if single:
+                a = a[None]
+            in_w, in_h = self.compute_optimal_size(a[0], params['inference_img_size'])
+            map_w, map_h = self.compute_optimal_size(a[0], params['heatmap_size'])
+            self.engine.stream_submit(a, in_h, in_w, map_h, map_w, slot=slot, img_len=map_w)
+            cur = (slot, single, a.shape[2], a.shape[1], map_w, map_h, len(a))
+            if pending is not None:
+                yield self._collect_stream(pending)
+            pending, slot = cur, slot ^ 1
+        if pending is not None:
+            yield self._collect_stream(pending)
+
+    def _collect_stream(self, pending):
+        slot, single, ow, oh, map_w, map_h, n = pending
+        headers, persons = self.engine.stream_collect(slot)
+        out = [self._poses_from_records(headers[i], persons[i], ow / map_w, oh / map_h) for i in range(n)]
+        return out[0] if single else out
 
 
 _LIMB_COLORS = [

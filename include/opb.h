@@ -170,6 +170,17 @@ int opb_detect_image(opb_ctx* ctx, const uint8_t* img, int img_loc, int orig_h, 
                      int in_w, int map_h, int map_w, double img_len, opb_image_header* header_out,
                      opb_person* persons_out, int out_loc);
 
+/* -- streaming mode: the camera loop of camera_pose_demo.py:20-31, pipelined.  Two slots; submit()
+ *    enqueues [pinned staging ->] H2D on a copy stream, the device resize (if orig != in), the whole
+ *    pipeline and the D2H of the records, and returns without waiting; collect() blocks until that
+ *    slot's records are on the host.  Submitting batch i+1 before collecting batch i overlaps its
+ *    upload with batch i's kernels.  frames: HOST [n,orig_h,orig_w,3] uint8 BGR (pinned or pageable).
+ *    inject_* as in opb_detect_batch (device pointers or NULL).                                 */
+int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, int orig_w, int in_h,
+                      int in_w, int map_h, int map_w, double img_len, const float* inject_paf,
+                      const float* inject_heat, int slot);
+int opb_stream_collect(opb_ctx* ctx, int slot, opb_image_header* headers_out, opb_person* persons_out);
+
 /* device pointers of the last opb_detect_batch outputs/intermediates (valid until the next
  * call with a different shape): 0 paf_lo, 1 heat_lo, 2 pafs (full-res), 3 heatmaps (full-res),
  * 4 headers, 5 persons, 6 peak table ([N,max_peaks] of {int32 type,x,y; float score})       */

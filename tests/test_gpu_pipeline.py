@@ -144,6 +144,33 @@ def test_detect_batch_matches_single_calls(det_parity):
         assert abs(len(poses) - len(g["poses"])) <= 3
 
 
+def test_stream_mode_matches_single_calls(det_parity):
+    """Pipelined submit/collect (two slots, copy stream, device resize) returns, in order, exactly what the
+    synchronous __call__ returns for every frame -- frames of different sizes, single frames and batches."""
+    syn = pkg("synthetic")
+    frames = [syn.procedural_image(480, 640, seed=3), syn.procedural_image(584, 584, seed=1),
+              syn.random_images(2, 368, 656, seed=0), syn.procedural_image(240, 320, seed=7),
+              syn.procedural_image(480, 640, seed=4)]
+    got = list(det_parity.detect_stream(iter(frames)))
+    assert len(got) == len(frames)
+    for f, g in zip(frames, got):
+        if f.ndim == 4:
+            for i in range(len(f)):
+                p, sc = det_parity(f[i])
+                assert g[i][0].shape == p.shape and np.array_equal(g[i][0], p) and np.array_equal(g[i][1], sc)
+        else:
+            p, sc = det_parity(f)
+            assert g[0].shape == p.shape and np.array_equal(g[0], p) and np.array_equal(g[1], sc)
+    # protocol errors are reported, not silently overwritten
+    eng = det_parity.engine
+    eng.stream_submit(frames[0], 368, 496, 320, 432, slot=0)
+    with pytest.raises(RuntimeError):
+        eng.stream_submit(frames[0], 368, 496, 320, 432, slot=0)
+    eng.stream_collect(0)
+    with pytest.raises(RuntimeError):
+        eng.stream_collect(0)
+
+
 def test_injected_synthetic_eight_person_maps(det_parity):
     """Config #3: synthetic 8-person maps injected as the network output (the conv chain still
     runs); 8 persons must come out for every image of the batch, identical to the oracle run
