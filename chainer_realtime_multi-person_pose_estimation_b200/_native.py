@@ -63,6 +63,10 @@ _SIGNATURES = {
     "opb_stream_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "opb_stream_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "opb_keypoints_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "opb_keypoints_from_heatmaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_double, C.c_void_p, C.c_void_p]),
     "opb_get_image_detail": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p,
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "opb_precise_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -162,6 +166,8 @@ class Engine(object):
             self._check(self.lib.opb_load_weights(self.ctx, name.encode(), _ptr(W), shape, _ptr(b)))
         self._check(self.lib.opb_finalize_weights(self.ctx, int(self.precision)))
         self._weights_ready = True
+        last = dict(model.children_items()).get("conv6_2_CPM")      # FaceNet / HandNet: channels of the final maps
+        self.kp_channels = int(last.W.data.shape[0]) if last is not None else 0
 
     def set_stream(self, stream_handle):
         self._check(self.lib.opb_set_stream(self.ctx, C.c_void_p(int(stream_handle) if stream_handle else 0)))
@@ -315,6 +321,49 @@ class Engine(object):
         persons = np.empty((n, self.max_persons), PERSON_DTYPE)
         self._check(self.lib.opb_stream_collect(self.ctx, slot, _ptr(headers), _ptr(persons)))
         return headers, persons
+
+    # -- face / hand nets (include/opb.h: opb_keypoints_*) ---------------------------------------
+    def forward_keypoint_maps(self, x, n_out=None):
+        """FaceNet / HandNet forward: x [N,3,H,W] float32 (already /256 - 0.5) or [N,H,W,3] uint8 -> [N,C,h,w]."""
+        x = np.ascontiguousarray(x)
+        if x.dtype == np.uint8:
+            n, h, w, _ = x.shape
+            fmt = U8_NHWC_BGR
+        else:
+            x = np.ascontiguousarray(x, np.float32)
+            n, _, h, w = x.shape
+            fmt = F32_NCHW
+        heat = np.empty((n, n_out or self.kp_channels, h // 8, w // 8), np.float32)
+        self._check(self.lib.opb_forward(self.ctx, _ptr(x), fmt, OPB_HOST, n, h, w, None, _ptr(heat), OPB_HOST))
+        return heat
+
+    @staticmethod
+    def _keypoint_list(out, valid):
+        return [[int(x), int(y), np.float32(c)] if v else None for (x, y, c), v in zip(out, valid)]
+
+    def keypoints_detect(self, img, net_size, thresh, mirror=False, return_maps=False):
+        """One BGR crop -> list of [x, y, conf] / None per keypoint channel (opb_keypoints_detect)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, _ = img.shape
+        planes = self.kp_channels - 1
+        out = np.empty((planes, 3), np.float64)
+        valid = np.empty(planes, np.int32)
+        maps = np.empty((planes, h, w), np.float32) if return_maps else None
+        self._check(self.lib.opb_keypoints_detect(self.ctx, _ptr(img), OPB_HOST, h, w, net_size, int(bool(mirror)),
+                                                  float(thresh), _ptr(out), _ptr(valid),
+                                                  _ptr(maps) if return_maps else None))
+        kps = self._keypoint_list(out, valid)
+        return (kps, maps) if return_maps else kps
+
+    def keypoints_from_heatmaps(self, heatmaps, thresh, mirror=False):
+        """heatmaps [C,H,W] float32, background channel already dropped (opb_keypoints_from_heatmaps)."""
+        hm = np.ascontiguousarray(heatmaps, np.float32)
+        planes, h, w = hm.shape
+        out = np.empty((planes, 3), np.float64)
+        valid = np.empty(planes, np.int32)
+        self._check(self.lib.opb_keypoints_from_heatmaps(self.ctx, _ptr(hm), OPB_HOST, planes, h, w, int(bool(mirror)),
+                                                         float(thresh), _ptr(out), _ptr(valid)))
+        return self._keypoint_list(out, valid)
 
     def image_detail(self, img):
         pk = np.empty((self.max_peaks, 5), np.float64)

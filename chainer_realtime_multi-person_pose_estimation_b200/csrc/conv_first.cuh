@@ -21,7 +21,7 @@ constexpr int CF_TH = 8, CF_TW = 32;
 __global__ void __launch_bounds__(256, 2)
 conv_first_kernel(const uint8_t* __restrict__ x_u8, const float* __restrict__ x_f32, const float* __restrict__ wt,
                   const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W, int cstride,
-                  int lo_off) {
+                  int lo_off, float u8_denom) {
   __shared__ __align__(16) float s_w[27 * 64];
   __shared__ float s_b[64];
   __shared__ float s_lut[256];
@@ -29,7 +29,7 @@ conv_first_kernel(const uint8_t* __restrict__ x_u8, const float* __restrict__ x_
   const int tid = threadIdx.x;
   for (int i = tid; i < 27 * 64; i += 256) s_w[i] = wt[i];
   if (tid < 64) s_b[tid] = bias[tid];
-  s_lut[tid] = __fsub_rn(__fdiv_rn(static_cast<float>(tid), 255.f), 0.5f);
+  s_lut[tid] = __fsub_rn(__fdiv_rn(static_cast<float>(tid), u8_denom), 0.5f);   // 255: pose (:429), 256: face / hand
   const int tiles_x = (W + CF_TW - 1) / CF_TW, tiles_y = (H + CF_TH - 1) / CF_TH;
   const int half = tid >> 7;           // output channels half*32 .. +31; warp-uniform so that every
                                        // weight LDS.128 is a single broadcast wavefront
@@ -151,7 +151,7 @@ namespace opb {
 // wth: [64][32] fp16 (row = output channel, k = (r*3+s)*3 + c, k >= 27 zero); bias [64] fp32
 __global__ void __launch_bounds__(128)
 conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict__ wth, const float* __restrict__ bias,
-                     __half* __restrict__ out, int N, int H, int W, int cstride) {
+                     __half* __restrict__ out, int N, int H, int W, int cstride, float u8_denom) {
   __shared__ __align__(1024) uint8_t sA[128 * 128];
   __shared__ __align__(1024) uint8_t sB[64 * 128];
   __shared__ __half s_lut[260];
@@ -162,7 +162,7 @@ conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict_
   const int tid = threadIdx.x, warp = tid >> 5;
   // one-time setup
   for (int i = tid; i < 257; i += 128)
-    s_lut[i] = (i < 256) ? __float2half_rn(__fsub_rn(__fdiv_rn(static_cast<float>(i), 255.f), 0.5f)) : __float2half(0.f);
+    s_lut[i] = (i < 256) ? __float2half_rn(__fsub_rn(__fdiv_rn(static_cast<float>(i), u8_denom), 0.5f)) : __float2half(0.f);
   if (tid < 64) {
     s_bias[tid] = bias[tid];
     // weight row `tid`: 4 chunks of 8 halfs, physical chunk = logical ^ (row & 7)

@@ -18,6 +18,7 @@
 #include "../../include/opb.h"
 #include "conv_first.cuh"
 #include "ingest.cuh"
+#include "keypoints.cuh"
 #include "conv_tcgen05.cuh"
 #include "conv_tcgen05_pair.cuh"
 #include "conv_tcgen05_swap.cuh"
@@ -82,7 +83,7 @@ struct Chain {            // everything cached for one (N, H, W)
   std::vector<Op> ops;
   std::vector<void*> allocs;
   float* paf_lo = nullptr;   // [N][38][h][w]
-  float* heat_lo = nullptr;  // [N][19][h][w]
+  float* heat_lo = nullptr;  // [N][19][h][w]  (keypoint nets: [N][kp_out][h][w])
   uint8_t* img_u8 = nullptr;
   float* img_f32 = nullptr;
   const uint8_t* img_u8_src = nullptr;   // where conv1_1 reads uint8 frames (img_u8, or the caller's device buffer)
@@ -113,6 +114,15 @@ struct PostWs {           // post-process workspace for (N, map_h, map_w)
   std::vector<void*> allocs;
 };
 
+struct KpWs {             // face / hand post-process workspace (grown on demand)
+  size_t cap = 0;             // floats per buffer
+  int planes = 0;
+  float* up = nullptr;        // upsampled maps [planes][H][W]
+  float* tmp = nullptr;       // after the axis-0 pass
+  ChannelMax* res = nullptr;  // [planes]
+  ChannelMax* h_res = nullptr;  // pinned
+};
+
 }  // namespace
 
 struct opb_ctx {
@@ -127,6 +137,9 @@ struct opb_ctx {
   int64_t launches = 0;
   EncodeTiledFn encode = nullptr;
   int precision = -1;
+  int kp_out = 0;            // 0: CocoPoseNet; 71 / 22: FaceNet / HandNet (channels of the final 1x1, incl. background)
+  float u8_denom = 255.f;    // uint8 normalisation: /255 (pose_detector.py:429) or /256 (face_detector.py:32)
+  KpWs* kp_ws = nullptr;
   std::map<std::string, HostLayer> host_layers;
   std::map<std::string, PackedW> packed;
   float* w_first = nullptr;  // conv1_1 [27][64] fp32
@@ -366,7 +379,7 @@ int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
     const int tiles = op.N * ((op.H + 15) / 16) * ((op.W + 7) / 8);
     const int grid = std::min(tiles, ctx->num_sms * 8);
     conv_first_tc_kernel<<<grid, 128, 0, ctx->stream>>>(ch->img_u8_src ? ch->img_u8_src : ch->img_u8, ctx->w_first_h,
-                                                        ctx->b_first, op.out, op.N, op.H, op.W, op.cstride);
+                                                        ctx->b_first, op.out, op.N, op.H, op.W, op.cstride, ctx->u8_denom);
     ctx->launches++;
     OPB_CUDA(ctx, cudaGetLastError());
     return OPB_OK;
@@ -375,7 +388,7 @@ int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
   const int grid = std::min(tiles, ctx->num_sms * 8);
   conv_first_kernel<<<grid, 256, 0, ctx->stream>>>(op.C == 1 ? (ch->img_u8_src ? ch->img_u8_src : ch->img_u8) : nullptr,
                                                    op.C == 1 ? nullptr : ch->img_f32, ctx->w_first, ctx->b_first,
-                                                   op.out, op.N, op.H, op.W, op.cstride, op.lo_off);
+                                                   op.out, op.N, op.H, op.W, op.cstride, op.lo_off, ctx->u8_denom);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   return OPB_OK;
@@ -555,7 +568,10 @@ int alloc_act(opb_ctx* ctx, Chain* ch, Act* a, int N, int H, int W, int C) {
   return dev_alloc(ctx, &a->p, a->bytes() / sizeof(__half), ch->allocs, true);
 }
 
+int build_chain_keypoint(opb_ctx* ctx, Chain* ch, int N, int H, int W);
+
 int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
+  if (ctx->kp_out) return build_chain_keypoint(ctx, ch, N, H, W);
   ch->N = N; ch->H = H; ch->W = W;
   const bool split = ctx->precision == OPB_PRECISION_PARITY;
   const int h8 = H / 8, w8 = W / 8;
@@ -648,6 +664,74 @@ int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
     RC(conv2("Mconv6", "Mconv6" + S + "_L1", "Mconv6" + S + "_L2", SA, 0, 128, SB, 0, 128, 128, 128, 1, nullptr, nullptr));
     RC(conv2("Mconv7", "Mconv7" + S + "_L1", "Mconv7" + S + "_L2", SB, 0, 128, CAT, 128, 166, 38, 19, 0,
              st == 6 ? ch->paf_lo : nullptr, st == 6 ? ch->heat_lo : nullptr));
+  }
+#undef RC
+  return OPB_OK;
+}
+
+// FaceNet / HandNet (models/FaceNet.py:78-161, models/HandNet.py): one branch, VGG front to conv5_2, conv5_3_CPM -> 128
+// features, stage 1 = two 1x1 convs, stages 2-6 on concat(previous maps, features).  Device concat layout:
+// [features 0..127 | maps 128..128+kp_out-1 | 0 pad] (the Mconv1 weights are permuted to match).
+int build_chain_keypoint(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
+  ch->N = N; ch->H = H; ch->W = W;
+  const bool split = ctx->precision == OPB_PRECISION_PARITY;
+  const int h8 = H / 8, w8 = W / 8, KC = ctx->kp_out;
+  int rc;
+#define RC(x) do { rc = (x); if (rc) return rc; } while (0)
+  RC(dev_alloc(ctx, &ch->img_u8, static_cast<size_t>(N) * H * W * 3, ch->allocs, false));
+  RC(dev_alloc(ctx, &ch->img_f32, static_cast<size_t>(N) * H * W * 3, ch->allocs, false));
+  RC(dev_alloc(ctx, &ch->paf_lo, 64, ch->allocs, true));
+  RC(dev_alloc(ctx, &ch->heat_lo, static_cast<size_t>(N) * KC * h8 * w8, ch->allocs, true));
+  Act B0, P1, B2, P2, B4, B5, P3, B6, B7, CAT, SA, SB, S512;
+  RC(alloc_act(ctx, ch, &B0, N, H, W, 64));
+  RC(alloc_act(ctx, ch, &P1, N, H / 2, W / 2, 64));
+  RC(alloc_act(ctx, ch, &B2, N, H / 2, W / 2, 128));
+  RC(alloc_act(ctx, ch, &P2, N, H / 4, W / 4, 128));
+  RC(alloc_act(ctx, ch, &B4, N, H / 4, W / 4, 256));
+  RC(alloc_act(ctx, ch, &B5, N, H / 4, W / 4, 256));
+  RC(alloc_act(ctx, ch, &P3, N, h8, w8, 256));
+  RC(alloc_act(ctx, ch, &B6, N, h8, w8, 512));
+  RC(alloc_act(ctx, ch, &B7, N, h8, w8, 512));
+  RC(alloc_act(ctx, ch, &CAT, N, h8, w8, round_up(128 + KC, 64)));
+  RC(alloc_act(ctx, ch, &SA, N, h8, w8, 128));
+  RC(alloc_act(ctx, ch, &SB, N, h8, w8, 128));
+  RC(alloc_act(ctx, ch, &S512, N, h8, w8, 512));
+  {
+    Op op; op.kind = OP_FIRST; op.tag = "conv1_1"; op.out = B0.p; op.N = N; op.H = H; op.W = W; op.C = 1;
+    op.cstride = B0.Ctot; op.lo_off = split ? B0.C : 0; ch->ops.push_back(op);
+  }
+  auto conv = [&](const std::string& layer, const Act& in, const Act& out, int out_coff, int cout, int relu = 1,
+                  int fuse_pool = 0, float* o32 = nullptr) -> int {
+    ConvSpec s{};
+    s.in[0] = &in; s.in_coff[0] = 0; s.wkey[0] = layer; s.out[0] = &out; s.out_coff[0] = out_coff;
+    s.cout_valid[0] = cout; s.out32[0] = o32; s.n_problems = 1; s.relu = relu; s.pool = fuse_pool;
+    return add_conv(ctx, ch, layer.rfind("Mconv", 0) == 0 ? layer.substr(0, 6) : layer, s);
+  };
+  RC(conv("conv1_2", B0, P1, 0, 64, 1, 1));      // max-pools (models/FaceNet.py:83,86,91) fused into the producers
+  RC(conv("conv2_1", P1, B2, 0, 128));
+  RC(conv("conv2_2", B2, P2, 0, 128, 1, 1));
+  RC(conv("conv3_1", P2, B4, 0, 256));
+  RC(conv("conv3_2", B4, B5, 0, 256));
+  RC(conv("conv3_3", B5, B4, 0, 256));
+  RC(conv("conv3_4", B4, P3, 0, 256, 1, 1));
+  RC(conv("conv4_1", P3, B6, 0, 512));
+  RC(conv("conv4_2", B6, B7, 0, 512));
+  RC(conv("conv4_3", B7, B6, 0, 512));
+  RC(conv("conv4_4", B6, B7, 0, 512));
+  RC(conv("conv5_1", B7, B6, 0, 512));
+  RC(conv("conv5_2", B6, B7, 0, 512));
+  RC(conv("conv5_3_CPM", B7, CAT, 0, 128));
+  RC(conv("conv6_1_CPM", CAT, S512, 0, 512));
+  RC(conv("conv6_2_CPM", S512, CAT, 128, KC, 0));
+  for (int st = 2; st <= 6; ++st) {
+    const std::string S = "_stage" + std::to_string(st);
+    RC(conv("Mconv1" + S, CAT, SA, 0, 128));
+    RC(conv("Mconv2" + S, SA, SB, 0, 128));
+    RC(conv("Mconv3" + S, SB, SA, 0, 128));
+    RC(conv("Mconv4" + S, SA, SB, 0, 128));
+    RC(conv("Mconv5" + S, SB, SA, 0, 128));
+    RC(conv("Mconv6" + S, SA, SB, 0, 128));
+    RC(conv("Mconv7" + S, SB, CAT, 128, KC, 0, 0, st == 6 ? ch->heat_lo : nullptr));
   }
 #undef RC
   return OPB_OK;
@@ -923,6 +1007,10 @@ void opb_destroy(opb_ctx* ctx) {
   for (auto& kv : ctx->posts) { free_all(kv.second->allocs); delete kv.second; }
   free_all(ctx->weight_allocs);
   if (ctx->ingest_buf) cudaFree(ctx->ingest_buf);
+  if (ctx->kp_ws) {
+    cudaFree(ctx->kp_ws->up); cudaFree(ctx->kp_ws->tmp); cudaFree(ctx->kp_ws->res); cudaFreeHost(ctx->kp_ws->h_res);
+    delete ctx->kp_ws;
+  }
   for (auto& sl : ctx->slots) {
     if (sl.d_frames) cudaFree(sl.d_frames);
     if (sl.h_frames) cudaFreeHost(sl.h_frames);
@@ -1005,6 +1093,37 @@ int opb_finalize_weights(opb_ctx* ctx, int precision_mode) {
   auto simple = [&](const std::string& name, int cin, int cout, int ks) -> int {
     return pack_weights(ctx, name, {{name, cout}}, identity_map(cin, round_up(cin, 64)), ks, split);
   };
+  ctx->kp_out = 0;
+  ctx->u8_denom = 255.f;
+  if (ctx->host_layers.count("conv6_2_CPM")) {
+    // FaceNet / HandNet (models/FaceNet.py:10-76): 52 layers, single branch; uint8 input is /256 - 0.5
+    const int KC = ctx->host_layers.at("conv6_2_CPM").cout;
+    if (KC < 2 || KC > 128) OPB_FAIL(ctx, OPB_ERR_ARG, "conv6_2_CPM must have 2..128 output channels");
+    const int kc_pad = KC <= 48 ? 48 : KC <= 64 ? 64 : 128;
+    const struct { const char* n; int cin, cout; } vgg[] = {
+        {"conv1_2", 64, 64},   {"conv2_1", 64, 128},  {"conv2_2", 128, 128}, {"conv3_1", 128, 256}, {"conv3_2", 256, 256},
+        {"conv3_3", 256, 256}, {"conv3_4", 256, 256}, {"conv4_1", 256, 512}, {"conv4_2", 512, 512}, {"conv4_3", 512, 512},
+        {"conv4_4", 512, 512}, {"conv5_1", 512, 512}, {"conv5_2", 512, 512}, {"conv5_3_CPM", 512, 128}};
+    for (auto& b : vgg)
+      if ((rc = simple(b.n, b.cin, b.cout, 3))) return rc;
+    if ((rc = simple("conv6_1_CPM", 128, 512, 1))) return rc;
+    if ((rc = pack_weights(ctx, "conv6_2_CPM", {{"conv6_2_CPM", kc_pad}}, identity_map(512, 512), 1, split))) return rc;
+    // device concat [features 0..127 | maps 128..128+KC-1]; reference order is (h, feature_map) (models/FaceNet.py:108)
+    std::vector<int> cat_map(round_up(128 + KC, 64), -1);
+    for (int d = 0; d < 128; ++d) cat_map[d] = KC + d;
+    for (int d = 0; d < KC; ++d) cat_map[128 + d] = d;
+    for (int st = 2; st <= 6; ++st) {
+      const std::string S = "_stage" + std::to_string(st);
+      if ((rc = pack_weights(ctx, "Mconv1" + S, {{"Mconv1" + S, 128}}, cat_map, 7, split))) return rc;
+      for (int i = 2; i <= 5; ++i)
+        if ((rc = simple("Mconv" + std::to_string(i) + S, 128, 128, 7))) return rc;
+      if ((rc = simple("Mconv6" + S, 128, 128, 1))) return rc;
+      if ((rc = pack_weights(ctx, "Mconv7" + S, {{"Mconv7" + S, kc_pad}}, identity_map(128, 128), 1, split))) return rc;
+    }
+    ctx->kp_out = KC;
+    ctx->u8_denom = 256.f;
+    return OPB_OK;
+  }
   const struct { const char* n; int cin, cout; } backbone[] = {
       {"conv1_2", 64, 64},    {"conv2_1", 64, 128},   {"conv2_2", 128, 128},     {"conv3_1", 128, 256},
       {"conv3_2", 256, 256},  {"conv3_3", 256, 256},  {"conv3_4", 256, 256},     {"conv4_1", 256, 512},
@@ -1060,8 +1179,8 @@ int opb_forward(opb_ctx* ctx, const void* x, int x_format, int x_loc, int n, int
   }
   if ((rc = run_chain(ctx, ch, x_format == OPB_U8_NHWC_BGR))) return rc;
   const size_t lo = static_cast<size_t>(n) * (h / 8) * (w / 8);
-  if (paf_out && (rc = copy_out(ctx, paf_out, ch->paf_lo, lo * 38 * 4, out_loc))) return rc;
-  if (heat_out && (rc = copy_out(ctx, heat_out, ch->heat_lo, lo * 19 * 4, out_loc))) return rc;
+  if (paf_out && !ctx->kp_out && (rc = copy_out(ctx, paf_out, ch->paf_lo, lo * 38 * 4, out_loc))) return rc;
+  if (heat_out && (rc = copy_out(ctx, heat_out, ch->heat_lo, lo * (ctx->kp_out ? ctx->kp_out : 19) * 4, out_loc))) return rc;
   OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return OPB_OK;
 }
@@ -1280,6 +1399,7 @@ int opb_group(opb_ctx* ctx, const double* conns, const int* conn_counts, const d
 static int run_pipeline(opb_ctx* ctx, Chain* ch, PostWs* ws, int n, int h, int w, int map_h, int map_w, double img_len,
                         const float* inject_paf, const float* inject_heat) {
   int rc;
+  if (ctx->kp_out) OPB_FAIL(ctx, OPB_ERR_STATE, "this context holds a face / hand net: use opb_keypoints_detect");
   if ((rc = run_chain(ctx, ch, true))) return rc;
   const int h8 = h / 8, w8 = w / 8;
   const float* paf_lo = inject_paf ? inject_paf : ch->paf_lo;
@@ -1570,6 +1690,86 @@ int opb_stream_collect(opb_ctx* ctx, int slot, opb_image_header* headers_out, op
   memcpy(headers_out, sl.h_result, sizeof(ImageHeader) * sl.n);
   memcpy(persons_out, sl.h_result + sizeof(ImageHeader) * sl.n, sizeof(PersonOut) * sl.n * static_cast<size_t>(ctx->prm.max_persons));
   return OPB_OK;
+}
+
+static int kp_workspace(opb_ctx* ctx, int planes, int H, int W, KpWs** out) {
+  if (!ctx->kp_ws) ctx->kp_ws = new KpWs();
+  KpWs* ws = ctx->kp_ws;
+  const size_t need = static_cast<size_t>(planes) * H * W;
+  if (ws->cap < need || ws->planes < planes) {
+    OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ws->up); cudaFree(ws->tmp); cudaFree(ws->res); cudaFreeHost(ws->h_res);
+    ws->up = ws->tmp = nullptr; ws->res = nullptr; ws->h_res = nullptr; ws->cap = 0; ws->planes = 0;
+    OPB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ws->up), need * 4));
+    OPB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ws->tmp), need * 4));
+    OPB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ws->res), sizeof(ChannelMax) * planes));
+    OPB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ws->h_res), sizeof(ChannelMax) * planes));
+    ws->cap = need; ws->planes = planes;
+  }
+  *out = ws;
+  return OPB_OK;
+}
+
+// smooth ws->up [planes][H][W] (both passes), per-plane maximum, records to the host
+static int kp_peaks(opb_ctx* ctx, KpWs* ws, int planes, int H, int W, int mirror, double thresh, double* out, int32_t* valid) {
+  dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, planes);
+  gauss_pass_kernel<0><<<grid, block, 0, ctx->stream>>>(ws->up, ws->tmp, H, W, ctx->taps);
+  gauss_pass_kernel<1><<<grid, block, 0, ctx->stream>>>(ws->tmp, ws->up, H, W, ctx->taps);
+  channel_argmax_kernel<<<planes, 256, 0, ctx->stream>>>(ws->up, H, W, mirror, ws->res);
+  ctx->launches += 3;
+  OPB_CUDA(ctx, cudaGetLastError());
+  OPB_CUDA(ctx, cudaMemcpyAsync(ws->h_res, ws->res, sizeof(ChannelMax) * planes, cudaMemcpyDeviceToHost, ctx->stream));
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const float th = static_cast<float>(thresh);      // `max_value > thresh` with a float32 max_value compares in float32
+  for (int c = 0; c < planes; ++c) {
+    const ChannelMax& r = ws->h_res[c];
+    valid[c] = r.value > th ? 1 : 0;
+    // np.array(np.where(g == m)).flatten() = [y0..yk-1, x0..xk-1]; the reference reads [1] as x and [0] as y
+    const int y0 = r.key0 / W, x0 = r.key0 - y0 * W;
+    out[c * 3 + 0] = r.count >= 2 ? static_cast<double>(r.key1 / W) : static_cast<double>(x0);
+    out[c * 3 + 1] = static_cast<double>(y0);
+    out[c * 3 + 2] = static_cast<double>(r.value);
+  }
+  return OPB_OK;
+}
+
+int opb_keypoints_from_heatmaps(opb_ctx* ctx, const float* heat, int heat_loc, int planes, int h, int w, int mirror,
+                                double thresh, double* out, int32_t* valid) {
+  if (!ctx || !heat || !out || !valid || planes <= 0 || h <= 0 || w <= 0) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  KpWs* ws = nullptr;
+  int rc = kp_workspace(ctx, planes, h, w, &ws);
+  if (rc) return rc;
+  if ((rc = copy_in(ctx, ws->up, heat, static_cast<size_t>(planes) * h * w * 4, heat_loc))) return rc;
+  return kp_peaks(ctx, ws, planes, h, w, mirror, thresh, out, valid);
+}
+
+int opb_keypoints_detect(opb_ctx* ctx, const uint8_t* img, int img_loc, int img_h, int img_w, int net_size, int mirror,
+                         double thresh, double* out, int32_t* valid, float* maps_out) {
+  if (!ctx || !img || !out || !valid || img_h <= 0 || img_w <= 0) return OPB_ERR_ARG;
+  if (!ctx->kp_out) OPB_FAIL(ctx, OPB_ERR_STATE, "this context holds the pose net: load FaceNet / HandNet weights first");
+  cudaSetDevice(ctx->device);
+  Chain* ch = nullptr;
+  int rc = get_chain(ctx, 1, net_size, net_size, &ch);
+  if (rc) return rc;
+  const size_t in_b = static_cast<size_t>(img_h) * img_w * 3;
+  const uint8_t* d_src = img;
+  if (img_loc == OPB_HOST) {
+    if ((rc = ensure_ingest(ctx, in_b + 512))) return rc;
+    if ((rc = copy_in(ctx, ctx->ingest_buf, img, in_b, OPB_HOST))) return rc;
+    d_src = ctx->ingest_buf;
+  }
+  // cv2.resize(crop, (368, 368)) (face_detector.py:31), bit-exact uint8 INTER_LINEAR on the device
+  if ((rc = launch_resize_u8(ctx, d_src, 1, img_h, img_w, ch->img_u8, net_size, net_size))) return rc;
+  ch->img_u8_src = nullptr;
+  if ((rc = run_chain(ctx, ch, true))) return rc;
+  const int planes = ctx->kp_out - 1;              // the last channel is background (face_detector.py:59)
+  KpWs* ws = nullptr;
+  if ((rc = kp_workspace(ctx, planes, img_h, img_w, &ws))) return rc;
+  // F.resize_images(hs[-1], (crop_h, crop_w)) (face_detector.py:38)
+  if ((rc = launch_upsample(ctx, ch->heat_lo, planes, net_size / 8, net_size / 8, ws->up, img_h, img_w))) return rc;
+  if (maps_out && (rc = copy_out(ctx, maps_out, ws->up, static_cast<size_t>(planes) * img_h * img_w * 4, OPB_HOST))) return rc;
+  return kp_peaks(ctx, ws, planes, img_h, img_w, mirror, thresh, out, valid);
 }
 
 void* opb_device_buffer(opb_ctx* ctx, int which) {

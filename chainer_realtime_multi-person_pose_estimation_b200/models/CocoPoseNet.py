@@ -11,6 +11,11 @@ reference's callers actually read ([-1], pose_detector.py:453-454,501-502).
 """
 import numpy as np
 
+try:
+    from ._container import NetContainer, _ConvParam  # noqa: F401
+except ImportError:  # flat import, like the reference
+    from models._container import NetContainer, _ConvParam  # noqa: F401
+
 
 def _build_layer_table():
     t = [("conv1_1", 3, 64, 3), ("conv1_2", 64, 64, 3), ("conv2_1", 64, 128, 3), ("conv2_2", 128, 128, 3),
@@ -51,68 +56,9 @@ def conv_flops_per_image(h, w):
     return total
 
 
-class _ConvParam(object):
-    """Stand-in for a Chainer link: `.W.data` / `.b.data` numpy arrays."""
-
-    class _P(object):
-        def __init__(self, a):
-            self.data = a
-
-        @property
-        def array(self):
-            return self.data
-
-    def __init__(self, W, b):
-        self.W = _ConvParam._P(W)
-        self.b = _ConvParam._P(b)
-
-
-class CocoPoseNet(object):
-    insize = 368
-
-    def __init__(self, seed=None):
-        # Chainer's default is LeCunNormal from numpy's *global* RNG (not reproducible);
-        # here: sigma = sqrt(1/fan_in), b = 0, from RandomState(seed or 0).
-        rs = np.random.RandomState(0 if seed is None else seed)
-        self._names = []
-        for name, cin, cout, k in LAYERS:
-            W = (rs.standard_normal((cout, cin, k, k)) * np.sqrt(1.0 / (cin * k * k))).astype(np.float32)
-            setattr(self, name, _ConvParam(W, np.zeros(cout, np.float32)))
-            self._names.append(name)
-        self._engine = None       # set by PoseDetector (device context owning the packed weights)
-
-    # -- chainer.Chain-like helpers -------------------------------------------------
-    def children_items(self):
-        return [(n, getattr(self, n)) for n in self._names]
-
-    def load_npz(self, path_or_dict):
-        """Chainer save_npz layout: '<layer>/W' [Cout,Cin,k,k] f32 and '<layer>/b' [Cout]."""
-        f = np.load(path_or_dict) if isinstance(path_or_dict, str) else path_or_dict
-        for name, cin, cout, k in LAYERS:
-            W = np.ascontiguousarray(f[name + "/W"], np.float32)
-            b = np.ascontiguousarray(f[name + "/b"], np.float32)
-            if W.shape != (cout, cin, k, k) or b.shape != (cout,):
-                raise ValueError("bad shape for layer %s: %s %s" % (name, W.shape, b.shape))
-            link = getattr(self, name)
-            link.W.data, link.b.data = W, b
-        self._engine = None
-
-    def state_dict(self):
-        d = {}
-        for n, l in self.children_items():
-            d[n + "/W"] = l.W.data
-            d[n + "/b"] = l.b.data
-        return d
-
-    def to_gpu(self, device=None):
-        return self
-
-    def to_cpu(self):
-        return self
+class CocoPoseNet(NetContainer):
+    LAYERS = LAYERS
 
     def __call__(self, x):
-        if self._engine is None:
-            raise RuntimeError("CocoPoseNet is not bound to a device engine; construct a PoseDetector "
-                               "with model=<this object> (there is no CPU forward in this package)")
-        paf, heat = self._engine.forward(np.ascontiguousarray(x, np.float32))
+        paf, heat = self._bound_engine().forward(np.ascontiguousarray(x, np.float32))
         return [paf] * 6, [heat] * 6

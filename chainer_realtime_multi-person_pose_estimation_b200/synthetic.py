@@ -22,12 +22,12 @@ _LIMBS = ((1, 8), (8, 9), (9, 10), (1, 11), (11, 12), (12, 13), (1, 2), (2, 3), 
           (1, 5), (5, 6), (6, 7), (5, 17), (1, 0), (0, 14), (0, 15), (14, 16), (15, 17))
 
 
-def he_weights(seed=0, bias_scale=0.02, gain=2.0):
+def he_weights(seed=0, bias_scale=0.02, gain=2.0, layers=None):
     """W ~ N(0, sqrt(gain/fan_in)), b ~ N(0, bias_scale); one RandomState stream in the
-    reference's layer declaration order (models/CocoPoseNet.py:26-129)."""
+    reference's layer declaration order (models/CocoPoseNet.py:26-129; `layers` = another net's table)."""
     rs = np.random.RandomState(seed)
     out = {}
-    for name, cin, cout, k in LAYERS:
+    for name, cin, cout, k in (LAYERS if layers is None else layers):
         fan_in = cin * k * k
         out[name + "/W"] = (rs.standard_normal((cout, cin, k, k)) * np.sqrt(gain / fan_in)).astype(np.float32)
         out[name + "/b"] = (rs.standard_normal(cout) * bias_scale).astype(np.float32)

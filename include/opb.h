@@ -181,6 +181,23 @@ int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, in
                       const float* inject_heat, int slot);
 int opb_stream_collect(opb_ctx* ctx, int slot, opb_image_header* headers_out, opb_person* persons_out);
 
+/* -- face / hand nets.  A context whose loaded layers contain "conv6_2_CPM" is a FaceNet /
+ *    HandNet context (models/FaceNet.py:10-76, models/HandNet.py; 52 layers, final 1x1 with 71 / 22 channels):
+ *    opb_forward then returns only heat_out [n, 71|22, h/8, w/8] and uint8 input is normalised /256 - 0.5
+ *    (face_detector.py:32).
+ *    opb_keypoints_detect = FaceDetector.__call__ (face_detector.py:28-41) / HandDetector.__call__
+ *    (hand_detector.py:28-51) for one BGR crop [img_h,img_w,3]: device cv2-exact resize to net_size^2,
+ *    forward, F.resize_images to the crop size, gaussian_filter(sigma 2.5), per-channel maximum.
+ *    out [C-1][3] = (x, y, conf), valid [C-1] = conf > thresh (float32 compare).  mirror = 1 reports positions
+ *    in the horizontally flipped maps (hand_type "left": the caller passes the already flipped crop,
+ *    hand_detector.py:29-30,46-47).  maps_out (host, may be NULL) receives the unsmoothed upsampled maps.
+ *    opb_keypoints_from_heatmaps = compute_peaks_from_heatmaps (face_detector.py:55-67) on caller maps
+ *    [planes,h,w] (background channel already dropped).                                          */
+int opb_keypoints_detect(opb_ctx* ctx, const uint8_t* img, int img_loc, int img_h, int img_w, int net_size,
+                         int mirror, double thresh, double* out, int32_t* valid, float* maps_out);
+int opb_keypoints_from_heatmaps(opb_ctx* ctx, const float* heat, int heat_loc, int planes, int h, int w,
+                                int mirror, double thresh, double* out, int32_t* valid);
+
 /* device pointers of the last opb_detect_batch outputs/intermediates (valid until the next
  * call with a different shape): 0 paf_lo, 1 heat_lo, 2 pafs (full-res), 3 heatmaps (full-res),
  * 4 headers, 5 persons, 6 peak table ([N,max_peaks] of {int32 type,x,y; float score})       */

@@ -136,6 +136,46 @@ def main():
     precise_padded(ref, he)
 
 
+def keypoint_goldens():
+    """G8/G9: FaceDetector / HandDetector (face_detector.py:28-41, hand_detector.py:28-51) run verbatim on
+    seeded crops with He-initialised FaceNet / HandNet weights (seed 0)."""
+    tmp = tempfile.mkdtemp()
+    mods = {"face": importlib.import_module("chainer_realtime_multi-person_pose_estimation_b200.models.FaceNet"),
+            "hand": importlib.import_module("chainer_realtime_multi-person_pose_estimation_b200.models.HandNet")}
+    cases = [("face", reference_loader.load_face, "FaceDetector", "facenet", (150, 170, 11), {}),
+             ("face", reference_loader.load_face, "FaceDetector", "facenet", (401, 401, 12), {}),
+             ("hand", reference_loader.load_hand, "HandDetector", "handnet", (120, 131, 13), {"hand_type": "right"}),
+             ("hand", reference_loader.load_hand, "HandDetector", "handnet", (120, 131, 13), {"hand_type": "left"})]
+    dets = {}
+    for kind, loader, cls, arch, (h, w, seed), kw in cases:
+        if kind not in dets:
+            f = os.path.join(tmp, kind + ".npz")
+            np.savez(f, **syn.he_weights(0, layers=mods[kind].LAYERS))
+            dets[kind] = getattr(loader(), cls)(arch, f, device=-1)
+        det = dets[kind]
+        rec = {}
+        model = det.model
+        orig_call = type(model).__call__
+
+        def wrapped(self, x, _o=orig_call, _r=rec):
+            hs = _o(self, x)
+            _r["heat_lo"] = np.array(hs[-1].data[0], np.float32)
+            return hs
+
+        type(model).__call__ = wrapped
+        try:
+            kps = det(syn.procedural_image(h, w, seed=seed), **kw)
+        finally:
+            type(model).__call__ = orig_call
+        valid = np.array([k is not None for k in kps])
+        xy = np.array([[k[0], k[1]] if k is not None else [-1, -1] for k in kps], np.int64)
+        conf = np.array([k[2] if k is not None else 0 for k in kps], np.float32)
+        name = "%s_%dx%d_he0%s.npz" % (kind, h, w, "_" + kw["hand_type"] if kw else "")
+        np.savez_compressed(os.path.join(GOLD, name), heat_lo=rec["heat_lo"], valid=valid, xy=xy, conf=conf,
+                            img_hw_seed=np.array([h, w, seed]))
+        print(name, int(valid.sum()), "of", len(kps))
+
+
 def precise_padded(ref, he):
     # G7: precise path on a 200x300 frame: the scaled images (184x276, 368x552, 552x828, 736x1104) need
     # right-padding to a multiple of 8 at scales 0.5 and 1.5 -> exercises pad_image / crop (:445,:462,:466)

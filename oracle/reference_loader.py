@@ -29,15 +29,18 @@ def available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "pose_detector.py"))
 
 
-def load():
-    """Returns the reference `pose_detector` module object (executed verbatim)."""
+_REF_MODS = ("chainer", "entity", "models", "models.CocoPoseNet", "models.FaceNet", "models.HandNet", "pose_detector",
+             "face_detector", "hand_detector")
+
+
+def _exec_reference(filename, modname, fixes=()):
+    """Executes one reference file verbatim (plus the listed in-memory source fixes) as module `modname`."""
     if not available():
         raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
-    if "ref_pose_detector" in sys.modules:
-        return sys.modules["ref_pose_detector"]
+    if modname in sys.modules:
+        return sys.modules[modname]
     saved_path = list(sys.path)
-    saved_mods = {k: sys.modules.get(k) for k in ("chainer", "entity", "models", "models.CocoPoseNet",
-                                                  "models.FaceNet", "models.HandNet", "pose_detector")}
+    saved_mods = {k: sys.modules.get(k) for k in _REF_MODS}
     for k in list(sys.modules):
         if k == "chainer" or k.startswith("chainer.") or k in saved_mods:
             del sys.modules[k]
@@ -46,14 +49,15 @@ def load():
     try:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            with open(os.path.join(REFERENCE_ROOT, "pose_detector.py"), "r") as f:
+            with open(os.path.join(REFERENCE_ROOT, filename), "r") as f:
                 src = f.read()
-            assert src.count(_OLD) == 1, "reference source changed; numpy-2 fix does not apply"
-            src = src.replace(_OLD, _NEW)
-            mod = types.ModuleType("ref_pose_detector")
-            mod.__file__ = os.path.join(REFERENCE_ROOT, "pose_detector.py")
+            for old, new in fixes:
+                assert src.count(old) == 1, "reference source changed; fix does not apply"
+                src = src.replace(old, new)
+            mod = types.ModuleType(modname)
+            mod.__file__ = os.path.join(REFERENCE_ROOT, filename)
             code = compile(src, mod.__file__, "exec")
-            mod.__dict__["__name__"] = "ref_pose_detector"
+            mod.__dict__["__name__"] = modname
             exec(code, mod.__dict__)
             mod.ref_entity = sys.modules["entity"]
             mod.ref_chainer = sys.modules["chainer"]
@@ -61,11 +65,25 @@ def load():
         sys.path[:] = saved_path
         # leave the reference modules reachable only through `mod`
         for k in list(sys.modules):
-            if k == "chainer" or k.startswith("chainer.") or k in ("entity", "models", "models.CocoPoseNet",
-                                                                    "models.FaceNet", "models.HandNet"):
+            if k == "chainer" or k.startswith("chainer.") or k in _REF_MODS[1:]:
                 del sys.modules[k]
         for k, v in saved_mods.items():
             if v is not None:
                 sys.modules[k] = v
-    sys.modules["ref_pose_detector"] = mod
+    sys.modules[modname] = mod
     return mod
+
+
+def load():
+    """Returns the reference `pose_detector` module object (executed verbatim + the numpy-2 fix)."""
+    return _exec_reference("pose_detector.py", "ref_pose_detector", ((_OLD, _NEW),))
+
+
+def load_face():
+    """The reference `face_detector` module (face_detector.py), verbatim."""
+    return _exec_reference("face_detector.py", "ref_face_detector")
+
+
+def load_hand():
+    """The reference `hand_detector` module (hand_detector.py), verbatim."""
+    return _exec_reference("hand_detector.py", "ref_hand_detector")

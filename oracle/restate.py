@@ -510,3 +510,95 @@ def detect_precise(weights, img, return_parts=False):
         return poses, subsets[:, -2], dict(pafs=pafs, heatmaps=heat, all_peaks=peaks, connections=conns,
                                             subsets=subsets)
     return poses, subsets[:, -2]
+
+
+# ----------------------------------------------------------------------------
+# face / hand keypoint nets (models/FaceNet.py, models/HandNet.py, face_detector.py, hand_detector.py)
+# ----------------------------------------------------------------------------
+KEYPOINT_PEAK_THRESH = 0.1          # entity.py:128,144 (face_/hand_heatmap_peak_thresh)
+KEYPOINT_IMG_SIZE = 368             # entity.py:127,143
+
+
+def keypoint_layer_table(n_out):
+    """[(name, cin, cout, ksize)] of FaceNet (n_out 71) / HandNet (n_out 22), models/FaceNet.py:10-76."""
+    t = [("conv1_1", 3, 64, 3), ("conv1_2", 64, 64, 3), ("conv2_1", 64, 128, 3), ("conv2_2", 128, 128, 3),
+         ("conv3_1", 128, 256, 3), ("conv3_2", 256, 256, 3), ("conv3_3", 256, 256, 3), ("conv3_4", 256, 256, 3),
+         ("conv4_1", 256, 512, 3), ("conv4_2", 512, 512, 3), ("conv4_3", 512, 512, 3), ("conv4_4", 512, 512, 3),
+         ("conv5_1", 512, 512, 3), ("conv5_2", 512, 512, 3), ("conv5_3_CPM", 512, 128, 3),
+         ("conv6_1_CPM", 128, 512, 1), ("conv6_2_CPM", 512, n_out, 1)]
+    for st in range(2, 7):
+        t.append(("Mconv1_stage%d" % st, 128 + n_out, 128, 7))
+        for i in (2, 3, 4, 5):
+            t.append(("Mconv%d_stage%d" % (i, st), 128, 128, 7))
+        t.append(("Mconv6_stage%d" % st, 128, 128, 1))
+        t.append(("Mconv7_stage%d" % st, 128, n_out, 1))
+    return t
+
+
+def keypoint_forward(weights, x):
+    """models/FaceNet.py:78-161 (HandNet identical) with torch CPU fp32: x [N,3,368,368] -> last-stage maps
+    [N,n_out,46,46].  `weights`: {layer: (W, b)}."""
+    import torch
+    import torch.nn.functional as F
+
+    def conv(name, h, relu=True):
+        W, b = weights[name]
+        y = F.conv2d(h, torch.from_numpy(W), torch.from_numpy(b), stride=1, padding=(W.shape[2] - 1) // 2)
+        return torch.relu(y) if relu else y
+
+    with torch.no_grad():
+        h = torch.from_numpy(np.ascontiguousarray(x, np.float32))
+        h = conv("conv1_2", conv("conv1_1", h))
+        h = F.max_pool2d(h, 2, 2, ceil_mode=True)
+        h = conv("conv2_2", conv("conv2_1", h))
+        h = F.max_pool2d(h, 2, 2, ceil_mode=True)
+        for n in ("conv3_1", "conv3_2", "conv3_3", "conv3_4"):
+            h = conv(n, h)
+        h = F.max_pool2d(h, 2, 2, ceil_mode=True)
+        for n in ("conv4_1", "conv4_2", "conv4_3", "conv4_4", "conv5_1", "conv5_2", "conv5_3_CPM"):
+            h = conv(n, h)
+        feat = h
+        h = conv("conv6_2_CPM", conv("conv6_1_CPM", feat), relu=False)
+        for st in range(2, 7):
+            h = torch.cat((h, feat), dim=1)                      # order (h, feature_map), models/FaceNet.py:108
+            for i in (1, 2, 3, 4, 5, 6):
+                h = conv("Mconv%d_stage%d" % (i, st), h)
+            h = conv("Mconv7_stage%d" % st, h, relu=False)
+    return h.numpy()
+
+
+def keypoint_preprocess(img):
+    """face_detector.py:32: float32, /256 (not /255), -0.5, HWC -> NCHW."""
+    return np.array(img[np.newaxis], dtype=np.float32).transpose(0, 3, 1, 2) / 256 - 0.5
+
+
+def keypoints_from_heatmaps(heatmaps, thresh=KEYPOINT_PEAK_THRESH):
+    """face_detector.py:55-67 / hand_detector.py:65-77 (CPU branch): per channel except the last (background) the
+    smoothed map's maximum; above `thresh` (compared in float32) -> [x, y, conf] else None.  With k >= 2 exact
+    ties the reference's flatten() of np.where yields [y0..yk-1, x0..xk-1], so it reports (x, y) = (y1, y0)."""
+    out = []
+    sm = gaussian_smooth(np.ascontiguousarray(heatmaps[:-1], np.float32))
+    for m in sm:
+        mx = m.max()
+        if mx > np.float32(thresh):
+            coords = np.array(np.where(m == mx)).flatten().tolist()
+            out.append([coords[1], coords[0], mx])
+        else:
+            out.append(None)
+    return out
+
+
+def detect_keypoints(weights, img, hand_type=None):
+    """FaceDetector.__call__ (face_detector.py:28-41) when hand_type is None, else HandDetector.__call__
+    (hand_detector.py:28-51; 'left' mirrors the crop before and the maps after the network)."""
+    import cv2
+    if hand_type == "left":
+        img = cv2.flip(img, 1)
+    h, w = img.shape[:2]
+    resized = cv2_resize_linear_u8(np.ascontiguousarray(img), (KEYPOINT_IMG_SIZE, KEYPOINT_IMG_SIZE))
+    lo = keypoint_forward(weights, keypoint_preprocess(resized))
+    maps = resize_bilinear_align_corners(lo, (h, w))[0]
+    if hand_type == "left":
+        maps = np.ascontiguousarray(maps[:, :, ::-1])
+    return keypoints_from_heatmaps(maps), lo[0], maps
+

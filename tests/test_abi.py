@@ -121,3 +121,46 @@ def test_camera_demo_import_flow_and_drawing():
                              os.path.join(ROOT, "chainer_realtime_multi-person_pose_estimation_b200", "compat"))
     r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout
+
+
+def test_demo_import_flow_face_hand_modules():
+    """What demo.py does before inference (reference demo.py:1-20), flat imports: the three detector modules and
+    their drawing helpers; host-only helpers (draw_*, crop_face) checked against the reference's own functions when
+    the reference tree is present."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import chainer\n"
+        "from entity import params\n"
+        "from pose_detector import PoseDetector, draw_person_pose\n"
+        "from face_detector import FaceDetector, draw_face_keypoints, crop_face\n"
+        "from hand_detector import HandDetector, draw_hand_keypoints\n"
+        "assert set(params['archs']) == {'posenet', 'facenet', 'handnet'}\n"
+        "assert len(params['archs']['facenet'].LAYERS) == 52 and len(params['archs']['handnet'].LAYERS) == 52\n"
+        "img = np.zeros((100, 120, 3), np.uint8)\n"
+        "face = [[10 + i, 20 + (i %% 7), np.float32(0.5)] if i %% 5 else None for i in range(70)]\n"
+        "hand = [[15 + 3 * i, 30 + (i %% 4), np.float32(0.5)] if i %% 6 else None for i in range(21)]\n"
+        "a = draw_face_keypoints(img, face, (3, 4)); b = draw_hand_keypoints(img, hand, (3, 4))\n"
+        "assert a.any() and b.any() and not img.any()\n"
+        "pf, lt = crop_face(np.arange(100 * 120 * 3, dtype=np.uint8).reshape(100, 120, 3), (30, 20, 40, 50))\n"
+        "assert pf.shape[0] == pf.shape[1] and lt == (20, 7)\n"
+        "np.save(sys.argv[1], np.concatenate([a.ravel(), b.ravel(), pf.ravel()]))\n"
+        "print('ok')\n") % (os.path.join(ROOT, "chainer_realtime_multi-person_pose_estimation_b200"),
+                             os.path.join(ROOT, "chainer_realtime_multi-person_pose_estimation_b200", "compat"))
+    import tempfile
+    out = os.path.join(tempfile.mkdtemp(), "draw.npy")
+    r = subprocess.run([sys.executable, "-c", code, out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout
+    from oracle import reference_loader
+    if reference_loader.available():
+        rf, rh = reference_loader.load_face(), reference_loader.load_hand()
+        img = np.zeros((100, 120, 3), np.uint8)
+        face = [[10 + i, 20 + (i % 7), np.float32(0.5)] if i % 5 else None for i in range(70)]
+        hand = [[15 + 3 * i, 30 + (i % 4), np.float32(0.5)] if i % 6 else None for i in range(21)]
+        pf, _ = rf.crop_face(np.arange(100 * 120 * 3, dtype=np.uint8).reshape(100, 120, 3), (30, 20, 40, 50))
+        ref = np.concatenate([rf.draw_face_keypoints(img, face, (3, 4)).ravel(),
+                              rh.draw_hand_keypoints(img, hand, (3, 4)).ravel(), pf.ravel()])
+        assert np.array_equal(np.load(out), ref)
+

@@ -140,3 +140,23 @@ def test_grouping_third_match_raises_index_error():
     conns[6] = np.array([[0., 6., 1.], [2., 6., 0.9], [4., 6., 0.8]])
     with pytest.raises(IndexError):
         R.grouping_key_points(conns, peaks)
+
+
+@pytest.mark.parametrize("name,kind,hand_type", [("face_150x170_he0.npz", "face", None),
+                                                  ("hand_120x131_he0_right.npz", "hand", "right"),
+                                                  ("hand_120x131_he0_left.npz", "hand", "left")])
+def test_keypoint_restatement_matches_reference_goldens(name, kind, hand_type):
+    """FaceDetector / HandDetector run verbatim (oracle/make_goldens.py keypoint_goldens) vs the restatement."""
+    g = load_golden(name)
+    h, w, seed = (int(v) for v in g["img_hw_seed"])
+    mod = pkg("models.FaceNet" if kind == "face" else "models.HandNet")
+    wd = pkg("synthetic").he_weights(0, layers=mod.LAYERS)
+    weights = {n: (wd[n + "/W"], wd[n + "/b"]) for n, _, _, _ in mod.LAYERS}
+    assert [tuple(t) for t in R.keypoint_layer_table(mod.N_OUT)] == [tuple(t) for t in mod.LAYERS]
+    kps, lo, _ = R.detect_keypoints(weights, pkg("synthetic").procedural_image(h, w, seed=seed), hand_type)
+    assert np.array_equal(lo, g["heat_lo"])
+    assert [k is not None for k in kps] == g["valid"].tolist()
+    for k, xy, c in zip(kps, g["xy"], g["conf"]):
+        if k is not None:
+            assert (k[0], k[1]) == (xy[0], xy[1]) and np.float32(k[2]) == c
+

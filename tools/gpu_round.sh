@@ -12,6 +12,7 @@ for s in $STAGES; do
     probe) timeout 900 python tools/conv_probe.py > gpurun_out/probe.log 2>&1; tail -n 60 gpurun_out/probe.log ;;
     post)  timeout 900 python -m pytest tests/test_gpu_postprocess.py -m gpu -q --timeout 600 > gpurun_out/post.log 2>&1; tail -n 30 gpurun_out/post.log ;;
     conv)  timeout 900 python -m pytest tests/test_gpu_conv.py -m gpu -q --timeout 300 > gpurun_out/conv.log 2>&1; tail -n 30 gpurun_out/conv.log ;;
+    kp)    timeout 900 python -m pytest tests/test_gpu_keypoints.py -m gpu -q -s --timeout 600 > gpurun_out/kp.log 2>&1; tail -n 40 gpurun_out/kp.log ;;
     pipe)  timeout 1500 python -m pytest tests/test_gpu_pipeline.py -m gpu -q -s --timeout 900 > gpurun_out/pipe.log 2>&1; tail -n 40 gpurun_out/pipe.log ;;
     smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -n 5 gpurun_out/smoke.log ;;
     bench) timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; tail -n 3 gpurun_out/bench.log ;;
