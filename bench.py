@@ -305,6 +305,39 @@ def run_ours(args):
         del det
     except Exception as e:  # the headline numbers must not depend on this extra
         extra["single_frame_640x480_ms"] = {"error": str(e)[:200]}
+    # one FaceNet / HandNet crop through FaceDetector / HandDetector.__call__ (demo.py:33-55), and the
+    # CPU restatement of the same call (torch-CPU conv + SciPy) once, for scale
+    try:
+        kp = {}
+        for kind, modname, cls, netmod in (("face", "face_detector", "FaceDetector", "models.FaceNet"),
+                                           ("hand", "hand_detector", "HandDetector", "models.HandNet")):
+            nm = pkg(netmod)
+            net = getattr(nm, "FaceNet" if kind == "face" else "HandNet")()
+            wd = syn.he_weights(0, layers=nm.LAYERS)
+            net.load_npz(wd)
+            d = getattr(pkg(modname), cls)(model=net, device=local_rank, precision=args.precision)
+            crop = syn.procedural_image(200, 200, seed=21)
+            for _ in range(3):
+                d(crop)
+            ts = []
+            for _ in range(20):
+                t0 = time.perf_counter()
+                d(crop)
+                ts.append(time.perf_counter() - t0)
+            kp[kind + "_200x200_crop_ms"] = 1e3 * float(np.median(ts))
+            if not args.no_cpu_baseline and kind == "face":
+                from oracle import restate as R
+                import torch as _t
+                _t.set_num_threads(16)
+                weights = {n: (wd[n + "/W"], wd[n + "/b"]) for n, _, _, _ in nm.LAYERS}
+                R.detect_keypoints(weights, crop)
+                t0 = time.perf_counter()
+                R.detect_keypoints(weights, crop)
+                kp["face_200x200_crop_cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
+            del d
+        extra["keypoint_nets"] = kp
+    except Exception as e:
+        extra["keypoint_nets"] = {"error": str(e)[:200]}
     # CPU baseline: the oracle port on this box's host cores, bounded sample
     cpu = None
     if not args.no_cpu_baseline:
