@@ -101,10 +101,10 @@ struct PostWs {           // post-process workspace for (N, map_h, map_w)
   int* type_start = nullptr;  // [N][19]
   int* status = nullptr;      // [N]
   Candidate* cands = nullptr; // [N][19][max_cand]
+  Candidate* cands_alt = nullptr;  // ping-pong partner of cands for limb_assign's per-round compaction
   int* cand_counts = nullptr; // [N][19]
   Connection* conns = nullptr;  // [N][19][conn_cap]
   int* conn_counts = nullptr;
-  double* subsets = nullptr;  // [N][max_persons][20]
   double* subsets_out = nullptr;
   ImageHeader* headers = nullptr;
   PersonOut* persons = nullptr;
@@ -796,10 +796,10 @@ int get_post(opb_ctx* ctx, int n, int H, int W, PostWs** out) {
   RC(dev_alloc(ctx, &ws->type_start, static_cast<size_t>(n) * 19, ws->allocs));
   RC(dev_alloc(ctx, &ws->status, n, ws->allocs));
   RC(dev_alloc(ctx, &ws->cands, static_cast<size_t>(n) * 19 * p.max_candidates, ws->allocs, false));
+  RC(dev_alloc(ctx, &ws->cands_alt, static_cast<size_t>(n) * 19 * p.max_candidates, ws->allocs, false));
   RC(dev_alloc(ctx, &ws->cand_counts, static_cast<size_t>(n) * 19, ws->allocs));
   RC(dev_alloc(ctx, &ws->conns, static_cast<size_t>(n) * 19 * ctx->conn_cap, ws->allocs, false));
   RC(dev_alloc(ctx, &ws->conn_counts, static_cast<size_t>(n) * 19, ws->allocs));
-  RC(dev_alloc(ctx, &ws->subsets, static_cast<size_t>(n) * p.max_persons * 20, ws->allocs, false));
   RC(dev_alloc(ctx, &ws->subsets_out, static_cast<size_t>(n) * p.max_persons * 20, ws->allocs, false));
   RC(dev_alloc(ctx, &ws->headers, n, ws->allocs));
   RC(dev_alloc(ctx, &ws->persons, static_cast<size_t>(n) * p.max_persons, ws->allocs));
@@ -878,19 +878,24 @@ int launch_connections(opb_ctx* ctx, PostWs* ws, const float* pafs, int n, int H
   OPB_CUDA(ctx, cudaGetLastError());
   prof_mark(ctx, "paf_candidates");
   dim3 g2(19, n);
-  limb_assign_kernel<<<g2, 256, 0, ctx->stream>>>(ws->peaks, ws->idx_list, ws->type_start, p.max_peaks, 18, ctx->pc,
-                                                  ws->cands, ws->cand_counts, p.max_candidates, ws->conns,
-                                                  ws->conn_counts, ctx->conn_cap, ws->status);
+  limb_assign_kernel<<<g2, kAssignThreads, 0, ctx->stream>>>(ws->peaks, ws->idx_list, ws->type_start, p.max_peaks, 18,
+                                                             ctx->pc, ws->cands, ws->cands_alt, ws->cand_counts,
+                                                             p.max_candidates, ws->conns, ws->conn_counts, ctx->conn_cap,
+                                                             ws->status);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   return OPB_OK;
 }
 
 int launch_group(opb_ctx* ctx, PostWs* ws, int n, bool with_counts) {
-  group_persons_kernel<<<n, 32, 0, ctx->stream>>>(ws->peaks, with_counts ? ws->peak_counts : nullptr,
-                                                  ctx->prm.max_peaks, ctx->pc, ws->conns, ws->conn_counts,
-                                                  ctx->conn_cap, ws->subsets, ctx->prm.max_persons, ws->status,
-                                                  ws->headers, ws->persons, ws->subsets_out);
+  // peak ids fit int16 (max_peaks <= 16384); the subset table takes 52 B of shared memory per row
+  const size_t table_bytes = group_smem_bytes(ctx->prm.max_persons, ctx->prm.max_peaks);
+  if (table_bytes > 48 * 1024)
+    OPB_CUDA(ctx, cudaFuncSetAttribute(group_persons_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(table_bytes)));
+  group_persons_kernel<<<n, 32, table_bytes, ctx->stream>>>(
+      ws->peaks, with_counts ? ws->peak_counts : nullptr, ctx->prm.max_peaks, ctx->pc, ws->conns, ws->conn_counts,
+      ctx->conn_cap, ctx->prm.max_persons, ws->status, ws->headers, ws->persons, ws->subsets_out);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   return OPB_OK;
@@ -959,8 +964,8 @@ int opb_create(opb_ctx** out, int device, const opb_params* params) {
     return OPB_ERR_UNSUPPORTED;
   }
   if (params->n_integ_points != 10 || params->gauss_radius < 1 || params->gauss_radius > PK_R_MAX ||
-      params->max_peaks < 32 || params->max_peaks > 16384 || params->max_candidates < 32 || params->max_persons < 1) {
-    g_create_error = "unsupported opb_params (n_integ_points must be 10, gauss_radius 1..16, max_peaks 32..16384)";
+      params->max_peaks < 32 || params->max_peaks > 16384 || params->max_candidates < 32 || params->max_persons < 1 || params->max_persons > 4096) {
+    g_create_error = "unsupported opb_params (n_integ_points must be 10, gauss_radius 1..16, max_peaks 32..16384, max_persons 1..4096)";
     return OPB_ERR_ARG;
   }
   opb_ctx* ctx = new opb_ctx();
@@ -1814,9 +1819,10 @@ int opb_time_stage(opb_ctx* ctx, const char* stage, int reps, float* ms) {
       if (s == "limb_assign") {
         ++n_launch;
         dim3 g2(19, n);
-        limb_assign_kernel<<<g2, 256, 0, ctx->stream>>>(ws->peaks, ws->idx_list, ws->type_start, ctx->prm.max_peaks, 18,
-                                                        ctx->pc, ws->cands, ws->cand_counts, ctx->prm.max_candidates,
-                                                        ws->conns, ws->conn_counts, ctx->conn_cap, ws->status);
+        limb_assign_kernel<<<g2, kAssignThreads, 0, ctx->stream>>>(ws->peaks, ws->idx_list, ws->type_start,
+                                                                   ctx->prm.max_peaks, 18, ctx->pc, ws->cands, ws->cands_alt,
+                                                                   ws->cand_counts, ctx->prm.max_candidates, ws->conns,
+                                                                   ws->conn_counts, ctx->conn_cap, ws->status);
         return OPB_OK;
       }
       ++n_launch;

@@ -110,26 +110,31 @@ paf_candidates_kernel(const float* __restrict__ paf, int H, int W, const PeakD* 
 // One block per (limb, image).  Exact greedy matching by descending (score, then generation
 // order) without a global sort: a candidate that is the best alive one of BOTH its endpoints
 // is exactly what the sequential greedy loop would accept next for those endpoints; accept
-// all such candidates, kill the ones sharing an endpoint, repeat.  Accepted connections are
+// all such candidates, kill the ones sharing an endpoint, repeat.  Every round first compacts the
+// still-alive candidates into the other of two buffers (cands <-> cands_alt), so the work per
+// round is proportional to what is left, not to the original list.  Accepted connections are
 // finally ordered by (score desc, pair asc) = the reference's acceptance order.
-__global__ void __launch_bounds__(256)
+constexpr int kAssignThreads = 512;
+__global__ void __launch_bounds__(kAssignThreads)
 limb_assign_kernel(const PeakD* __restrict__ peaks, const int* __restrict__ idx_list,
                    const int* __restrict__ type_start, int peaks_cap, int n_types, PafConsts K,
-                   Candidate* __restrict__ cands, int* __restrict__ cand_counts, int cand_cap,
-                   Connection* __restrict__ conns, int* __restrict__ conn_counts, int conn_cap,
+                   Candidate* __restrict__ cands, Candidate* __restrict__ cands_alt, int* __restrict__ cand_counts,
+                   int cand_cap, Connection* __restrict__ conns, int* __restrict__ conn_counts, int conn_cap,
                    int* __restrict__ status) {
   __shared__ unsigned long long bestA_s[kAssignMaxType], bestB_s[kAssignMaxType];
   __shared__ unsigned int bestA_i[kAssignMaxType], bestB_i[kAssignMaxType];
   __shared__ unsigned char usedA[kAssignMaxType], usedB[kAssignMaxType];
-  __shared__ int s_alive, s_nacc;
-  __shared__ unsigned int acc_slot[kAssignMaxType];   // candidate index of each accepted connection
+  __shared__ int s_cnt, s_nacc;
+  __shared__ double acc_score[kAssignMaxType];        // accepted connections, by value
+  __shared__ unsigned int acc_pair[kAssignMaxType];
 
   const int l = blockIdx.x, img = blockIdx.y;
   const int ja = K.limbs[l][0], jb = K.limbs[l][1];
   const int* ts = type_start + img * (n_types + 1);
   const int a0 = ts[ja], nA = ts[ja + 1] - a0;
   const int b0 = ts[jb], nB = ts[jb + 1] - b0;
-  Candidate* cd = cands + (static_cast<size_t>(img) * 19 + l) * cand_cap;
+  Candidate* src = cands + (static_cast<size_t>(img) * 19 + l) * cand_cap;
+  Candidate* dst = cands_alt + (static_cast<size_t>(img) * 19 + l) * cand_cap;
   Connection* out = conns + (static_cast<size_t>(img) * 19 + l) * conn_cap;
   int m = cand_counts[img * 19 + l];
   if (threadIdx.x == 0) {
@@ -145,46 +150,58 @@ limb_assign_kernel(const PeakD* __restrict__ peaks, const int* __restrict__ idx_
   for (int i = threadIdx.x; i < nA; i += blockDim.x) usedA[i] = 0;
   for (int i = threadIdx.x; i < nB; i += blockDim.x) usedB[i] = 0;
   __syncthreads();
+  const int lane = threadIdx.x & 31;
 
-  for (int round = 0; round < 2 * kAssignMaxType + 2; ++round) {
+  for (int round = 0; round < 2 * kAssignMaxType + 2 && m > 0; ++round) {
     for (int i = threadIdx.x; i < nA; i += blockDim.x) { bestA_s[i] = 0ull; bestA_i[i] = 0xffffffffu; }
     for (int i = threadIdx.x; i < nB; i += blockDim.x) { bestB_s[i] = 0ull; bestB_i[i] = 0xffffffffu; }
-    if (threadIdx.x == 0) s_alive = 0;
+    if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    int alive_local = 0;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
-      if (cd[i].state != 0) continue;
-      const uint32_t pr = cd[i].pair;
-      const int a = pr / nB, b = pr - a * nB;
-      if (usedA[a] || usedB[b]) { cd[i].state = 1; continue; }
-      alive_local = 1;
-      const unsigned long long sb = static_cast<unsigned long long>(__double_as_longlong(cd[i].score));  // score > 0
-      atomicMax(&bestA_s[a], sb);
-      atomicMax(&bestB_s[b], sb);
+    // pass 1: drop candidates with a used endpoint, compact the rest, best score per endpoint
+    for (int base = 0; base < m; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      Candidate c;
+      bool alive = false;
+      int a = 0, b = 0;
+      if (i < m) {
+        c = src[i];
+        a = c.pair / nB; b = c.pair - a * nB;
+        alive = !(usedA[a] || usedB[b]);
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, alive);
+      int wbase = 0;
+      if (lane == 0 && mask) wbase = atomicAdd(&s_cnt, __popc(mask));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (alive) {
+        dst[wbase + __popc(mask & ((1u << lane) - 1))] = c;
+        const unsigned long long sb = static_cast<unsigned long long>(__double_as_longlong(c.score));  // score > 0
+        atomicMax(&bestA_s[a], sb);
+        atomicMax(&bestB_s[b], sb);
+      }
     }
-    if (alive_local) s_alive = 1;
     __syncthreads();
-    if (!s_alive) break;
+    m = s_cnt;
+    { Candidate* t = src; src = dst; dst = t; }
+    if (m == 0) break;
+    // pass 2: among equal best scores the earliest generated pair wins (stable sort order)
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
-      if (cd[i].state != 0) continue;
-      const uint32_t pr = cd[i].pair;
-      const int a = pr / nB, b = pr - a * nB;
-      const unsigned long long sb = static_cast<unsigned long long>(__double_as_longlong(cd[i].score));
-      if (sb == bestA_s[a]) atomicMin(&bestA_i[a], pr);
-      if (sb == bestB_s[b]) atomicMin(&bestB_i[b], pr);
+      const Candidate c = src[i];
+      const int a = c.pair / nB, b = c.pair - a * nB;
+      const unsigned long long sb = static_cast<unsigned long long>(__double_as_longlong(c.score));
+      if (sb == bestA_s[a]) atomicMin(&bestA_i[a], c.pair);
+      if (sb == bestB_s[b]) atomicMin(&bestB_i[b], c.pair);
     }
     __syncthreads();
+    // pass 3: mutual best -> accepted
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
-      if (cd[i].state != 0) continue;
-      const uint32_t pr = cd[i].pair;
-      const int a = pr / nB, b = pr - a * nB;
-      const unsigned long long sb = static_cast<unsigned long long>(__double_as_longlong(cd[i].score));
-      if (sb == bestA_s[a] && pr == bestA_i[a] && sb == bestB_s[b] && pr == bestB_i[b]) {
-        cd[i].state = 2;
+      const Candidate c = src[i];
+      const int a = c.pair / nB, b = c.pair - a * nB;
+      const unsigned long long sb = static_cast<unsigned long long>(__double_as_longlong(c.score));
+      if (sb == bestA_s[a] && c.pair == bestA_i[a] && sb == bestB_s[b] && c.pair == bestB_i[b]) {
         usedA[a] = 1;
         usedB[b] = 1;
         const int k = atomicAdd(&s_nacc, 1);
-        if (k < kAssignMaxType) acc_slot[k] = i;
+        if (k < kAssignMaxType) { acc_score[k] = c.score; acc_pair[k] = c.pair; }
       }
     }
     __syncthreads();
@@ -194,16 +211,17 @@ limb_assign_kernel(const PeakD* __restrict__ peaks, const int* __restrict__ idx_
   if (nacc > conn_cap && threadIdx.x == 0) atomicOr(&status[img], 8);
   // rank sort by (score desc, pair asc)
   for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
-    const Candidate ci = cd[acc_slot[i]];
+    const double si = acc_score[i];
+    const unsigned int pi = acc_pair[i];
     int rank = 0;
     for (int j = 0; j < nacc; ++j) {
-      const Candidate cj = cd[acc_slot[j]];
-      if (cj.score > ci.score || (cj.score == ci.score && cj.pair < ci.pair)) ++rank;
+      const double sj = acc_score[j];
+      if (sj > si || (sj == si && acc_pair[j] < pi)) ++rank;
     }
     if (rank < conn_cap) {
-      const int a = ci.pair / nB, b = ci.pair - a * nB;
+      const int a = pi / nB, b = pi - a * nB;
       Connection c;
-      c.score = ci.score;
+      c.score = si;
       c.id_a = idx_list[static_cast<size_t>(img) * peaks_cap + a0 + a];
       c.id_b = idx_list[static_cast<size_t>(img) * peaks_cap + b0 + b];
       out[rank] = c;
@@ -223,101 +241,157 @@ struct ImageHeader {  // == opb_image_header
   int n_peaks, n_persons, status, n_connections;
 };
 
-// One warp per image.  subsets: [n_img][max_persons][20] float64 workspace.
-// subsets_out (optional): final kept rows [n_img][max_persons][20].
+// One warp per image.  The subset table of grouping_key_points lives in shared memory for the whole kernel:
+//   ids  [18][max_persons] int16  peak id per joint (-1 empty, -2 = row removed by a merge), column-major
+//   tot  [max_persons]     f64    subset[-2] total score
+//   cnt  [max_persons]     f64    subset[-1] joint count (non-integer after a merge, :216-217)
+// (52 B per row; max_persons <= 4096 fits the 227 KB of one CTA), plus one bit per peak saying whether any row
+// holds it -- a connection between two peaks no row holds starts a new subset without scanning the table; the
+// scan itself reads four rows per lane and load.  Connections are fetched 32 at a time (one per
+// lane, with both endpoint peak scores) and broadcast with shuffles, so the sequential merge loop never waits on
+// global memory.  np.delete on a merge (:218) marks the row dead instead of shifting the rows below it; dead rows
+// are skipped by the final filter, which preserves the reference's row order, and are reclaimed by one compaction
+// if the table fills up.  subsets_out (optional): final kept rows [n_img][max_persons][20] float64.
+inline size_t group_smem_bytes(int max_persons, int peaks_cap) {
+  return static_cast<size_t>(16) * max_persons + static_cast<size_t>(36) * ((max_persons + 3) & ~3) + 4 * ((peaks_cap + 31) / 32) + 16;
+}
 __global__ void __launch_bounds__(32)
 group_persons_kernel(const PeakD* __restrict__ peaks, const int* __restrict__ peak_counts, int peaks_cap,
                      PafConsts K, const Connection* __restrict__ conns, const int* __restrict__ conn_counts,
-                     int conn_cap, double* __restrict__ subsets, int max_persons, const int* __restrict__ status_in,
+                     int conn_cap, int max_persons, const int* __restrict__ status_in,
                      ImageHeader* __restrict__ headers, PersonOut* __restrict__ persons,
                      double* __restrict__ subsets_out) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  double* tot = reinterpret_cast<double*>(s_raw);
+  double* cnt = tot + max_persons;
+  short* ids = reinterpret_cast<short*>(cnt + max_persons);      // ids[j * stride + k]
+  const int stride = (max_persons + 3) & ~3;                      // 8-byte aligned columns
+  unsigned* in_row = reinterpret_cast<unsigned*>(ids + 18 * stride);   // [peaks_cap / 32] peak held by some row
   const int img = blockIdx.x, lane = threadIdx.x;
+  for (int i = lane; i < (peaks_cap + 31) / 32; i += 32) in_row[i] = 0u;
+  __syncwarp();
   const PeakD* pk = peaks + static_cast<size_t>(img) * peaks_cap;
-  double* S = subsets + static_cast<size_t>(img) * max_persons * 20;
-  int P = 0;
+  int P = 0;               // rows in use (alive + dead)
+  int n_dead = 0;
   int err = 0;
   int n_conn_total = 0;
-  const int st_in = status_in[img];
-  if (st_in) err = -4;  // OPB_ERR_CAPACITY from an earlier stage
+  if (status_in[img]) err = -4;  // OPB_ERR_CAPACITY from an earlier stage
 
   for (int l = 0; l < 19 && !err; ++l) {
     const int ja = K.limbs[l][0], jb = K.limbs[l][1];
     const Connection* cl = conns + (static_cast<size_t>(img) * 19 + l) * conn_cap;
     const int nc = conn_counts[img * 19 + l];
     n_conn_total += nc;
-    for (int ci = 0; ci < nc && !err; ++ci) {
-      const Connection c = cl[ci];
-      const double da = static_cast<double>(c.id_a), db = static_cast<double>(c.id_b);
-      // find the subsets that already hold one endpoint (first two, in row order)
-      int found = 0, f0 = -1, f1 = -1;
-      for (int base = 0; base < P; base += 32) {
-        const int k = base + lane;
-        const bool hit = (k < P) && (S[k * 20 + ja] == da || S[k * 20 + jb] == db);
-        unsigned mask = __ballot_sync(0xffffffffu, hit);
-        while (mask) {
-          const int bit = __ffs(mask) - 1;
-          mask &= mask - 1;
-          if (found == 0) f0 = base + bit;
-          else if (found == 1) f1 = base + bit;
-          ++found;
-        }
+    short* col_a = ids + ja * stride;
+    short* col_b = ids + jb * stride;
+    for (int c0 = 0; c0 < nc && !err; c0 += 32) {
+      // lane i fetches connection c0 + i and the scores of its two peaks
+      Connection mine;
+      mine.score = 0.0; mine.id_a = 0; mine.id_b = 0;
+      double my_sa = 0.0, my_sb = 0.0;
+      if (c0 + lane < nc) {
+        mine = cl[c0 + lane];
+        my_sa = static_cast<double>(pk[mine.id_a].score);
+        my_sb = static_cast<double>(pk[mine.id_b].score);
       }
-      if (found >= 3) { err = -5; break; }   // reference: IndexError at pose_detector.py:197
-      if (found == 1) {
-        if (lane == 0) {
-          double* s = S + f0 * 20;
-          if (s[jb] != db) {
-            s[jb] = db;
-            s[19] = __dadd_rn(s[19], 1.0);
-            s[18] = __dadd_rn(s[18], __dadd_rn(static_cast<double>(pk[c.id_b].score), c.score));
+      const int chunk = min(32, nc - c0);
+      for (int t = 0; t < chunk && !err; ++t) {
+        const int id_a = __shfl_sync(0xffffffffu, mine.id_a, t), id_b = __shfl_sync(0xffffffffu, mine.id_b, t);
+        const double score = __shfl_sync(0xffffffffu, mine.score, t);
+        const double sa = __shfl_sync(0xffffffffu, my_sa, t), sb = __shfl_sync(0xffffffffu, my_sb, t);
+        const short ha = static_cast<short>(id_a), hb = static_cast<short>(id_b);
+        // find the subsets that already hold one endpoint (first two, in row order)
+        int found = 0, f0 = -1, f1 = -1;
+        const bool known = ((in_row[id_a >> 5] >> (id_a & 31)) | (in_row[id_b >> 5] >> (id_b & 31))) & 1u;
+        for (int base = 0; known && base < P; base += 128) {
+          const int k0 = base + lane * 4;
+          unsigned h = 0;
+          if (k0 < P) {
+            const uint2 va = *reinterpret_cast<const uint2*>(col_a + k0), vb = *reinterpret_cast<const uint2*>(col_b + k0);
+            const short a4[4] = {static_cast<short>(va.x & 0xffff), static_cast<short>(va.x >> 16),
+                                 static_cast<short>(va.y & 0xffff), static_cast<short>(va.y >> 16)};
+            const short b4[4] = {static_cast<short>(vb.x & 0xffff), static_cast<short>(vb.x >> 16),
+                                 static_cast<short>(vb.y & 0xffff), static_cast<short>(vb.y >> 16)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (k0 + e < P && (a4[e] == ha || b4[e] == hb)) h |= 1u << e;
           }
-        }
-      } else if (found == 2) {
-        double* s1 = S + f0 * 20;
-        double* s2 = S + f1 * 20;
-        const bool both = (lane < 18) && (s1[lane] >= 0.0) && (s2[lane] >= 0.0);
-        const bool overlap = __any_sync(0xffffffffu, both);
-        if (!overlap) {
-          if (lane < 18) s1[lane] = __dadd_rn(s1[lane], __dadd_rn(s2[lane], 1.0));
-          if (lane >= 18 && lane < 20) s1[lane] = __dadd_rn(__dadd_rn(s1[lane], s2[lane]), c.score);  // :216-217
-          __syncwarp();
-          for (int r = f1; r < P - 1; ++r) {            // np.delete(subsets, f1, axis=0)
-            double v = 0.0;
-            if (lane < 20) v = S[(r + 1) * 20 + lane];
-            __syncwarp();
-            if (lane < 20) S[r * 20 + lane] = v;
-            __syncwarp();
-          }
-          --P;
-        } else if (lane == 0) {
-          for (int w = 0; w < 2; ++w) {
-            double* s = w ? s2 : s1;
-            if (s[ja] == -1.0) {
-              s[ja] = da;
-              s[19] = __dadd_rn(s[19], 1.0);
-              s[18] = __dadd_rn(s[18], __dadd_rn(static_cast<double>(pk[c.id_a].score), c.score));
-            } else if (s[jb] == -1.0) {
-              s[jb] = db;
-              s[19] = __dadd_rn(s[19], 1.0);
-              s[18] = __dadd_rn(s[18], __dadd_rn(static_cast<double>(pk[c.id_b].score), c.score));
+          unsigned any = __ballot_sync(0xffffffffu, h != 0);
+          while (any) {                                    // lanes ascending, bits ascending = row order
+            const int src = __ffs(any) - 1;
+            any &= any - 1;
+            unsigned hl = __shfl_sync(0xffffffffu, h, src);
+            while (hl) {
+              const int e = __ffs(hl) - 1;
+              hl &= hl - 1;
+              if (found == 0) f0 = base + src * 4 + e;
+              else if (found == 1) f1 = base + src * 4 + e;
+              ++found;
             }
           }
         }
-      } else if (found == 0 && l != 9 && l != 13) {
-        if (P >= max_persons) { err = -4; break; }
-        if (lane < 20) {
-          double v = -1.0;
-          if (lane == ja) v = da;
-          if (lane == jb) v = db;
-          if (lane == 19) v = 2.0;
-          if (lane == 18)
-            v = __dadd_rn(__dadd_rn(static_cast<double>(pk[c.id_a].score), static_cast<double>(pk[c.id_b].score)),
-                          c.score);
-          S[P * 20 + lane] = v;
+        if (found >= 3) { err = -5; break; }   // reference: IndexError at pose_detector.py:197
+        if (found == 1) {
+          if (lane == 0 && col_b[f0] != hb) {            // a match through joint_b changes nothing (:200-206)
+            col_b[f0] = hb;
+            in_row[id_b >> 5] |= 1u << (id_b & 31);
+            cnt[f0] = __dadd_rn(cnt[f0], 1.0);
+            tot[f0] = __dadd_rn(tot[f0], __dadd_rn(sb, score));
+          }
+        } else if (found == 2) {
+          const int v1 = (lane < 18) ? ids[lane * stride + f0] : -1;
+          const int v2 = (lane < 18) ? ids[lane * stride + f1] : -1;
+          const bool overlap = __any_sync(0xffffffffu, v1 >= 0 && v2 >= 0);
+          if (!overlap) {
+            if (lane < 18) {
+              ids[lane * stride + f0] = static_cast<short>(v1 + v2 + 1);    // subset1[:-2] += subset2[:-2] + 1
+              ids[lane * stride + f1] = -2;                                  // np.delete(subsets, f1, axis=0)
+            }
+            if (lane == 18) tot[f0] = __dadd_rn(__dadd_rn(tot[f0], tot[f1]), score);   // [-2:] += ... ; += score (:216-217)
+            if (lane == 19) cnt[f0] = __dadd_rn(__dadd_rn(cnt[f0], cnt[f1]), score);
+            ++n_dead;
+          } else if (lane == 0) {
+            for (int w = 0; w < 2; ++w) {
+              const int row = w ? f1 : f0;
+              if (col_a[row] == -1) {
+                col_a[row] = ha;
+                in_row[id_a >> 5] |= 1u << (id_a & 31);
+                cnt[row] = __dadd_rn(cnt[row], 1.0);
+                tot[row] = __dadd_rn(tot[row], __dadd_rn(sa, score));
+              } else if (col_b[row] == -1) {
+                col_b[row] = hb;
+                in_row[id_b >> 5] |= 1u << (id_b & 31);
+                cnt[row] = __dadd_rn(cnt[row], 1.0);
+                tot[row] = __dadd_rn(tot[row], __dadd_rn(sb, score));
+              }
+            }
+          }
+        } else if (found == 0 && l != 9 && l != 13) {
+          if (P >= max_persons && n_dead > 0) {            // reclaim removed rows before giving up
+            __syncwarp();
+            int w = 0;
+            for (int r = 0; r < P; ++r) {
+              if (ids[r] == -2) continue;
+              if (w != r) {
+                if (lane < 18) ids[lane * stride + w] = ids[lane * stride + r];
+                if (lane == 18) tot[w] = tot[r];
+                if (lane == 19) cnt[w] = cnt[r];
+                __syncwarp();
+              }
+              ++w;
+            }
+            P = w;
+            n_dead = 0;
+          }
+          if (P >= max_persons) { err = -4; break; }
+          if (lane < 18) ids[lane * stride + P] = (lane == ja) ? ha : (lane == jb) ? hb : static_cast<short>(-1);
+          if (lane == 18) tot[P] = __dadd_rn(__dadd_rn(sa, sb), score);
+          if (lane == 19) cnt[P] = 2.0;
+          if (lane == 0) { in_row[id_a >> 5] |= 1u << (id_a & 31); in_row[id_b >> 5] |= 1u << (id_b & 31); }
+          ++P;
         }
-        ++P;
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   __syncwarp();
@@ -325,21 +399,23 @@ group_persons_kernel(const PeakD* __restrict__ peaks, const int* __restrict__ pe
   int kept = 0;
   if (!err) {
     for (int k = 0; k < P; ++k) {
-      const double cnt = S[k * 20 + 19], sc = S[k * 20 + 18];
-      const bool keep = (cnt >= K.n_subset_limbs_thresh) && (__ddiv_rn(sc, cnt) >= K.subset_score_thresh);
+      if (ids[k] == -2) continue;                        // row removed by a merge
+      const double c = cnt[k], sc = tot[k];
+      const bool keep = (c >= K.n_subset_limbs_thresh) && (__ddiv_rn(sc, c) >= K.subset_score_thresh);
       if (keep) {
+        const int id = (lane < 18) ? ids[lane * stride + k] : -1;
         if (subsets_out && lane < 20)
-          subsets_out[(static_cast<size_t>(img) * max_persons + kept) * 20 + lane] = S[k * 20 + lane];
+          subsets_out[(static_cast<size_t>(img) * max_persons + kept) * 20 + lane] =
+              lane < 18 ? static_cast<double>(id) : (lane == 18 ? sc : c);
         if (persons) {
           PersonOut* po = persons + static_cast<size_t>(img) * max_persons + kept;
           if (lane < 18) {
-            const int id = static_cast<int>(S[k * 20 + lane]);
             po->peak_id[lane] = id;
             po->x[lane] = (id >= 0) ? static_cast<int>(pk[id].x) : 0;
             po->y[lane] = (id >= 0) ? static_cast<int>(pk[id].y) : 0;
           }
           if (lane == 18) po->score = sc;
-          if (lane == 19) po->count = cnt;
+          if (lane == 19) po->count = c;
         }
         ++kept;
       }

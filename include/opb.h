@@ -65,7 +65,7 @@ typedef struct opb_params {
   double gauss_taps[OPB_MAX_TAPS];    /* 2*gauss_radius+1 normalised float64 taps              */
   int32_t max_peaks;                  /* per image   (default 8192)                            */
   int32_t max_candidates;             /* per (image, limb) accepted PAF candidates (def 32768) */
-  int32_t max_persons;                /* per image subsets alive at any time (default 1024)    */
+  int32_t max_persons;                /* per image subsets alive at any time (default 1024, <= 4096) */
   int32_t reserved1;
 } opb_params;
 
