@@ -325,7 +325,7 @@ def run_ours(args):
                 d(crop)
                 ts.append(time.perf_counter() - t0)
             kp[kind + "_200x200_crop_ms"] = 1e3 * float(np.median(ts))
-            if not args.no_cpu_baseline and kind == "face":
+            if not args.no_cpu_baseline and kind == "face" and world == 1:
                 from oracle import restate as R
                 import torch as _t
                 _t.set_num_threads(16)
@@ -340,7 +340,7 @@ def run_ours(args):
         extra["keypoint_nets"] = {"error": str(e)[:200]}
     # CPU baseline: the oracle port on this box's host cores, bounded sample
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:            # rank 0 at N = 1 only
         wd = syn.he_weights(0)
         weights = {k[:-2]: (wd[k], wd[k[:-2] + "/b"]) for k in wd if k.endswith("/W")}
         fr = imgs_host[0].numpy()
