@@ -67,6 +67,8 @@ _SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "opb_keypoints_from_heatmaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_double, C.c_void_p, C.c_void_p]),
+    "opb_precise_add_scale_unpadded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                 C.c_int, C.c_int]),
     "opb_get_image_detail": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p,
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "opb_precise_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -383,6 +385,14 @@ class Engine(object):
     # -- precise path -----------------------------------------------------------------------
     def precise_begin(self, orig_h, orig_w):
         self._check(self.lib.opb_precise_begin(self.ctx, orig_h, orig_w))
+
+    def precise_add_scale_unpadded(self, img, stride, pad_value, scale_index, n_scales):
+        """Resized but unpadded uint8 frame; pad_image (pose_detector.py:46-55) runs on the device."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, _ = img.shape
+        pv = (C.c_uint8 * 3)(*[int(v) for v in pad_value])
+        self._check(self.lib.opb_precise_add_scale_unpadded(self.ctx, _ptr(img), OPB_HOST, h, w, int(stride), pv,
+                                                            scale_index, n_scales))
 
     def precise_add_scale(self, padded_img, pad, scale_index, n_scales):
         img = np.ascontiguousarray(padded_img, np.uint8)

@@ -155,7 +155,7 @@ conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict_
   __shared__ __align__(1024) uint8_t sA[128 * 128];
   __shared__ __align__(1024) uint8_t sB[64 * 128];
   __shared__ __half s_lut[260];
-  __shared__ uint16_t s_idx[18 * 10 * 3];
+  __shared__ __align__(4) __half s_val[18 * 10 * 3 + 4];   // normalised halo tile, [row][col][c]
   __shared__ float s_bias[64];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
@@ -194,26 +194,42 @@ conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict_
     const int n = tile / (tiles_y * tiles_x);
     const int rem = tile - n * (tiles_y * tiles_x);
     const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
-    // (1) halo tile of byte indices (256 = zero padding)
+    // (1) halo tile, already normalised to fp16 through the look-up table (entry 256 = zero padding)
     for (int i = tid; i < 18 * 10 * 3; i += 128) {
       const int c = i % 3, q = i / 3;
       const int xx = x0 - 1 + q % 10, yy = y0 - 1 + q / 10;
-      uint16_t v = 256;
+      int v = 256;
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x_u8[((static_cast<size_t>(n) * H + yy) * W + xx) * 3 + c];
-      s_idx[i] = v;
+      s_val[i] = s_lut[v];
     }
     __syncthreads();
-    // (2) this thread's im2col row: k = (r*3+s)*3 + c  ->  27 consecutive idx of each halo row segment
+    // (2) this thread's im2col row: k = (r*3+s)*3 + c = 9 consecutive halfs of each of 3 halo rows.  Each row segment
+    //     is fetched as six aligned 32-bit words and funnel-shifted by its parity; the 27 halfs are then packed with
+    //     compile-time byte permutes (row r starts at the odd position 9r).
     {
-      uint32_t pk[16];                  // 32 halfs packed in registers (27 taps + 5 zeros)
+      uint32_t seg[3][5];               // seg[r][j] = halfs (2j, 2j+1) of row r's 9-half segment (half 9 is junk)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int k0 = 2 * i, k1 = 2 * i + 1;
-        const __half lo = (k0 < 27) ? s_lut[s_idx[((hl + k0 / 9) * 10 + wl) * 3 + k0 % 9]] : __float2half(0.f);
-        const __half hi = (k1 < 27) ? s_lut[s_idx[((hl + k1 / 9) * 10 + wl) * 3 + k1 % 9]] : __float2half(0.f);
-        const __half2 t = __halves2half2(lo, hi);
-        pk[i] = *reinterpret_cast<const uint32_t*>(&t);
+      for (int r = 0; r < 3; ++r) {
+        const int o = ((hl + r) * 10 + wl) * 3;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_val) + (o >> 1);
+        const uint32_t sh = (o & 1) * 16;
+        uint32_t w[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) w[j] = wp[j];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) seg[r][j] = __funnelshift_r(w[j], w[j + 1], sh);
       }
+      const uint32_t LO_LO = 0x5410, HI_LO = 0x5432;   // __byte_perm selectors: (a.lo, b.lo), (a.hi, b.lo)
+      uint32_t pk[16];
+      pk[0] = seg[0][0]; pk[1] = seg[0][1]; pk[2] = seg[0][2]; pk[3] = seg[0][3];
+      pk[4] = __byte_perm(seg[0][4], seg[1][0], LO_LO);            // (a8, b0)
+      pk[5] = __byte_perm(seg[1][0], seg[1][1], HI_LO);            // (b1, b2)
+      pk[6] = __byte_perm(seg[1][1], seg[1][2], HI_LO);
+      pk[7] = __byte_perm(seg[1][2], seg[1][3], HI_LO);
+      pk[8] = __byte_perm(seg[1][3], seg[1][4], HI_LO);            // (b7, b8)
+      pk[9] = seg[2][0]; pk[10] = seg[2][1]; pk[11] = seg[2][2]; pk[12] = seg[2][3];
+      pk[13] = seg[2][4] & 0xffffu;                                 // (c8, 0)
+      pk[14] = 0u; pk[15] = 0u;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) * 16)) =
@@ -254,7 +270,7 @@ conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict_
       }
     }
     ptx::tc_fence_before();
-    __syncthreads();                   // s_idx / sA / TMEM are free for the next tile
+    __syncthreads();                   // s_val / sA / TMEM are free for the next tile
   }
   if (warp == 0) ptx::tmem_dealloc<64>(tmem);
 }

@@ -49,4 +49,20 @@ resize_linear_u8_kernel(const uint8_t* __restrict__ src, int h0, int w0, uint8_t
   }
 }
 
+// pad_image (pose_detector.py:46-55): copy src [h][w][3] into the top-left corner of dst [ph][pw][3] and fill the
+// bottom / right margin with the per-channel pad value (104, 117, 123 in detect_precise, :445).
+__global__ void __launch_bounds__(256)
+pad_image_u8_kernel(const uint8_t* __restrict__ src, int h, int w, uint8_t* __restrict__ dst, int ph, int pw, int v0,
+                    int v1, int v2) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= pw || y >= ph) return;
+  uint8_t* o = dst + (static_cast<size_t>(y) * pw + x) * 3;
+  if (x < w && y < h) {
+    const uint8_t* i = src + (static_cast<size_t>(y) * w + x) * 3;
+    o[0] = i[0]; o[1] = i[1]; o[2] = i[2];
+  } else {
+    o[0] = static_cast<uint8_t>(v0); o[1] = static_cast<uint8_t>(v1); o[2] = static_cast<uint8_t>(v2);
+  }
+}
+
 }  // namespace opb

@@ -151,6 +151,8 @@ struct opb_ctx {
   std::map<long long, PostWs*> posts;
   PostWs* last_post = nullptr;
   uint8_t* ingest_buf = nullptr;   // staging for the original frame(s) of opb_detect_image
+  float* precise_mid = nullptr;    // x8 cubic intermediate of the precise path
+  size_t precise_mid_cap = 0;
   size_t ingest_bytes = 0;
   // streaming mode (opb_stream_submit / opb_stream_collect): two slots, pinned staging, a copy stream
   struct StreamSlot {
@@ -1012,6 +1014,7 @@ void opb_destroy(opb_ctx* ctx) {
   for (auto& kv : ctx->posts) { free_all(kv.second->allocs); delete kv.second; }
   free_all(ctx->weight_allocs);
   if (ctx->ingest_buf) cudaFree(ctx->ingest_buf);
+  if (ctx->precise_mid) cudaFree(ctx->precise_mid);
   if (ctx->kp_ws) {
     cudaFree(ctx->kp_ws->up); cudaFree(ctx->kp_ws->tmp); cudaFree(ctx->kp_ws->res); cudaFreeHost(ctx->kp_ws->h_res);
     delete ctx->kp_ws;
@@ -1496,23 +1499,23 @@ int opb_precise_begin(opb_ctx* ctx, int orig_h, int orig_w) {
   return get_post(ctx, 1, orig_h, orig_w, &ws);
 }
 
-int opb_precise_add_scale(opb_ctx* ctx, const uint8_t* img, int img_loc, int ph, int pw, int pad_h, int pad_w,
-                          int scale_index, int n_scales) {
-  if (!ctx || !img) return OPB_ERR_ARG;
-  PostWs* ws = ctx->last_post;
-  if (!ws || ws->N != 1) OPB_FAIL(ctx, OPB_ERR_STATE, "opb_precise_begin was not called");
-  cudaSetDevice(ctx->device);
-  Chain* ch = nullptr;
-  int rc = get_chain(ctx, 1, ph, pw, &ch);
-  if (rc) return rc;
+static int ensure_ingest(opb_ctx* ctx, size_t bytes);
+
+// forward + both cubic resizes + accumulate for the padded frame already in ch->img_u8 (:447-467)
+static int precise_accumulate(opb_ctx* ctx, PostWs* ws, Chain* ch, int ph, int pw, int pad_h, int pad_w, int scale_index,
+                              int n_scales) {
+  int rc;
   ch->img_u8_src = nullptr;
-  if ((rc = copy_in(ctx, ch->img_u8, img, static_cast<size_t>(ph) * pw * 3, img_loc))) return rc;
   if ((rc = run_chain(ctx, ch, true))) return rc;
   const int h8 = ph / 8, w8 = pw / 8;
   const int ch_h = ph - pad_h, ch_w = pw - pad_w;   // crop after the x8 resize (:462,:466)
-  std::vector<void*> tmp;
-  float* mid = nullptr;
-  if ((rc = dev_alloc(ctx, &mid, static_cast<size_t>(38) * ch_h * ch_w, tmp, false))) { free_all(tmp); return rc; }
+  const size_t need = static_cast<size_t>(38) * ch_h * ch_w;
+  if (ctx->precise_mid_cap < need) {                 // x8 intermediate, kept across scales and calls
+    if (ctx->precise_mid) { OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->precise_mid); ctx->precise_mid = nullptr; }
+    OPB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->precise_mid), need * sizeof(float)));
+    ctx->precise_mid_cap = need;
+  }
+  float* mid = ctx->precise_mid;
   const float scale = (scale_index == n_scales - 1) ? 1.0f / static_cast<float>(n_scales) : 1.0f;
   for (int which = 0; which < 2; ++which) {
     const int C = which ? 19 : 38;
@@ -1526,11 +1529,47 @@ int opb_precise_add_scale(opb_ctx* ctx, const uint8_t* img, int img_loc, int ph,
                                                        scale_index > 0 ? 1 : 0, scale);
     ctx->launches += 2;
   }
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  free_all(tmp);
-  if (e != cudaSuccess) OPB_FAIL(ctx, OPB_ERR_CUDA, std::string("precise add_scale: ") + cudaGetErrorString(e));
+  OPB_CUDA(ctx, cudaGetLastError());
   return OPB_OK;
+}
+
+int opb_precise_add_scale(opb_ctx* ctx, const uint8_t* img, int img_loc, int ph, int pw, int pad_h, int pad_w,
+                          int scale_index, int n_scales) {
+  if (!ctx || !img) return OPB_ERR_ARG;
+  PostWs* ws = ctx->last_post;
+  if (!ws || ws->N != 1) OPB_FAIL(ctx, OPB_ERR_STATE, "opb_precise_begin was not called");
+  cudaSetDevice(ctx->device);
+  Chain* ch = nullptr;
+  int rc = get_chain(ctx, 1, ph, pw, &ch);
+  if (rc) return rc;
+  if ((rc = copy_in(ctx, ch->img_u8, img, static_cast<size_t>(ph) * pw * 3, img_loc))) return rc;
+  return precise_accumulate(ctx, ws, ch, ph, pw, pad_h, pad_w, scale_index, n_scales);
+}
+
+int opb_precise_add_scale_unpadded(opb_ctx* ctx, const uint8_t* img, int img_loc, int h, int w, int stride,
+                                   const uint8_t pad_value[3], int scale_index, int n_scales) {
+  if (!ctx || !img || !pad_value || h <= 0 || w <= 0 || stride <= 0) return OPB_ERR_ARG;
+  PostWs* ws = ctx->last_post;
+  if (!ws || ws->N != 1) OPB_FAIL(ctx, OPB_ERR_STATE, "opb_precise_begin was not called");
+  cudaSetDevice(ctx->device);
+  const int pad_h = (stride - h % stride) % stride, pad_w = (stride - w % stride) % stride;     // :50-51
+  const int ph = h + pad_h, pw = w + pad_w;
+  Chain* ch = nullptr;
+  int rc = get_chain(ctx, 1, ph, pw, &ch);
+  if (rc) return rc;
+  const size_t in_b = static_cast<size_t>(h) * w * 3;
+  const uint8_t* d_src = img;
+  if (img_loc == OPB_HOST) {
+    if ((rc = ensure_ingest(ctx, in_b + 512))) return rc;
+    if ((rc = copy_in(ctx, ctx->ingest_buf, img, in_b, OPB_HOST))) return rc;
+    d_src = ctx->ingest_buf;
+  }
+  dim3 block(32, 8), grid((pw + 31) / 32, (ph + 7) / 8);
+  pad_image_u8_kernel<<<grid, block, 0, ctx->stream>>>(d_src, h, w, ch->img_u8, ph, pw, pad_value[0], pad_value[1],
+                                                       pad_value[2]);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  return precise_accumulate(ctx, ws, ch, ph, pw, pad_h, pad_w, scale_index, n_scales);
 }
 
 int opb_precise_finish(opb_ctx* ctx, double img_len, opb_image_header* header_out, opb_person* persons_out,

@@ -227,17 +227,18 @@ class PoseDetector(object):
         return poses, scores
 
     def detect_precise(self, orig_img):
-        """Multi-scale path (pose_detector.py:433-482): per scale the uint8 image is resized
-        (INTER_CUBIC) and padded on the host as in the reference; forward, both cubic map
-        resizes, averaging and the whole post-process run on the device."""
+        """Multi-scale path (pose_detector.py:433-482): per scale the uint8 image is resized on the host with
+        cv2 INTER_CUBIC exactly as the reference does (OpenCV dispatches 8-bit cubic to IPP, whose arithmetic cannot be
+        restated bit-exactly); padding, forward, both cubic map resizes, averaging and the whole
+        post-process run on the device."""
         oh, ow = orig_img.shape[:2]
         scales = params['inference_scales']
         self.engine.precise_begin(oh, ow)
         for k, scale in enumerate(scales):
             m = scale * params['inference_img_size'] / min(orig_img.shape[:2])
             img = cv2.resize(orig_img, (math.ceil(ow * m), math.ceil(oh * m)), interpolation=cv2.INTER_CUBIC)
-            padded, pad = self.pad_image(img, params['downscale'], (104, 117, 123))
-            self.engine.precise_add_scale(padded, pad, k, len(scales))
+            # pad_image(img, 8, (104, 117, 123)) of :445 runs on the device (csrc/ingest.cuh)
+            self.engine.precise_add_scale_unpadded(img, params['downscale'], (104, 117, 123), k, len(scales))
         header, persons = self.engine.precise_finish(ow)
         self.pafs, self.heatmaps = self.engine.download_maps(oh, ow)
         self.engine.raise_for_status(int(header[0]["status"]))

@@ -220,6 +220,10 @@ int opb_get_image_detail(opb_ctx* ctx, int img, double* peaks_out, int peaks_cap
 int opb_precise_begin(opb_ctx* ctx, int orig_h, int orig_w);
 int opb_precise_add_scale(opb_ctx* ctx, const uint8_t* img, int img_loc, int ph, int pw, int pad_h,
                           int pad_w, int scale_index, int n_scales);
+/* same, with pad_image (pose_detector.py:46-55) on the device: img is the resized, UNPADDED frame [h,w,3];
+ * the bottom / right margin up to the next multiple of `stride` is filled with pad_value (B,G,R).  */
+int opb_precise_add_scale_unpadded(opb_ctx* ctx, const uint8_t* img, int img_loc, int h, int w, int stride,
+                                   const uint8_t pad_value[3], int scale_index, int n_scales);
 int opb_precise_finish(opb_ctx* ctx, double img_len, opb_image_header* header_out,
                        opb_person* persons_out, int out_loc);
 /* copies the full-resolution maps of image 0 of the current post-process workspace

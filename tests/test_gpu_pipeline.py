@@ -65,6 +65,25 @@ def test_forward_maps_parity_mode(det_parity):
     assert np.abs(paf_u8 - paf).max() <= 1e-5 and np.abs(heat_u8 - heat).max() <= 1e-5
 
 
+def test_fast_mode_uint8_entry_matches_float_entry(weights_model):
+    """conv1_1 on tensor cores (uint8 frames, im2col built per thread) vs the CUDA-core conv1_1 fed the preprocessed
+    float32 image: same network, so the maps may differ only by fp16 rounding of the first layer's operands (which the
+    other 91 layers amplify to ~1e-2 on a white-noise frame whose maps are O(10); a misplaced tap would give O(1)).
+    The bound is relative to the map magnitude."""
+    det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="fast")
+    imgs = pkg("synthetic").random_images(2, 368, 496, seed=4)
+    imgs[1, :, :, :] = pkg("synthetic").procedural_image(368, 496, seed=9)
+    paf_u8, heat_u8 = det.engine.forward(imgs)
+    x = np.concatenate([det.preprocess(im) for im in imgs])
+    paf_f, heat_f = det.engine.forward(x)
+    for i in range(2):
+        e = max(float(np.abs(paf_u8[i] - paf_f[i]).max()), float(np.abs(heat_u8[i] - heat_f[i]).max()))
+        mag = max(float(np.abs(paf_f[i]).max()), float(np.abs(heat_f[i]).max()))
+        print("fast mode, uint8 (tensor-core conv1_1) vs float32 entry, image %d: max abs diff %.3e (maps up to %.2f)"
+              % (i, e, mag))
+        assert e < 4e-3 * max(mag, 1.0)
+
+
 def test_forward_maps_fast_mode(weights_model):
     det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="fast")
     g = load_golden("fast_584_he0.npz")
