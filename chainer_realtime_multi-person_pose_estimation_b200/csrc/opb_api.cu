@@ -508,6 +508,26 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
       op.mt = 1;
     }
   }
+  {  // Small batches (one camera frame): the throughput-optimal shapes above leave most SMs idle (a 46x62 map is 12
+     // 16x16 tiles).  When the launch would fill less than half a wave, trade per-instruction efficiency for
+     // parallelism: plain kernel, one 16x8 sub-tile per CTA, and halve the channel block (down to 64) while the
+     // launch still fits one wave.  OPB_SMALL_BATCH=0 disables.
+    const char* e = getenv("OPB_SMALL_BATCH");
+    auto tiles_of = [&](bool swap, bool pair, int mt, int bn) {
+      const int tw = (pair ? 16 : 8) * mt;
+      int tx = (a0.W + tw - 1) / tw;
+      if (swap) tx = a0.W / 16 + ((a0.W % 16) ? 1 : 0);
+      return s.n_problems * (per_problem_cout_pad / bn) * a0.N * ((a0.H + 15) / 16) * tx / (pair ? 1 : 1);
+    };
+    const bool enabled = !(e && atoi(e) == 0);
+    if (enabled && op.bn >= 64 && op.bn != 48 && tiles_of(op.swap, op.pair, op.mt, op.bn) * 2 <= ctx->num_sms) {
+      op.swap = false;
+      op.pair = false;
+      op.mt = 1;
+      if (op.bn > 128 && per_problem_cout_pad % 128 == 0 && tiles_of(false, false, 1, op.bn) * 2 <= ctx->num_sms) op.bn = 128;
+      if (op.bn == 128 && !s.pool && tiles_of(false, false, 1, 128) * 2 <= ctx->num_sms) op.bn = 64;
+    }
+  }
   std::memset(&op.P, 0, sizeof(op.P));
   ConvParams& P = op.P;
   P.N = a0.N; P.H = a0.H; P.W = a0.W;
