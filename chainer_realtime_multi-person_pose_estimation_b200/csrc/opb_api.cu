@@ -161,8 +161,24 @@ struct opb_ctx {
     uint8_t* h_result = nullptr; size_t r_bytes = 0;     // pinned [headers | persons] of the slot
     cudaEvent_t h2d_done = nullptr, done = nullptr;
     int n = 0; bool busy = false;
+    // CUDA-graph replay of the slot's pipeline: the launch sequence of one (shape, buffers) combination is captured
+    // the second time it is submitted and replayed afterwards
+    struct Key {
+      int n, oh, ow, ih, iw, mh, mw; double img_len; const void *ip, *ih_, *frames, *result, *chain, *post;
+      uint64_t epoch;
+      bool operator==(const Key& o) const {
+        return n == o.n && oh == o.oh && ow == o.ow && ih == o.ih && iw == o.iw && mh == o.mh && mw == o.mw &&
+               img_len == o.img_len && ip == o.ip && ih_ == o.ih_ && frames == o.frames && result == o.result &&
+               chain == o.chain && post == o.post && epoch == o.epoch;
+      }
+    } key{};
+    int key_seen = 0;               // consecutive submits with `key`
+    cudaGraphExec_t gexec = nullptr;
+    int64_t graph_launches = 0;
   } slots[2];
   cudaStream_t copy_stream = nullptr;
+  uint64_t cache_epoch = 0;        // bumped whenever cached chains / workspaces / weights are freed (invalidates graphs)
+  int use_graphs = 1;              // OPB_GRAPH=0: streaming mode launches kernel by kernel
   int conn_cap = kAssignMaxType;
   bool profile = false;                       // OPB_PROFILE=1: cudaEvent after every launch of a batch
   std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -771,6 +787,7 @@ int get_chain(opb_ctx* ctx, int n, int h, int w, Chain** out) {
   if (ctx->chains.size() >= 6) {
     for (auto& kv : ctx->chains) { cudaStreamSynchronize(ctx->stream); free_all(kv.second->allocs); delete kv.second; }
     ctx->chains.clear();
+    ctx->cache_epoch++;
     ctx->last_chain = nullptr;
   }
   Chain* ch = new Chain();
@@ -801,6 +818,7 @@ int get_post(opb_ctx* ctx, int n, int H, int W, PostWs** out) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->posts) { free_all(kv.second->allocs); delete kv.second; }
     ctx->posts.clear();
+    ctx->cache_epoch++;
     ctx->last_post = nullptr;
   }
   PostWs* ws = new PostWs();
@@ -1022,6 +1040,7 @@ int opb_create(opb_ctx** out, int device, const opb_params* params) {
   for (int i = 0; i < 2 * params->gauss_radius + 1; ++i) ctx->taps.w[i] = params->gauss_taps[i];
   ctx->conn_cap = kAssignMaxType;
   ctx->profile = getenv("OPB_PROFILE") && atoi(getenv("OPB_PROFILE")) > 0;
+  if (const char* g = getenv("OPB_GRAPH")) ctx->use_graphs = atoi(g);
   *out = ctx;
   return OPB_OK;
 }
@@ -1043,6 +1062,7 @@ void opb_destroy(opb_ctx* ctx) {
     if (sl.d_frames) cudaFree(sl.d_frames);
     if (sl.h_frames) cudaFreeHost(sl.h_frames);
     if (sl.h_result) cudaFreeHost(sl.h_result);
+    if (sl.gexec) cudaGraphExecDestroy(sl.gexec);
     if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
     if (sl.done) cudaEventDestroy(sl.done);
   }
@@ -1089,6 +1109,7 @@ int opb_finalize_weights(opb_ctx* ctx, int precision_mode) {
   OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (auto& kv : ctx->chains) { free_all(kv.second->allocs); delete kv.second; }
   ctx->chains.clear();
+  ctx->cache_epoch++;
   ctx->last_chain = nullptr;
   free_all(ctx->weight_allocs);
   ctx->packed.clear();
@@ -1728,16 +1749,49 @@ int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, in
   OPB_CUDA(ctx, cudaMemcpyAsync(sl.d_frames, h_src, in_b, cudaMemcpyHostToDevice, ctx->copy_stream));
   OPB_CUDA(ctx, cudaEventRecord(sl.h2d_done, ctx->copy_stream));
   OPB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
-  if (orig_h == in_h && orig_w == in_w) {
-    ch->img_u8_src = sl.d_frames;
-  } else {
-    if ((rc = launch_resize_u8(ctx, sl.d_frames, n, orig_h, orig_w, ch->img_u8, in_h, in_w))) return rc;
-    ch->img_u8_src = nullptr;
+  // everything between the upload and the `done` event: [resize] + pipeline + record download
+  auto body = [&]() -> int {
+    int r;
+    if (orig_h == in_h && orig_w == in_w) {
+      ch->img_u8_src = sl.d_frames;
+    } else {
+      if ((r = launch_resize_u8(ctx, sl.d_frames, n, orig_h, orig_w, ch->img_u8, in_h, in_w))) return r;
+      ch->img_u8_src = nullptr;
+    }
+    if ((r = run_pipeline(ctx, ch, ws, n, in_h, in_w, map_h, map_w, img_len, inject_paf, inject_heat))) return r;
+    if ((r = copy_out(ctx, sl.h_result, ws->headers, sizeof(ImageHeader) * n, OPB_HOST))) return r;
+    return copy_out(ctx, sl.h_result + sizeof(ImageHeader) * n, ws->persons,
+                    sizeof(PersonOut) * n * static_cast<size_t>(ctx->prm.max_persons), OPB_HOST);
+  };
+  const opb_ctx::StreamSlot::Key key{n, orig_h, orig_w, in_h, in_w, map_h, map_w, img_len, inject_paf, inject_heat,
+                                     sl.d_frames, sl.h_result, ch, ws, ctx->cache_epoch};
+  const bool graphs = ctx->use_graphs && !ctx->profile;
+  if (!(key == sl.key)) {
+    if (sl.gexec) { cudaGraphExecDestroy(sl.gexec); sl.gexec = nullptr; }
+    sl.key = key;
+    sl.key_seen = 0;
   }
-  if ((rc = run_pipeline(ctx, ch, ws, n, in_h, in_w, map_h, map_w, img_len, inject_paf, inject_heat))) return rc;
-  if ((rc = copy_out(ctx, sl.h_result, ws->headers, sizeof(ImageHeader) * n, OPB_HOST))) return rc;
-  if ((rc = copy_out(ctx, sl.h_result + sizeof(ImageHeader) * n, ws->persons,
-                     sizeof(PersonOut) * n * static_cast<size_t>(ctx->prm.max_persons), OPB_HOST))) return rc;
+  if (graphs && sl.gexec) {
+    OPB_CUDA(ctx, cudaGraphLaunch(sl.gexec, ctx->stream));
+    ctx->launches += sl.graph_launches;
+  } else if (graphs && sl.key_seen >= 1) {
+    // second submit of this combination: capture the launch sequence, then run it as a graph
+    const int64_t l0 = ctx->launches;
+    OPB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    rc = body();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess || !graph) OPB_FAIL(ctx, OPB_ERR_CUDA, std::string("stream capture failed: ") + cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&sl.gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { sl.gexec = nullptr; OPB_FAIL(ctx, OPB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+    sl.graph_launches = ctx->launches - l0;
+    OPB_CUDA(ctx, cudaGraphLaunch(sl.gexec, ctx->stream));
+  } else {
+    if ((rc = body())) return rc;
+  }
+  sl.key_seen++;
   OPB_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream));
   sl.n = n;
   sl.busy = true;

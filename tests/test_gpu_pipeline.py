@@ -180,6 +180,13 @@ def test_stream_mode_matches_single_calls(det_parity):
         else:
             p, sc = det_parity(f)
             assert g[0].shape == p.shape and np.array_equal(g[0], p) and np.array_equal(g[1], sc)
+    # same shape submitted repeatedly: from the second submit per slot the launch sequence is captured into a CUDA
+    # graph and replayed -- results must not change (8 frames = 4 per slot: eager, capture, replay, replay)
+    same = [syn.procedural_image(480, 640, seed=30 + i) for i in range(8)]
+    got = list(det_parity.detect_stream(iter(same)))
+    for f, g in zip(same, got):
+        p, sc = det_parity(f)
+        assert g[0].shape == p.shape and np.array_equal(g[0], p) and np.array_equal(g[1], sc)
     # protocol errors are reported, not silently overwritten
     eng = det_parity.engine
     eng.stream_submit(frames[0], 368, 496, 320, 432, slot=0)
