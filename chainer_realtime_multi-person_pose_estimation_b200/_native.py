@@ -61,8 +61,9 @@ _SIGNATURES = {
     "opb_detect_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "opb_stream_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                    C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
+                                    C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "opb_stream_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "opb_stream_join": (C.c_int, [C.c_void_p]),
     "opb_keypoints_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "opb_keypoints_from_heatmaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -297,8 +298,10 @@ class Engine(object):
                                               _ptr(persons), OPB_HOST))
         return headers, persons
 
-    def stream_submit(self, frames, in_h, in_w, map_h, map_w, slot, img_len=None, inject_paf=None, inject_heat=None):
-        """Enqueue one batch [N,H0,W0,3] uint8 (host) on `slot` (0/1) without waiting (opb_stream_submit)."""
+    def stream_submit(self, frames, in_h, in_w, map_h, map_w, slot, img_len=None, inject_paf=None, inject_heat=None,
+                      device=False):
+        """Enqueue one batch [N,H0,W0,3] uint8 on `slot` (0/1) without waiting (opb_stream_submit).  `frames`: a
+        NumPy array (host), or (address, n, h, w) of a pinned host buffer -- or of a device buffer with device=True."""
         if isinstance(frames, np.ndarray):
             frames = np.ascontiguousarray(frames, np.uint8)
             if frames.ndim == 3:
@@ -312,9 +315,14 @@ class Engine(object):
             ptr = C.c_void_p(addr)
         self._stream_n = getattr(self, "_stream_n", {})
         self._stream_n[slot] = n
-        self._check(self.lib.opb_stream_submit(self.ctx, ptr, n, oh, ow, in_h, in_w, map_h, map_w,
+        self._check(self.lib.opb_stream_submit(self.ctx, ptr, OPB_DEVICE if device else OPB_HOST, n, oh, ow, in_h, in_w,
+                                               map_h, map_w,
                                                float(map_w if img_len is None else img_len),
                                                C.c_void_p(inject_paf or 0), C.c_void_p(inject_heat or 0), slot))
+
+    def stream_join(self):
+        """Make the context's stream wait for every submitted, uncollected batch (opb_stream_join)."""
+        self._check(self.lib.opb_stream_join(self.ctx))
 
     def stream_collect(self, slot):
         """Block until the batch submitted on `slot` is done; returns (headers[N], persons[N, max_persons])."""

@@ -177,7 +177,10 @@ struct opb_ctx {
     int64_t graph_launches = 0;
   } slots[2];
   cudaStream_t copy_stream = nullptr;
+  int cur_slot = 0;                // streaming slot whose chain / workspace get_chain / get_post hand out
+  cudaStream_t stream_b = nullptr; // compute stream of streaming slot 1 (slot 0 uses `stream`)
   uint64_t cache_epoch = 0;        // bumped whenever cached chains / workspaces / weights are freed (invalidates graphs)
+  int two_streams = 1;             // OPB_TWO_STREAMS=0: both streaming slots share `stream` and one set of buffers
   int use_graphs = 1;              // OPB_GRAPH=0: streaming mode launches kernel by kernel
   int conn_cap = kAssignMaxType;
   bool profile = false;                       // OPB_PROFILE=1: cudaEvent after every launch of a batch
@@ -776,16 +779,19 @@ int build_chain_keypoint(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
 }
 
 long long shape_key(int n, int h, int w) { return (static_cast<long long>(n) << 40) | (static_cast<long long>(h) << 20) | w; }
+// streaming slot 1 owns its own activations / workspaces so that the two slots can run on two streams
+long long slot_key(const opb_ctx* ctx, int n, int h, int w) { return shape_key(n, h, w) | (static_cast<long long>(ctx->cur_slot) << 62); }
 
 int get_chain(opb_ctx* ctx, int n, int h, int w, Chain** out) {
   if (ctx->precision < 0) OPB_FAIL(ctx, OPB_ERR_STATE, "opb_finalize_weights has not been called");
   if (n <= 0 || h <= 0 || w <= 0 || (h % 8) || (w % 8)) OPB_FAIL(ctx, OPB_ERR_ARG, "H and W must be positive multiples of 8");
-  const long long key = shape_key(n, h, w);
+  const long long key = slot_key(ctx, n, h, w);
   auto it = ctx->chains.find(key);
   if (it != ctx->chains.end()) { *out = it->second; ctx->last_chain = it->second; return OPB_OK; }
   // keep at most a few cached shapes (the precise path cycles through 4)
-  if (ctx->chains.size() >= 6) {
-    for (auto& kv : ctx->chains) { cudaStreamSynchronize(ctx->stream); free_all(kv.second->allocs); delete kv.second; }
+  if (ctx->chains.size() >= 10) {
+    cudaDeviceSynchronize();   // both streaming slots may still be running on their chains
+    for (auto& kv : ctx->chains) { free_all(kv.second->allocs); delete kv.second; }
     ctx->chains.clear();
     ctx->cache_epoch++;
     ctx->last_chain = nullptr;
@@ -811,11 +817,11 @@ int run_chain(opb_ctx* ctx, Chain* ch, bool u8_input) {
 
 // ------------------------------------------------------------------ post-process
 int get_post(opb_ctx* ctx, int n, int H, int W, PostWs** out) {
-  const long long key = shape_key(n, H, W);
+  const long long key = slot_key(ctx, n, H, W);
   auto it = ctx->posts.find(key);
   if (it != ctx->posts.end()) { *out = it->second; ctx->last_post = it->second; return OPB_OK; }
-  if (ctx->posts.size() >= 4) {
-    cudaStreamSynchronize(ctx->stream);
+  if (ctx->posts.size() >= 6) {
+    cudaDeviceSynchronize();
     for (auto& kv : ctx->posts) { free_all(kv.second->allocs); delete kv.second; }
     ctx->posts.clear();
     ctx->cache_epoch++;
@@ -1041,6 +1047,7 @@ int opb_create(opb_ctx** out, int device, const opb_params* params) {
   ctx->conn_cap = kAssignMaxType;
   ctx->profile = getenv("OPB_PROFILE") && atoi(getenv("OPB_PROFILE")) > 0;
   if (const char* g = getenv("OPB_GRAPH")) ctx->use_graphs = atoi(g);
+  if (const char* g = getenv("OPB_TWO_STREAMS")) ctx->two_streams = atoi(g);
   *out = ctx;
   return OPB_OK;
 }
@@ -1067,6 +1074,7 @@ void opb_destroy(opb_ctx* ctx) {
     if (sl.done) cudaEventDestroy(sl.done);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->stream_b) cudaStreamDestroy(ctx->stream_b);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1703,8 +1711,8 @@ int opb_detect_image(opb_ctx* ctx, const uint8_t* img, int img_loc, int orig_h, 
                           persons_out, out_loc);
 }
 
-int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, int orig_w, int in_h, int in_w, int map_h,
-                      int map_w, double img_len, const float* inject_paf, const float* inject_heat, int slot) {
+int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int frames_loc, int n, int orig_h, int orig_w, int in_h, int in_w,
+                      int map_h, int map_w, double img_len, const float* inject_paf, const float* inject_heat, int slot) {
   if (!ctx || !frames || n <= 0 || slot < 0 || slot > 1) return OPB_ERR_ARG;
   cudaSetDevice(ctx->device);
   auto& sl = ctx->slots[slot];
@@ -1712,6 +1720,17 @@ int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, in
   Chain* ch = nullptr;
   PostWs* ws = nullptr;
   int rc;
+  if (slot == 1 && ctx->two_streams && !ctx->stream_b)
+    OPB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream_b, cudaStreamNonBlocking));
+  // slot 1 runs on its own stream with its own activations, so the tail / launch gaps of one slot's kernels are
+  // filled by the other slot's; everything below launches on ctx->stream, which is swapped for the call
+  struct SlotScope {
+    opb_ctx* c; cudaStream_t saved; int saved_slot;
+    SlotScope(opb_ctx* c_, int slot_) : c(c_), saved(c_->stream), saved_slot(c_->cur_slot) {
+      if (slot_ == 1 && c->two_streams) { c->stream = c->stream_b; c->cur_slot = 1; }
+    }
+    ~SlotScope() { c->stream = saved; c->cur_slot = saved_slot; }
+  } scope(ctx, slot);
   if ((rc = get_chain(ctx, n, in_h, in_w, &ch))) return rc;
   if ((rc = get_post(ctx, n, map_h, map_w, &ws))) return rc;
   if (!ctx->copy_stream) OPB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -1721,7 +1740,8 @@ int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, in
   }
   const size_t in_b = static_cast<size_t>(n) * orig_h * orig_w * 3;
   const size_t res_b = n * (sizeof(ImageHeader) + sizeof(PersonOut) * static_cast<size_t>(ctx->prm.max_persons));
-  if (sl.d_bytes < in_b) {
+  const bool resident = frames_loc == OPB_DEVICE;   // frames already in HBM: used in place, no upload
+  if (!resident && sl.d_bytes < in_b) {
     if (sl.d_frames) { OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(sl.d_frames); sl.d_frames = nullptr; }
     OPB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sl.d_frames), in_b));
     sl.d_bytes = in_b;
@@ -1734,7 +1754,7 @@ int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, in
   // pageable caller memory goes through the slot's pinned staging buffer so the H2D copy is truly asynchronous
   const uint8_t* h_src = frames;
   cudaPointerAttributes at{};
-  const bool pinned = cudaPointerGetAttributes(&at, frames) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  const bool pinned = resident || (cudaPointerGetAttributes(&at, frames) == cudaSuccess && at.type == cudaMemoryTypeHost);
   cudaGetLastError();
   if (!pinned) {
     if (sl.h_bytes < in_b) {
@@ -1746,16 +1766,19 @@ int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, in
     h_src = sl.h_frames;
   }
   // the slot's previous batch was collected (sl.done reached), so its device frames are free to overwrite
-  OPB_CUDA(ctx, cudaMemcpyAsync(sl.d_frames, h_src, in_b, cudaMemcpyHostToDevice, ctx->copy_stream));
-  OPB_CUDA(ctx, cudaEventRecord(sl.h2d_done, ctx->copy_stream));
-  OPB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
+  const uint8_t* d_frames = resident ? frames : sl.d_frames;
+  if (!resident) {
+    OPB_CUDA(ctx, cudaMemcpyAsync(sl.d_frames, h_src, in_b, cudaMemcpyHostToDevice, ctx->copy_stream));
+    OPB_CUDA(ctx, cudaEventRecord(sl.h2d_done, ctx->copy_stream));
+    OPB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
+  }
   // everything between the upload and the `done` event: [resize] + pipeline + record download
   auto body = [&]() -> int {
     int r;
     if (orig_h == in_h && orig_w == in_w) {
-      ch->img_u8_src = sl.d_frames;
+      ch->img_u8_src = d_frames;
     } else {
-      if ((r = launch_resize_u8(ctx, sl.d_frames, n, orig_h, orig_w, ch->img_u8, in_h, in_w))) return r;
+      if ((r = launch_resize_u8(ctx, d_frames, n, orig_h, orig_w, ch->img_u8, in_h, in_w))) return r;
       ch->img_u8_src = nullptr;
     }
     if ((r = run_pipeline(ctx, ch, ws, n, in_h, in_w, map_h, map_w, img_len, inject_paf, inject_heat))) return r;
@@ -1764,7 +1787,7 @@ int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, in
                     sizeof(PersonOut) * n * static_cast<size_t>(ctx->prm.max_persons), OPB_HOST);
   };
   const opb_ctx::StreamSlot::Key key{n, orig_h, orig_w, in_h, in_w, map_h, map_w, img_len, inject_paf, inject_heat,
-                                     sl.d_frames, sl.h_result, ch, ws, ctx->cache_epoch};
+                                     d_frames, sl.h_result, ch, ws, ctx->cache_epoch};
   const bool graphs = ctx->use_graphs && !ctx->profile;
   if (!(key == sl.key)) {
     if (sl.gexec) { cudaGraphExecDestroy(sl.gexec); sl.gexec = nullptr; }
@@ -1795,6 +1818,14 @@ int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, in
   OPB_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream));
   sl.n = n;
   sl.busy = true;
+  return OPB_OK;
+}
+
+int opb_stream_join(opb_ctx* ctx) {
+  if (!ctx) return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  for (auto& sl : ctx->slots)
+    if (sl.busy && sl.done) OPB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.done, 0));
   return OPB_OK;
 }
 

@@ -174,12 +174,17 @@ int opb_detect_image(opb_ctx* ctx, const uint8_t* img, int img_loc, int orig_h, 
  *    enqueues [pinned staging ->] H2D on a copy stream, the device resize (if orig != in), the whole
  *    pipeline and the D2H of the records, and returns without waiting; collect() blocks until that
  *    slot's records are on the host.  Submitting batch i+1 before collecting batch i overlaps its
- *    upload with batch i's kernels.  frames: HOST [n,orig_h,orig_w,3] uint8 BGR (pinned or pageable).
+ *    upload with batch i's kernels.  frames: [n,orig_h,orig_w,3] uint8 BGR, HOST (pinned or pageable) or DEVICE
+ *    (used in place; must stay valid until the slot is collected).
  *    inject_* as in opb_detect_batch (device pointers or NULL).                                 */
-int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int n, int orig_h, int orig_w, int in_h,
-                      int in_w, int map_h, int map_w, double img_len, const float* inject_paf,
+int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int frames_loc, int n, int orig_h, int orig_w,
+                      int in_h, int in_w, int map_h, int map_w, double img_len, const float* inject_paf,
                       const float* inject_heat, int slot);
 int opb_stream_collect(opb_ctx* ctx, int slot, opb_image_header* headers_out, opb_person* persons_out);
+/* Slot 1 runs on a library-owned stream (its kernels fill the tails and launch gaps of slot 0's).  join makes the
+ * context's stream (opb_set_stream) wait for every submitted, uncollected batch -- for callers that time or
+ * order other work on that stream.                                                              */
+int opb_stream_join(opb_ctx* ctx);
 
 /* -- face / hand nets.  A context whose loaded layers contain "conv6_2_CPM" is a FaceNet /
  *    HandNet context (models/FaceNet.py:10-76, models/HandNet.py; 52 layers, final 1x1 with 71 / 22 channels):
