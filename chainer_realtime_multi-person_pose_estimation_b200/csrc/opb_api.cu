@@ -17,6 +17,7 @@
 
 #include "../../include/opb.h"
 #include "conv_first.cuh"
+#include "conv_mlp2.cuh"
 #include "ingest.cuh"
 #include "keypoints.cuh"
 #include "conv_tcgen05.cuh"
@@ -58,7 +59,7 @@ struct Act {              // NHWC fp16 activation tensor, channels [hi C | lo C]
   size_t bytes() const { return static_cast<size_t>(N) * H * W * Ctot * sizeof(__half); }
 };
 
-enum OpKind { OP_FIRST, OP_CONV, OP_POOL };
+enum OpKind { OP_FIRST, OP_CONV, OP_POOL, OP_MLP2 };
 
 struct Op {
   OpKind kind;
@@ -71,6 +72,7 @@ struct Op {
   CUtensorMap tmP16[2];
   CUtensorMap tmA[2], tmB[2];
   ConvParams P;
+  Mlp2Params M;        // OP_MLP2 (fused 1x1 -> ReLU -> 1x1): tmA = input, tmB = first weights, tmP16 = second weights
   int grid = 0;
   // OP_FIRST / OP_POOL
   const __half* in = nullptr;
@@ -387,6 +389,18 @@ int launch_conv(opb_ctx* ctx, const Op& op) {
 
 int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
   if (op.kind == OP_CONV) return launch_conv(ctx, op);
+  if (op.kind == OP_MLP2) {
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+      OPB_CUDA(ctx, cudaFuncSetAttribute(conv_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlp2Smem));
+      attr_set[ctx->device & 63] = true;
+    }
+    conv_mlp2_kernel<<<op.grid, 128, kMlp2Smem, ctx->stream>>>(op.tmA[0], op.tmB[0], op.tmP16[0], op.tmA[1], op.tmB[1],
+                                                              op.tmP16[1], op.M);
+    ctx->launches++;
+    OPB_CUDA(ctx, cudaGetLastError());
+    return OPB_OK;
+  }
   if (op.kind == OP_POOL) {
     const size_t total = static_cast<size_t>(op.N) * (op.H / 2) * (op.W / 2) * (op.C / 8);
     const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(ctx->num_sms) * 16));
@@ -611,6 +625,56 @@ int alloc_act(opb_ctx* ctx, Chain* ch, Act* a, int N, int H, int W, int C) {
 
 int build_chain_keypoint(opb_ctx* ctx, Chain* ch, int N, int H, int W);
 
+// Fused Mconv6 (1x1 128->128 + ReLU) -> Mconv7 (1x1 128->C, C <= 48) of one stage, fast precision (csrc/conv_mlp2.cuh).
+// in: 128 channels at in_coff[p] of `in`; out: channel slice out_coff[p] of `out` (+ optional planar fp32 copy).
+bool mlp2_enabled(const opb_ctx* ctx) {
+  const char* e = getenv("OPB_NO_MLP2");
+  return ctx->precision == OPB_PRECISION_FAST && !(e && atoi(e));
+}
+
+int add_mlp2(opb_ctx* ctx, Chain* ch, const std::string& tag, int n_problems, const Act& in, const int in_coff[2],
+             const std::string w1[2], const std::string w2[2], const Act& out, const int out_coff[2],
+             const int cout_valid[2], float* const out32[2]) {
+  Op op;
+  op.kind = OP_MLP2;
+  op.tag = tag;
+  std::memset(&op.M, 0, sizeof(op.M));
+  Mlp2Params& M = op.M;
+  M.N = in.N; M.H = in.H; M.W = in.W;
+  M.tiles_x = (in.W + 7) / 8;
+  M.tiles_y = (in.H + 15) / 16;
+  M.n_problems = n_problems;
+  if (in.H < 16 || in.W < 8) OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "feature map smaller than one TMA box (16 x 8)");
+  for (int p = 0; p < n_problems; ++p) {
+    const PackedW& a = ctx->packed.at(w1[p]);
+    const PackedW& b = ctx->packed.at(w2[p]);
+    if (a.ks != 1 || b.ks != 1 || a.cin_pad != 128 || a.cout_pad != 128 || b.cin_pad != 128 || b.cout_pad != kMlp2N2 ||
+        a.k_per_tap != 128 || b.k_per_tap != 128)
+      OPB_FAIL(ctx, OPB_ERR_ARG, "fused 1x1 pair needs 128 -> 128 -> <= 48 channels");
+    int rc = make_act_map(ctx, &op.tmA[p], in, in_coff[p], 1);
+    if (rc) return rc;
+    if ((rc = make_w_map(ctx, &op.tmB[p], a, 128))) return rc;
+    if ((rc = make_w_map(ctx, &op.tmP16[p], b, kMlp2N2))) return rc;
+    M.bias1[p] = a.bias;
+    ConvProblem& pr = M.prob[p];
+    pr.out = out.p;
+    pr.out32 = out32[p];
+    pr.bias = b.bias;
+    pr.out_cstride = out.Ctot;
+    pr.out_coff = out_coff[p];
+    pr.out_lo_off = 0;
+    pr.cout_valid = cout_valid[p];
+    pr.relu = 0;
+    pr.pool = 0;
+  }
+  if (n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; op.tmP16[1] = op.tmP16[0]; M.prob[1] = M.prob[0]; M.bias1[1] = M.bias1[0]; }
+  const int m_tiles = M.N * M.tiles_y * M.tiles_x;
+  const int per_problem = std::min(m_tiles, 2 * ctx->num_sms / n_problems);    // two CTAs per SM in total
+  op.grid = per_problem * n_problems;
+  ch->ops.push_back(op);
+  return OPB_OK;
+}
+
 int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
   if (ctx->kp_out) return build_chain_keypoint(ctx, ch, N, H, W);
   ch->N = N; ch->H = H; ch->W = W;
@@ -702,9 +766,16 @@ int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
     RC(conv2("Mconv7x7", "Mconv3" + S + "_L1", "Mconv3" + S + "_L2", SB, 0, 128, SA, 0, 128, 128, 128, 1, nullptr, nullptr));
     RC(conv2("Mconv7x7", "Mconv4" + S + "_L1", "Mconv4" + S + "_L2", SA, 0, 128, SB, 0, 128, 128, 128, 1, nullptr, nullptr));
     RC(conv2("Mconv7x7", "Mconv5" + S + "_L1", "Mconv5" + S + "_L2", SB, 0, 128, SA, 0, 128, 128, 128, 1, nullptr, nullptr));
-    RC(conv2("Mconv6", "Mconv6" + S + "_L1", "Mconv6" + S + "_L2", SA, 0, 128, SB, 0, 128, 128, 128, 1, nullptr, nullptr));
-    RC(conv2("Mconv7", "Mconv7" + S + "_L1", "Mconv7" + S + "_L2", SB, 0, 128, CAT, 128, 166, 38, 19, 0,
-             st == 6 ? ch->paf_lo : nullptr, st == 6 ? ch->heat_lo : nullptr));
+    if (mlp2_enabled(ctx)) {   // Mconv6 + Mconv7 of both branches in one launch; the 128-channel intermediate stays on chip
+      const int ic[2] = {0, 128}, oc[2] = {128, 166}, cv[2] = {38, 19};
+      const std::string w1[2] = {"Mconv6" + S + "_L1", "Mconv6" + S + "_L2"}, w2[2] = {"Mconv7" + S + "_L1", "Mconv7" + S + "_L2"};
+      float* const o32[2] = {st == 6 ? ch->paf_lo : nullptr, st == 6 ? ch->heat_lo : nullptr};
+      RC(add_mlp2(ctx, ch, "Mconv6+7", 2, SA, ic, w1, w2, CAT, oc, cv, o32));
+    } else {
+      RC(conv2("Mconv6", "Mconv6" + S + "_L1", "Mconv6" + S + "_L2", SA, 0, 128, SB, 0, 128, 128, 128, 1, nullptr, nullptr));
+      RC(conv2("Mconv7", "Mconv7" + S + "_L1", "Mconv7" + S + "_L2", SB, 0, 128, CAT, 128, 166, 38, 19, 0,
+               st == 6 ? ch->paf_lo : nullptr, st == 6 ? ch->heat_lo : nullptr));
+    }
   }
 #undef RC
   return OPB_OK;
@@ -771,8 +842,15 @@ int build_chain_keypoint(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
     RC(conv("Mconv3" + S, SB, SA, 0, 128));
     RC(conv("Mconv4" + S, SA, SB, 0, 128));
     RC(conv("Mconv5" + S, SB, SA, 0, 128));
-    RC(conv("Mconv6" + S, SA, SB, 0, 128));
-    RC(conv("Mconv7" + S, SB, CAT, 128, KC, 0, 0, st == 6 ? ch->heat_lo : nullptr));
+    if (mlp2_enabled(ctx) && KC <= kMlp2N2) {     // HandNet (22 maps); FaceNet's 71 maps keep the two launches
+      const int ic[2] = {0, 0}, oc[2] = {128, 128}, cv[2] = {KC, KC};
+      const std::string w1[2] = {"Mconv6" + S, "Mconv6" + S}, w2[2] = {"Mconv7" + S, "Mconv7" + S};
+      float* const o32[2] = {st == 6 ? ch->heat_lo : nullptr, nullptr};
+      RC(add_mlp2(ctx, ch, "Mconv6+7", 1, SA, ic, w1, w2, CAT, oc, cv, o32));
+    } else {
+      RC(conv("Mconv6" + S, SA, SB, 0, 128));
+      RC(conv("Mconv7" + S, SB, CAT, 128, KC, 0, 0, st == 6 ? ch->heat_lo : nullptr));
+    }
   }
 #undef RC
   return OPB_OK;

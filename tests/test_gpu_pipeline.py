@@ -84,6 +84,28 @@ def test_fast_mode_uint8_entry_matches_float_entry(weights_model):
         assert e < 4e-3 * max(mag, 1.0)
 
 
+def test_fused_1x1_pair_is_bit_identical_to_two_launches(weights_model, monkeypatch):
+    """Mconv6 + Mconv7 fused into one kernel (csrc/conv_mlp2.cuh, the 128-channel intermediate stays in shared memory)
+    vs the two separate 1x1 launches: same MMA shapes and accumulation order, so the maps must be bit-identical --
+    batch 2 (throughput tile shapes), batch 1 (small-batch shapes) and HandNet (single branch)."""
+    syn = pkg("synthetic")
+    imgs = syn.random_images(2, 368, 496, seed=4)
+    hn = pkg("models.HandNet")
+    hand = hn.HandNet()
+    hand.load_npz(syn.he_weights(0, layers=hn.LAYERS))
+    crop = syn.procedural_image(368, 368, seed=5)[None]
+    out = []
+    for no_fuse in ("0", "1"):
+        monkeypatch.setenv("OPB_NO_MLP2", no_fuse)
+        det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="fast")
+        hd = pkg("hand_detector").HandDetector(model=hand, device=0, precision="fast")
+        out.append((det.engine.forward(imgs), det.engine.forward(imgs[:1]), hd.engine.forward_keypoint_maps(crop)))
+        del det, hd
+    (a2, a1, ah), (b2, b1, bh) = out
+    for x, y in ((a2[0], b2[0]), (a2[1], b2[1]), (a1[0], b1[0]), (a1[1], b1[1]), (ah, bh)):
+        assert np.isfinite(x).all() and np.array_equal(x, y), float(np.abs(x - y).max())
+
+
 def test_forward_maps_fast_mode(weights_model):
     det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="fast")
     g = load_golden("fast_584_he0.npz")
