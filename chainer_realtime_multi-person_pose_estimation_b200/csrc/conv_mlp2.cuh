@@ -86,15 +86,21 @@ conv_mlp2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int m_tiles = P.N * P.tiles_y * P.tiles_x;
   uint32_t par_a = 0, par_m = 0;
   bool weights_ready = false;
+  auto load_tile = [&](int t) {                  // thread 0: input tile t -> sA (both 64-channel chunks)
+    const int tn = t / (P.tiles_y * P.tiles_x);
+    const int trem = t - tn * (P.tiles_y * P.tiles_x);
+    const int tty = trem / P.tiles_x, ttx = trem - tty * P.tiles_x;
+    ptx::mbar_expect_tx(&bars[1], kMlp2A);
+    ptx::tma_load_4d(sA, tmA, &bars[1], 0, ttx * 8, tty * 16, tn);
+    ptx::tma_load_4d(sA + 16384, tmA, &bars[1], 64, ttx * 8, tty * 16, tn);
+  };
+  if (tid == 0 && cta < m_tiles) load_tile(cta);
   for (int tile = cta; tile < m_tiles; tile += n_cta) {
     const int n = tile / (P.tiles_y * P.tiles_x);
     const int rem = tile - n * (P.tiles_y * P.tiles_x);
     const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
     const int y0 = ty * 16, x0 = tx * 8;
     if (tid == 0) {
-      ptx::mbar_expect_tx(&bars[1], kMlp2A);
-      ptx::tma_load_4d(sA, tmA, &bars[1], 0, x0, y0, n);
-      ptx::tma_load_4d(sA + 16384, tmA, &bars[1], 64, x0, y0, n);
       if (!weights_ready) ptx::mbar_wait(&bars[0], 0);
       ptx::mbar_wait(&bars[1], par_a);
       ptx::tc_fence_after();
@@ -113,6 +119,8 @@ conv_mlp2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     ptx::mbar_wait(&bars[2], par_m);
     par_m ^= 1;
     ptx::tc_fence_after();
+    // GEMM 1 has consumed sA: fetch the next tile now, behind this tile's epilogues and GEMM 2
+    if (tid == 0 && tile + n_cta < m_tiles) load_tile(tile + n_cta);
     // epilogue 1: h = relu(acc + b1) -> fp16 -> sI in the K-major SWIZZLE_128B layout (row = tid)
 #pragma unroll
     for (int c0 = 0; c0 < 128; c0 += 32) {
