@@ -1166,6 +1166,7 @@ int opb_set_stream(opb_ctx* ctx, void* cuda_stream) {
 int opb_synchronize(opb_ctx* ctx) {
   if (!ctx) return OPB_ERR_ARG;
   OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->stream_b) OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_b));   // streaming slot 1
   return OPB_OK;
 }
 
