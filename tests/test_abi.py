@@ -164,3 +164,39 @@ def test_demo_import_flow_face_hand_modules():
                               rh.draw_hand_keypoints(img, hand, (3, 4)).ravel(), pf.ravel()])
         assert np.array_equal(np.load(out), ref)
 
+
+
+@pytest.mark.parametrize("name,hw", [("fast_584_he0.npz", (584, 584)), ("fast_480x640_he0.npz", (480, 640)),
+                                      ("fast_368x656_he0_img0.npz", (368, 656))])
+def test_pose_records_to_pose_array_reproduces_reference_rescale(name, hw):
+    """Host half of __call__: the device returns integer peak coordinates at map resolution; the float64 rescale of
+    pose_detector.py:513-515 (`x *= orig_w / map_w` in place, then subsets_to_pose_array) is redone on the host and
+    must give the golden poses / scores bit for bit."""
+    from conftest import load_golden
+    from oracle import restate as R
+    native = pkg("_native")
+    PD = pkg("pose_detector").PoseDetector
+    det = PD.__new__(PD)
+
+    class _Eng(object):
+        def raise_for_status(self, s):
+            assert s == 0
+    det.engine = _Eng()
+    g = load_golden(name)
+    oh, ow = hw
+    map_w, map_h = R.compute_optimal_size(np.zeros((oh, ow, 3), np.uint8), 320)
+    subsets, peaks = g["subsets"], g["all_peaks"]
+    n = len(subsets)
+    header = np.zeros(1, native.HEADER_DTYPE)
+    header["n_peaks"], header["n_persons"] = len(peaks), n
+    persons = np.zeros(max(n, 1), native.PERSON_DTYPE)
+    ids = subsets[:, :18].astype(np.int64)
+    persons["peak_id"][:n] = ids
+    safe = np.where(ids >= 0, ids, 0)
+    persons["x"][:n] = np.where(ids >= 0, peaks[safe, 1].astype(np.int64), 0)
+    persons["y"][:n] = np.where(ids >= 0, peaks[safe, 2].astype(np.int64), 0)
+    persons["score"][:n] = subsets[:, 18]
+    persons["count"][:n] = subsets[:, 19]
+    poses, scores = det._poses_from_records(header[0], persons, ow / map_w, oh / map_h)
+    assert poses.shape == g["poses"].shape and np.array_equal(poses, g["poses"])
+    assert np.array_equal(scores, g["scores"])
