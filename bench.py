@@ -141,8 +141,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "full pipeline 368x656, synthetic 8-person maps injected, CPU oracle port "
-                               "(reference pose_detector.py restated; torch-CPU fp32 conv; Chainer not installable)",
+        "config": {"workload": "BASELINE.json configs[2]: full pipeline, synthetic 8-person maps injected, 368x656, "
+                               "batch %d per GPU" % args.batch,
+                   "impl_note": "CPU oracle port of the reference path (pose_detector.py restated in oracle/restate.py; "
+                                "torch-CPU fp32 conv; Chainer is not installable offline); the reference is batch-1, so a "
+                                "step is one frame of that workload",
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
