@@ -303,6 +303,7 @@ group_persons_kernel(const PeakD* __restrict__ peaks, const int* __restrict__ pe
         // find the subsets that already hold one endpoint (first two, in row order)
         int found = 0, f0 = -1, f1 = -1;
         const bool known = ((in_row[id_a >> 5] >> (id_a & 31)) | (in_row[id_b >> 5] >> (id_b & 31))) & 1u;
+        __syncwarp();   // every lane has read in_row before lane 0 may set bits for this connection below
         for (int base = 0; known && base < P; base += 128) {
           const int k0 = base + lane * 4;
           unsigned h = 0;

@@ -1,0 +1,100 @@
+"""TEST INFRASTRUCTURE ONLY: builds tests/cuda_emu/_build/libopb_emu.so, the library's own
+sources (csrc/opb_api.cu + kernels, unmodified) compiled by g++ on top of cuda_emu.h (CUDA
+execution model as fibers) and emu_runtime.cpp (host-memory CUDA runtime stubs).
+
+The package never loads this library: only tests/test_emu_*.py dlopen it, to run the
+plain-CUDA kernels and the C-ABI host orchestration on a box without a GPU and compare them
+bit-for-bit with the oracle.  Tensor-core kernels (inline PTX) trap under emulation.
+
+Source rewriting (textual, into _build/src; the originals are not touched):
+  kernel<<<grid, block, smem, stream>>>(args)  ->  emu::Launcher(grid, block, smem, stream).run(kernel, args)
+  extern __shared__ T name[];                  ->  T* name = reinterpret_cast<T*>(emu::g_dyn_smem);
+  asm volatile(...);                           ->  emu::unsupported_ptx();
+"""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+PKG = os.path.join(ROOT, "chainer_realtime_multi-person_pose_estimation_b200")
+CSRC = os.path.join(PKG, "csrc")
+BUILD = os.path.join(HERE, "_build")
+CUDA_INC = os.environ.get("CUDA_INC", "/usr/local/cuda/include")
+
+_LAUNCH = re.compile(r"([A-Za-z_][\w:]*(?:<[^<>;(){}]*>)?)\s*<<<(.*?)>>>\s*\(", re.S)
+_DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];")
+
+
+def _strip_asm(text):
+    out, i = [], 0
+    while True:
+        m = re.compile(r"\basm\s+(?:volatile\s*)?\(").search(text, i)
+        if not m:
+            out.append(text[i:])
+            return "".join(out)
+        out.append(text[i:m.start()])
+        depth, j, in_str = 1, m.end(), False
+        while depth:
+            c = text[j]
+            if in_str:
+                if c == "\\":
+                    j += 1
+                elif c == '"':
+                    in_str = False
+            elif c == '"':
+                in_str = True
+            elif c == "(":
+                depth += 1
+            elif c == ")":
+                depth -= 1
+            j += 1
+        while text[j] in " \t\r\n":
+            j += 1
+        assert text[j] == ";", text[m.start():j + 1]
+        out.append("emu::unsupported_ptx();")
+        i = j + 1
+
+
+def rewrite(text):
+    text = _strip_asm(text)
+    text = text.replace('#include "../../include/opb.h"', '#include "opb.h"')
+    text = _LAUNCH.sub(lambda m: "emu::Launcher(%s).run(%s, " % (m.group(2), m.group(1)), text)
+    text = _DYN_SMEM.sub(lambda m: "%s* %s = reinterpret_cast<%s*>(emu::g_dyn_smem);" % (m.group(1), m.group(2), m.group(1)), text)
+    return text
+
+
+def lib_path(contract):
+    return os.path.join(BUILD, "libopb_emu_%s.so" % ("fma" if contract else "nofma"))
+
+
+def build(contract=False, force=False):
+    """contract=True compiles with -ffp-contract=fast -mfma: g++ may then fuse every a*b+c that is
+    not written with an explicit _rn intrinsic, as nvcc does by default -- results must not change."""
+    src_dir = os.path.join(BUILD, "src")
+    os.makedirs(src_dir, exist_ok=True)
+    lib = lib_path(contract)
+    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [
+        os.path.join(HERE, f) for f in ("cuda_emu.h", "emu_runtime.cpp", "build_emu.py")] + [
+        os.path.join(ROOT, "include", "opb.h")]
+    if not force and os.path.isfile(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
+        return lib
+    for f in sorted(os.listdir(CSRC)):
+        with open(os.path.join(CSRC, f)) as fh:
+            text = rewrite(fh.read())
+        with open(os.path.join(src_dir, f.replace(".cu", ".cpp") if f.endswith(".cu") else f), "w") as fh:
+            fh.write(text)
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-w",
+           "-ffp-contract=fast" if contract else "-ffp-contract=off"] + (["-mfma"] if contract else []) + [
+           "-I", CUDA_INC, "-I", os.path.join(ROOT, "include"), "-I", HERE, "-include", os.path.join(HERE, "cuda_emu.h"),
+           os.path.join(src_dir, "opb_api.cpp"), os.path.join(HERE, "emu_runtime.cpp"), "-o", lib]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        open(os.path.join(BUILD, "build.log"), "w").write(r.stdout); sys.stderr.write(r.stdout[-3000:])
+        raise RuntimeError("g++ failed building the emulated library")
+    return lib
+
+
+if __name__ == "__main__":
+    print(build(contract="--fma" in sys.argv, force=True))

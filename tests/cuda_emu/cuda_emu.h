@@ -1,0 +1,369 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE ONLY (never loaded by the package).
+//
+// A single-OS-thread emulation of the CUDA execution model, just large enough to run the
+// library's plain-CUDA kernels (post-process, resize, keypoints) from the *unmodified* kernel
+// sources on a box without a GPU, so that `pytest -m "not gpu"` can check their arithmetic
+// bit-for-bit against the oracle:
+//
+//   * every CUDA thread of a block is a ucontext fiber; blocks run one after another;
+//   * __syncthreads / __syncthreads_or / __syncwarp / shuffles / ballots are cooperative
+//     yields to a scheduler that releases a barrier when all live participants wait on it;
+//   * __shared__ variables become function statics (one block is resident at a time), the
+//     dynamic shared memory window is one static buffer;
+//   * atomics are plain read-modify-writes (one OS thread), __ldg/__stcs plain accesses;
+//   * the _rn arithmetic intrinsics are single IEEE operations fenced against contraction, so
+//     the emulated build may be compiled with -ffp-contract=fast to expose any arithmetic that
+//     would depend on nvcc's FMA contraction.
+//
+// The tensor-core kernels (tcgen05 / TMA inline PTX) compile to traps here: they cannot be
+// emulated and are only ever validated on a B200 (tests marked gpu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <tuple>
+#include <type_traits>
+#include <utility>
+
+#undef __shared__
+#define __shared__ static
+#undef __grid_constant__
+#define __grid_constant__
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+#undef __cluster_dims__
+#define __cluster_dims__(...)
+
+namespace emu {
+
+enum { READY = 0, WAIT_BLOCK = 1, WAIT_WARP = 2, DONE = 3 };
+constexpr int MAX_THREADS = 1024;
+constexpr size_t STACK_BYTES = 256 * 1024;
+
+struct Fiber {
+  ucontext_t ctx;      // portable fallback
+  void* sp = nullptr;  // x86-64 fast path: saved stack pointer (emu_switch in emu_runtime.cpp)
+  char* stack = nullptr;
+  int state = DONE;
+  unsigned mask = 0;
+  int pred = 0;
+  int site = 0;      // which warp-level primitive (and which half of it) the fiber waits in
+  long long nwaits = 0;
+  uint3 tid;
+};
+
+inline Fiber g_fibers[MAX_THREADS];
+inline int g_nfib = 0, g_cur = 0;
+inline ucontext_t g_sched;
+inline void* g_sched_sp = nullptr;
+inline const std::function<void()>* g_body = nullptr;
+inline int g_red_or = 0, g_red_and = 0, g_red_cnt = 0;
+inline uint64_t g_warp_buf[MAX_THREADS / 32][32];
+inline int g_warp_pred[MAX_THREADS / 32][32];
+alignas(1024) inline unsigned char g_dyn_smem[232 * 1024];
+inline uint3 g_tid, g_bid;
+inline dim3 g_bdim, g_gdim;
+inline long long g_launches = 0;
+
+#if defined(__x86_64__)
+#define EMU_FAST_SWITCH 1
+// saves the callee-saved registers and the stack pointer of the running fiber, resumes `to`
+// (no signal-mask system call, unlike swapcontext: ~20x cheaper per synchronisation point)
+extern "C" void emu_switch(void** save_sp, void* to_sp);
+#endif
+
+inline void fiber_entry() {
+  (*g_body)();
+  g_fibers[g_cur].state = DONE;   // uc_link returns to the scheduler
+}
+
+inline void yield_wait(int state) {
+  Fiber& f = g_fibers[g_cur];
+  f.state = state;
+#ifdef EMU_FAST_SWITCH
+  emu_switch(&f.sp, g_sched_sp);
+#else
+  swapcontext(&f.ctx, &g_sched);
+#endif
+}
+
+#ifdef EMU_FAST_SWITCH
+inline void fiber_trampoline() {
+  fiber_entry();
+  emu_switch(&g_fibers[g_cur].sp, g_sched_sp);   // never resumed
+  abort();
+}
+#endif
+
+inline void run_block(int nthreads, const std::function<void()>& body) {
+  if (nthreads > MAX_THREADS) { fprintf(stderr, "emu: block of %d threads\n", nthreads); abort(); }
+  g_nfib = nthreads;
+  g_body = &body;
+  for (int i = 0; i < nthreads; ++i) {
+    Fiber& f = g_fibers[i];
+    if (!f.stack) f.stack = static_cast<char*>(malloc(STACK_BYTES));
+#ifdef EMU_FAST_SWITCH
+    {  // initial frame: six callee-saved registers, then the address emu_switch's `ret` jumps to
+      uintptr_t top = (reinterpret_cast<uintptr_t>(f.stack) + STACK_BYTES) & ~static_cast<uintptr_t>(15);
+      void** sp = reinterpret_cast<void**>(top);
+      *--sp = nullptr;                                            // fake return address of the trampoline
+      *--sp = reinterpret_cast<void*>(&fiber_trampoline);
+      for (int r = 0; r < 6; ++r) *--sp = nullptr;
+      f.sp = sp;
+    }
+#else
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = STACK_BYTES;
+    f.ctx.uc_link = &g_sched;
+    makecontext(&f.ctx, fiber_entry, 0);
+#endif
+    f.state = READY;
+    f.nwaits = 0;
+    f.tid.x = i % g_bdim.x;
+    f.tid.y = (i / g_bdim.x) % g_bdim.y;
+    f.tid.z = i / (g_bdim.x * g_bdim.y);
+  }
+  for (;;) {
+    bool ran = false;
+    for (int i = 0; i < nthreads; ++i) {
+      if (g_fibers[i].state != READY) continue;
+      g_cur = i;
+      g_tid = g_fibers[i].tid;
+#ifdef EMU_FAST_SWITCH
+      emu_switch(&g_sched_sp, g_fibers[i].sp);
+#else
+      swapcontext(&g_sched, &g_fibers[i].ctx);
+#endif
+      ran = true;
+    }
+    // warp-level barriers: release a group when every live lane of its mask waits
+    bool released = false;
+    for (int base = 0; base < nthreads; base += 32) {
+      for (int l = 0; l < 32 && base + l < nthreads; ++l) {
+        Fiber& f = g_fibers[base + l];
+        if (f.state != WAIT_WARP) continue;
+        bool all = true;
+        for (int j = 0; j < 32 && base + j < nthreads; ++j) {
+          if (!((f.mask >> j) & 1u)) continue;
+          const int s = g_fibers[base + j].state;
+          if (s == DONE) continue;
+          if (s != WAIT_WARP || g_fibers[base + j].mask != f.mask) { all = false; break; }
+        }
+        if (!all) continue;
+        for (int j = 0; j < 32 && base + j < nthreads; ++j) {   // convergence check: same primitive, same count
+          const Fiber& o = g_fibers[base + j];
+          if (!((f.mask >> j) & 1u) || o.state != WAIT_WARP) continue;
+          if (o.site != f.site || o.nwaits != f.nwaits) {
+            fprintf(stderr, "emu: divergent warp-synchronous code in block (%u,%u,%u): lane %d waits in primitive %d (#%lld), "
+                    "lane %d in primitive %d (#%lld)\n", g_bid.x, g_bid.y, g_bid.z, l, f.site, f.nwaits, j, o.site, o.nwaits);
+            abort();
+          }
+        }
+        const unsigned m = f.mask;
+        for (int j = 0; j < 32 && base + j < nthreads; ++j)
+          if (((m >> j) & 1u) && g_fibers[base + j].state == WAIT_WARP) g_fibers[base + j].state = READY;
+        released = true;
+      }
+    }
+    if (released) continue;
+    int live = 0, waiting = 0, r_or = 0, r_and = 1, r_cnt = 0;
+    for (int i = 0; i < nthreads; ++i) {
+      const Fiber& f = g_fibers[i];
+      if (f.state == DONE) continue;
+      ++live;
+      if (f.state == WAIT_BLOCK) { ++waiting; r_or |= (f.pred != 0); r_and &= (f.pred != 0); r_cnt += (f.pred != 0); }
+    }
+    if (live == 0) break;
+    if (waiting == live) {
+      g_red_or = r_or; g_red_and = r_and; g_red_cnt = r_cnt;
+      for (int i = 0; i < nthreads; ++i) if (g_fibers[i].state == WAIT_BLOCK) g_fibers[i].state = READY;
+      continue;
+    }
+    if (!ran) {
+      fprintf(stderr, "emu: deadlock in block (%u,%u,%u): %d live, %d at __syncthreads, rest at divergent warp barriers\n",
+              g_bid.x, g_bid.y, g_bid.z, live, waiting);
+      abort();
+    }
+  }
+}
+
+struct Launcher {
+  dim3 g, b;
+  size_t smem;
+  Launcher(dim3 grid, dim3 block, size_t smem_bytes = 0, cudaStream_t = nullptr) : g(grid), b(block), smem(smem_bytes) {}
+  template <class... KA, class... A>
+  void run(void (*k)(KA...), A&&... a) {
+    if (smem > sizeof(g_dyn_smem)) { fprintf(stderr, "emu: %zu B of dynamic shared memory\n", smem); abort(); }
+    std::tuple<std::decay_t<KA>...> args(std::forward<A>(a)...);
+    const std::function<void()> body = [&] { std::apply(k, args); };
+    g_bdim = b; g_gdim = g;
+    ++g_launches;
+    const int nthreads = static_cast<int>(b.x * b.y * b.z);
+    for (unsigned z = 0; z < g.z; ++z)
+      for (unsigned y = 0; y < g.y; ++y)
+        for (unsigned x = 0; x < g.x; ++x) {
+          g_bid.x = x; g_bid.y = y; g_bid.z = z;
+          run_block(nthreads, body);
+        }
+  }
+};
+
+[[noreturn]] inline void unsupported_ptx() {
+  fprintf(stderr, "emu: inline PTX (tcgen05 / TMA / mbarrier) cannot be emulated -- this kernel needs a B200\n");
+  abort();
+}
+
+inline int lane_id() { return g_cur & 31; }
+inline int warp_id() { return g_cur >> 5; }
+inline void warp_wait(unsigned mask, int site) {
+  Fiber& f = g_fibers[g_cur];
+  f.mask = mask; f.site = site; ++f.nwaits;
+  yield_wait(WAIT_WARP);
+}
+
+template <class T>
+inline T shfl_from(unsigned mask, T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  uint64_t bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  g_warp_buf[warp_id()][lane_id()] = bits;
+  warp_wait(mask, 10 + static_cast<int>(sizeof(T)));
+  const uint64_t r = g_warp_buf[warp_id()][src_lane & 31];
+  warp_wait(mask, 20 + static_cast<int>(sizeof(T)));
+  T out;
+  memcpy(&out, &r, sizeof(T));
+  return out;
+}
+
+inline unsigned ballot(unsigned mask, int pred) {
+  g_warp_pred[warp_id()][lane_id()] = pred != 0;
+  warp_wait(mask, 3);
+  unsigned r = 0;
+  const int base = warp_id() * 32;
+  for (int j = 0; j < 32 && base + j < g_nfib; ++j)
+    if (((mask >> j) & 1u) && g_fibers[base + j].state != DONE && g_warp_pred[warp_id()][j]) r |= 1u << j;
+  warp_wait(mask, 4);
+  return r;
+}
+
+inline unsigned live_mask(unsigned mask) {
+  unsigned r = 0;
+  const int base = warp_id() * 32;
+  for (int j = 0; j < 32 && base + j < g_nfib; ++j)
+    if (((mask >> j) & 1u) && g_fibers[base + j].state != DONE) r |= 1u << j;
+  return r;
+}
+
+}  // namespace emu
+
+#define threadIdx emu::g_tid
+#define blockIdx emu::g_bid
+#define blockDim emu::g_bdim
+#define gridDim emu::g_gdim
+constexpr int warpSize = 32;
+
+// ---- synchronisation ---------------------------------------------------------------------------
+inline void __syncthreads() { emu::g_fibers[emu::g_cur].pred = 0; emu::yield_wait(emu::WAIT_BLOCK); }
+inline int __syncthreads_or(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_or; }
+inline int __syncthreads_and(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_and; }
+inline int __syncthreads_count(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_cnt; }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_wait(mask, 1); }
+template <class T> inline T __shfl_sync(unsigned m, T v, int src, int width = 32) {
+  const int l = emu::lane_id();
+  return emu::shfl_from(m, v, (l & ~(width - 1)) | (src & (width - 1)));
+}
+template <class T> inline T __shfl_xor_sync(unsigned m, T v, int lane_mask, int width = 32) {
+  const int l = emu::lane_id(), s = l ^ lane_mask;
+  return emu::shfl_from(m, v, ((s & ~(width - 1)) == (l & ~(width - 1))) ? s : l);
+}
+template <class T> inline T __shfl_down_sync(unsigned m, T v, unsigned d, int width = 32) {
+  const int l = emu::lane_id(), s = l + static_cast<int>(d);
+  return emu::shfl_from(m, v, ((s & ~(width - 1)) == (l & ~(width - 1))) ? s : l);
+}
+template <class T> inline T __shfl_up_sync(unsigned m, T v, unsigned d, int width = 32) {
+  const int l = emu::lane_id(), s = l - static_cast<int>(d);
+  return emu::shfl_from(m, v, (s >= (l & ~(width - 1))) ? s : l);
+}
+inline unsigned __ballot_sync(unsigned m, int p) { return emu::ballot(m, p); }
+inline int __any_sync(unsigned m, int p) { return emu::ballot(m, p) != 0; }
+inline int __all_sync(unsigned m, int p) { const unsigned b = emu::ballot(m, p); return b == emu::live_mask(m); }
+[[noreturn]] inline void __trap() { fprintf(stderr, "emu: __trap()\n"); abort(); }
+
+// ---- memory ------------------------------------------------------------------------------------
+template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T, class U> inline void __stcs(T* p, U v) { *p = v; }
+template <class T, class U> inline T atomicAdd(T* p, U v) { const T o = *p; *p = static_cast<T>(o + v); return o; }
+template <class T, class U> inline T atomicMax(T* p, U v) { const T o = *p; if (static_cast<T>(v) > o) *p = static_cast<T>(v); return o; }
+template <class T, class U> inline T atomicMin(T* p, U v) { const T o = *p; if (static_cast<T>(v) < o) *p = static_cast<T>(v); return o; }
+template <class T, class U> inline T atomicOr(T* p, U v) { const T o = *p; *p = o | static_cast<T>(v); return o; }
+template <class T, class U> inline T atomicAnd(T* p, U v) { const T o = *p; *p = o & static_cast<T>(v); return o; }
+template <class T, class U> inline T atomicExch(T* p, U v) { const T o = *p; *p = static_cast<T>(v); return o; }
+template <class T, class U, class V> inline T atomicCAS(T* p, U c, V v) { const T o = *p; if (o == static_cast<T>(c)) *p = static_cast<T>(v); return o; }
+inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
+
+// ---- single IEEE operations, fenced against contraction ---------------------------------------------
+#define EMU_FENCE(x) asm volatile("" : "+x"(x))
+inline double __dadd_rn(double a, double b) { double r = a + b; EMU_FENCE(r); return r; }
+inline double __dsub_rn(double a, double b) { double r = a - b; EMU_FENCE(r); return r; }
+inline double __dmul_rn(double a, double b) { double r = a * b; EMU_FENCE(r); return r; }
+inline double __ddiv_rn(double a, double b) { double r = a / b; EMU_FENCE(r); return r; }
+inline double __dsqrt_rn(double a) { double r = std::sqrt(a); EMU_FENCE(r); return r; }
+inline double __fma_rn(double a, double b, double c) { double r = std::fma(a, b, c); EMU_FENCE(r); return r; }
+inline float __fadd_rn(float a, float b) { float r = a + b; EMU_FENCE(r); return r; }
+inline float __fsub_rn(float a, float b) { float r = a - b; EMU_FENCE(r); return r; }
+inline float __fmul_rn(float a, float b) { float r = a * b; EMU_FENCE(r); return r; }
+inline float __fdiv_rn(float a, float b) { float r = a / b; EMU_FENCE(r); return r; }
+inline float __fmaf_rn(float a, float b, float c) { float r = std::fmaf(a, b, c); EMU_FENCE(r); return r; }
+inline float __double2float_rn(double a) { float r = static_cast<float>(a); EMU_FENCE(r); return r; }
+inline int __double2int_rn(double a) { return static_cast<int>(std::nearbyint(a)); }
+inline int __float2int_rn(float a) { return static_cast<int>(std::nearbyintf(a)); }
+inline int __float2int_rd(float a) { return static_cast<int>(std::floor(a)); }
+inline int __double2int_rd(double a) { return static_cast<int>(std::floor(a)); }
+
+// ---- bit tricks ----------------------------------------------------------------------------------
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __clz(int x) { return x ? __builtin_clz(static_cast<unsigned>(x)) : 32; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
+inline long long __double_as_longlong(double d) { long long u; memcpy(&u, &d, 8); return u; }
+inline double __longlong_as_double(long long u) { double d; memcpy(&d, &u, 8); return d; }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+  const uint64_t src = (static_cast<uint64_t>(y) << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) {
+    const unsigned sel = (s >> (4 * i)) & 0xf;
+    unsigned byte = static_cast<unsigned>((src >> (8 * (sel & 7))) & 0xff);
+    if (sel & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+    r |= byte << (8 * i);
+  }
+  return r;
+}
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+  const uint64_t v = (static_cast<uint64_t>(hi) << 32) | lo;
+  return static_cast<unsigned>(v >> (shift & 31));
+}
+
+// CUDA's global min / max overloads
+template <class A, class B, class = std::enable_if_t<std::is_arithmetic<A>::value && std::is_arithmetic<B>::value>>
+inline std::common_type_t<A, B> max(A a, B b) { using T = std::common_type_t<A, B>; return static_cast<T>(a) < static_cast<T>(b) ? static_cast<T>(b) : static_cast<T>(a); }
+template <class A, class B, class = std::enable_if_t<std::is_arithmetic<A>::value && std::is_arithmetic<B>::value>>
+inline std::common_type_t<A, B> min(A a, B b) { using T = std::common_type_t<A, B>; return static_cast<T>(b) < static_cast<T>(a) ? static_cast<T>(b) : static_cast<T>(a); }
+
+// C++ conveniences that cuda_runtime.h only declares under nvcc
+template <class R, class... A>
+inline cudaError_t cudaFuncSetAttribute(R (*)(A...), cudaFuncAttribute, int) { return cudaSuccess; }
+inline long long clock64() { static long long t = 0; return t += 1000; }

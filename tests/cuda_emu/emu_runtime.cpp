@@ -1,0 +1,134 @@
+// emu_runtime.cpp -- TEST INFRASTRUCTURE ONLY: the handful of CUDA runtime entry points that
+// csrc/opb_api.cu calls, implemented over host memory for the emulated build (cuda_emu.h).
+// "Device" memory is malloc'ed host memory, streams and events are dummies (everything is
+// synchronous), graphs / cluster launches / tensor-map encoding report "not supported" or
+// do nothing: the tensor-core paths cannot run here.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+extern "C" {
+
+static int g_dummy_handles = 0;
+static void* new_handle() { ++g_dummy_handles; return malloc(16); }
+
+cudaError_t cudaMalloc(void** p, size_t n) {
+  *p = nullptr;
+  if (posix_memalign(p, 1024, n ? n : 1)) return cudaErrorMemoryAllocation;
+  memset(*p, 0xA5, n);                     // uninitialised device memory is not zero
+  return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMallocHost(p, n); }
+cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {   // macro-renamed to _v2 by the header
+  memset(p, 0, sizeof(*p));
+  strcpy(p->name, "cuda_emu (CPU fibers, tests only)");
+  p->major = 10; p->minor = 0; p->multiProcessorCount = 148;
+  p->sharedMemPerBlockOptin = 232448; p->warpSize = 32;
+  return cudaSuccess;
+}
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "cuda_emu: operation not supported under emulation"; }
+cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+  memset(a, 0, sizeof(*a));
+  a->type = cudaMemoryTypeUnregistered;
+  a->hostPointer = const_cast<void*>(p);
+  return cudaSuccess;
+}
+
+cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = static_cast<cudaStream_t>(new_handle()); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { return cudaStreamCreate(s); }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { if (g) *g = nullptr; return cudaErrorNotSupported; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = static_cast<cudaEvent_t>(new_handle()); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return cudaSuccess; }
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, unsigned long long) { if (e) *e = nullptr; return cudaErrorNotSupported; }
+cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t*, const void*, void**) { return cudaErrorNotSupported; }
+cudaError_t cudaLaunchKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { return cudaErrorNotSupported; }
+
+// cuTensorMapEncodeTiled & co: accept and leave the (unused) descriptor zeroed
+static CUresult emu_driver_stub(...) { return CUDA_SUCCESS; }
+cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
+  *fn = reinterpret_cast<void*>(&emu_driver_stub);
+  if (q) *q = cudaDriverEntryPointSuccess;
+  return cudaSuccess;
+}
+
+}  // extern "C"
+
+// Debug aid: OPB_EMU_BACKTRACE=1 prints a symbolised backtrace on SIGSEGV (fiber stacks included).
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+namespace {
+void emu_segv(int sig) {
+  void* frames[48];
+  const int n = backtrace(frames, 48);
+  const char msg[] = "emu: fatal signal, backtrace:\n";
+  (void)!write(2, msg, sizeof(msg) - 1);
+  backtrace_symbols_fd(frames, n, 2);
+  _exit(128 + sig);
+}
+struct EmuSegvInstaller {
+  EmuSegvInstaller() {
+    if (!getenv("OPB_EMU_BACKTRACE")) return;
+    static char alt[1 << 16];
+    stack_t ss; ss.ss_sp = alt; ss.ss_size = sizeof(alt); ss.ss_flags = 0;
+    sigaltstack(&ss, nullptr);
+    struct sigaction sa; memset(&sa, 0, sizeof(sa));
+    sa.sa_handler = emu_segv; sa.sa_flags = SA_ONSTACK;
+    sigaction(SIGSEGV, &sa, nullptr);
+  }
+} g_emu_segv_installer;
+}  // namespace
+
+#if defined(__x86_64__)
+// void emu_switch(void** save_sp, void* to_sp): cooperative fiber switch used by cuda_emu.h
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size emu_switch,.-emu_switch
+)");
+#endif
