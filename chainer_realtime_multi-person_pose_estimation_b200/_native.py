@@ -56,6 +56,8 @@ _SIGNATURES = {
                             C.POINTER(C.c_int)]),
     "opb_detect_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "opb_postprocess_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "opb_resize_linear_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                        C.c_int, C.c_int]),
     "opb_detect_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -274,6 +276,20 @@ class Engine(object):
                                               C.c_void_p(int(inject_paf)) if inject_paf else None,
                                               C.c_void_p(int(inject_heat)) if inject_heat else None,
                                               _ptr(headers), _ptr(persons), OPB_HOST))
+        return headers, persons
+
+    def postprocess_batch(self, paf_lo, heat_lo, map_h, map_w, img_len=None):
+        """Network outputs paf_lo [N,38,h8,w8] / heat_lo [N,19,h8,w8] float32 (host) -> (headers[N],
+        persons[N, max_persons]): upsample, peaks, connections, grouping (opb_postprocess_batch)."""
+        paf_lo = np.ascontiguousarray(paf_lo, np.float32)
+        heat_lo = np.ascontiguousarray(heat_lo, np.float32)
+        n, _, h8, w8 = paf_lo.shape
+        assert paf_lo.shape[1] == 38 and heat_lo.shape == (n, 19, h8, w8)
+        headers = np.empty(n, HEADER_DTYPE)
+        persons = np.empty((n, self.max_persons), PERSON_DTYPE)
+        self._check(self.lib.opb_postprocess_batch(self.ctx, _ptr(paf_lo), _ptr(heat_lo), OPB_HOST, n, h8, w8, map_h, map_w,
+                                                   float(map_w if img_len is None else img_len), _ptr(headers),
+                                                   _ptr(persons), OPB_HOST))
         return headers, persons
 
     def resize_linear_u8(self, imgs, out_h, out_w):

@@ -112,6 +112,9 @@ struct PostWs {           // post-process workspace for (N, map_h, map_w)
   PersonOut* persons = nullptr;
   const float* last_paf_lo = nullptr;   // low-res maps the last opb_detect_batch upsampled (network or injected)
   const float* last_heat_lo = nullptr;
+  int last_h8 = 0, last_w8 = 0;         // their size
+  float* lo_stage = nullptr;            // opb_postprocess_batch: device copy of host low-res maps [N][57][h8][w8]
+  size_t lo_cap = 0;                    // floats
   double last_img_len = 0;
   std::vector<void*> allocs;
 };
@@ -184,6 +187,9 @@ struct opb_ctx {
   uint64_t cache_epoch = 0;        // bumped whenever cached chains / workspaces / weights are freed (invalidates graphs)
   int two_streams = 1;             // OPB_TWO_STREAMS=0: both streaming slots share `stream` and one set of buffers
   int use_graphs = 1;              // OPB_GRAPH=0: streaming mode launches kernel by kernel
+  // Experimental (default off until measured on a B200; bit-exactness is covered by tests/test_emu_postprocess.py):
+  int fused_peaks = 0;             // OPB_FUSED_PEAKS=1: the peak kernel interpolates its tiles from the low-res heat maps
+  int paf_lowres = 0;              // OPB_PAF_LOWRES=1: PAF line integrals sample the low-res PAFs on demand
   int conn_cap = kAssignMaxType;
   bool profile = false;                       // OPB_PROFILE=1: cudaEvent after every launch of a batch
   std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -947,8 +953,11 @@ int launch_upsample(opb_ctx* ctx, const float* in, int planes, int h, int w, flo
   return OPB_OK;
 }
 
-// heat: [n][c_total][H][W]; fills ws->peaks / idx_list / type_start / peak_counts
-int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total, int H, int W) {
+// heat: [n][c_total][H][W]; fills ws->peaks / idx_list / type_start / peak_counts.
+// h_lo > 0: `heat` is the network-resolution map [n][c_total][h_lo][w_lo] and the peak kernel interpolates its tiles
+// from it (smooth_nms_lowres_kernel): the same peaks as upsampling to (H, W) first, without the full-resolution map.
+int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total, int H, int W, int h_lo = 0,
+                 int w_lo = 0) {
   const opb_params& p = ctx->prm;
   OPB_CUDA(ctx, cudaMemsetAsync(ws->peak_counts, 0, sizeof(int) * n, ctx->stream));
   OPB_CUDA(ctx, cudaMemsetAsync(ws->status, 0, sizeof(int) * n, ctx->stream));
@@ -962,6 +971,23 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
   }
   dim3 grid((W + PK_TX - 1) / PK_TX, (H + PK_TY - 1) / PK_TY, n * c_use);
   if (grid.z > 65535) OPB_FAIL(ctx, OPB_ERR_ARG, "batch too large for the peaks grid");
+  if (h_lo > 0) {
+    static bool attr3 = false;
+    if (!attr3) {
+      OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_lowres_kernel<PK_R_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_lowres_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr3 = true;
+    }
+    if (h_lo < 2 || w_lo < 2) OPB_FAIL(ctx, OPB_ERR_ARG, "low-resolution maps need at least 2 x 2 samples");
+    if (ctx->taps.radius == PK_R_FAST)
+      smooth_nms_lowres_kernel<PK_R_FAST><<<grid, PK_THREADS, smem, ctx->stream>>>(
+          heat, c_total, c_use, h_lo, w_lo, H, W, ctx->taps, static_cast<float>(p.heatmap_peak_thresh), ws->keys,
+          ws->peak_counts, p.max_peaks);
+    else
+      smooth_nms_lowres_kernel<0><<<grid, PK_THREADS, smem, ctx->stream>>>(
+          heat, c_total, c_use, h_lo, w_lo, H, W, ctx->taps, static_cast<float>(p.heatmap_peak_thresh), ws->keys,
+          ws->peak_counts, p.max_peaks);
+  } else {
   cell_max_kernel<<<grid, 256, 0, ctx->stream>>>(heat, c_total, c_use, H, W, ws->tile_max, (H + PK_CELL - 1) / PK_CELL,
                                                  (W + PK_CELL - 1) / PK_CELL);
   ctx->launches++;
@@ -974,6 +1000,7 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
     smooth_nms_kernel<0><<<grid, PK_THREADS, smem, ctx->stream>>>(heat, c_total, c_use, H, W, ctx->taps,
                                                            static_cast<float>(p.heatmap_peak_thresh), ws->keys,
                                                            ws->peak_counts, p.max_peaks, ws->tile_max);
+  }
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   prof_mark(ctx, "smooth_nms");
@@ -991,13 +1018,23 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
   return OPB_OK;
 }
 
-int launch_connections(opb_ctx* ctx, PostWs* ws, const float* pafs, int n, int H, int W, double img_len) {
+// h_lo > 0: `pafs` is the network-resolution map [n][38][h_lo][w_lo]; the line integrals sample it on demand
+// (paf_candidates_lowres_kernel) at the positions of the (H, W) map the reference upsamples to.
+int launch_connections(opb_ctx* ctx, PostWs* ws, const float* pafs, int n, int H, int W, double img_len, int h_lo = 0,
+                       int w_lo = 0) {
   const opb_params& p = ctx->prm;
   OPB_CUDA(ctx, cudaMemsetAsync(ws->cand_counts, 0, sizeof(int) * n * 19, ctx->stream));
   dim3 g1(8, 19, n);
+  if (h_lo > 0) {
+    if (h_lo < 2 || w_lo < 2) OPB_FAIL(ctx, OPB_ERR_ARG, "low-resolution maps need at least 2 x 2 samples");
+    paf_candidates_lowres_kernel<<<g1, 128, 0, ctx->stream>>>(pafs, h_lo, w_lo, H, W, ws->peaks, ws->idx_list,
+                                                              ws->type_start, p.max_peaks, 18, ctx->pc, img_len,
+                                                              ws->cands, ws->cand_counts, p.max_candidates);
+  } else {
   paf_candidates_kernel<<<g1, 128, 0, ctx->stream>>>(pafs, H, W, ws->peaks, ws->idx_list, ws->type_start,
                                                      p.max_peaks, 18, ctx->pc, img_len, ws->cands, ws->cand_counts,
                                                      p.max_candidates);
+  }
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   prof_mark(ctx, "paf_candidates");
@@ -1126,6 +1163,8 @@ int opb_create(opb_ctx** out, int device, const opb_params* params) {
   ctx->profile = getenv("OPB_PROFILE") && atoi(getenv("OPB_PROFILE")) > 0;
   if (const char* g = getenv("OPB_GRAPH")) ctx->use_graphs = atoi(g);
   if (const char* g = getenv("OPB_TWO_STREAMS")) ctx->two_streams = atoi(g);
+  if (const char* g = getenv("OPB_FUSED_PEAKS")) ctx->fused_peaks = atoi(g);
+  if (const char* g = getenv("OPB_PAF_LOWRES")) ctx->paf_lowres = atoi(g);
   *out = ctx;
   return OPB_OK;
 }
@@ -1530,6 +1569,34 @@ int opb_group(opb_ctx* ctx, const double* conns, const int* conn_counts, const d
   return OPB_OK;
 }
 
+// upsample + peaks + connections + grouping of n images' network outputs (device pointers, [n][38|19][h8][w8]):
+// pose_detector.py:501-512.  OPB_PAF_LOWRES / OPB_FUSED_PEAKS skip the materialised full-resolution PAFs / heat maps.
+static int run_postprocess(opb_ctx* ctx, PostWs* ws, int n, int h8, int w8, int map_h, int map_w, double img_len,
+                           const float* paf_lo, const float* heat_lo) {
+  int rc;
+  ws->last_paf_lo = paf_lo; ws->last_heat_lo = heat_lo; ws->last_img_len = img_len;
+  ws->last_h8 = h8; ws->last_w8 = w8;
+  if (!ctx->paf_lowres) {
+    if ((rc = launch_upsample(ctx, paf_lo, n * 38, h8, w8, ws->pafs, map_h, map_w))) return rc;
+    prof_mark(ctx, "upsample_paf");
+  }
+  if (ctx->fused_peaks) {
+    if ((rc = launch_peaks(ctx, ws, heat_lo, n, 19, map_h, map_w, h8, w8))) return rc;
+  } else {
+    if ((rc = launch_upsample(ctx, heat_lo, n * 19, h8, w8, ws->heat, map_h, map_w))) return rc;
+    prof_mark(ctx, "upsample_heat");
+    if ((rc = launch_peaks(ctx, ws, ws->heat, n, 19, map_h, map_w))) return rc;
+  }
+  prof_mark(ctx, "peaks");
+  if (ctx->paf_lowres) rc = launch_connections(ctx, ws, paf_lo, n, map_h, map_w, img_len, h8, w8);
+  else rc = launch_connections(ctx, ws, ws->pafs, n, map_h, map_w, img_len);
+  if (rc) return rc;
+  prof_mark(ctx, "connections");
+  if ((rc = launch_group(ctx, ws, n, true))) return rc;
+  prof_mark(ctx, "group");
+  return OPB_OK;
+}
+
 // conv chain + upsample + peaks + connections + grouping for the frames ch->img_u8_src points at (all on ctx->stream,
 // no host synchronisation): the device-resident body of PoseDetector.__call__ (pose_detector.py:495-512)
 static int run_pipeline(opb_ctx* ctx, Chain* ch, PostWs* ws, int n, int h, int w, int map_h, int map_w, double img_len,
@@ -1537,21 +1604,8 @@ static int run_pipeline(opb_ctx* ctx, Chain* ch, PostWs* ws, int n, int h, int w
   int rc;
   if (ctx->kp_out) OPB_FAIL(ctx, OPB_ERR_STATE, "this context holds a face / hand net: use opb_keypoints_detect");
   if ((rc = run_chain(ctx, ch, true))) return rc;
-  const int h8 = h / 8, w8 = w / 8;
-  const float* paf_lo = inject_paf ? inject_paf : ch->paf_lo;
-  const float* heat_lo = inject_heat ? inject_heat : ch->heat_lo;
-  ws->last_paf_lo = paf_lo; ws->last_heat_lo = heat_lo; ws->last_img_len = img_len;
-  if ((rc = launch_upsample(ctx, paf_lo, n * 38, h8, w8, ws->pafs, map_h, map_w))) return rc;
-  prof_mark(ctx, "upsample_paf");
-  if ((rc = launch_upsample(ctx, heat_lo, n * 19, h8, w8, ws->heat, map_h, map_w))) return rc;
-  prof_mark(ctx, "upsample_heat");
-  if ((rc = launch_peaks(ctx, ws, ws->heat, n, 19, map_h, map_w))) return rc;
-  prof_mark(ctx, "peaks");
-  if ((rc = launch_connections(ctx, ws, ws->pafs, n, map_h, map_w, img_len))) return rc;
-  prof_mark(ctx, "connections");
-  if ((rc = launch_group(ctx, ws, n, true))) return rc;
-  prof_mark(ctx, "group");
-  return OPB_OK;
+  return run_postprocess(ctx, ws, n, h / 8, w / 8, map_h, map_w, img_len, inject_paf ? inject_paf : ch->paf_lo,
+                         inject_heat ? inject_heat : ch->heat_lo);
 }
 
 int opb_detect_batch(opb_ctx* ctx, const uint8_t* imgs, int imgs_loc, int n, int h, int w, int map_h, int map_w,
@@ -1578,6 +1632,33 @@ int opb_detect_batch(opb_ctx* ctx, const uint8_t* imgs, int imgs_loc, int n, int
   prof_mark(ctx, "copy_out");
   OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   prof_report(ctx);
+  return OPB_OK;
+}
+
+int opb_postprocess_batch(opb_ctx* ctx, const float* paf_lo, const float* heat_lo, int maps_loc, int n, int h8, int w8,
+                          int map_h, int map_w, double img_len, opb_image_header* headers_out, opb_person* persons_out,
+                          int out_loc) {
+  if (!ctx || !paf_lo || !heat_lo || !headers_out || !persons_out || n <= 0 || h8 < 2 || w8 < 2 || map_h <= 0 || map_w <= 0)
+    return OPB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  PostWs* ws = nullptr;
+  int rc;
+  if ((rc = get_post(ctx, n, map_h, map_w, &ws))) return rc;
+  const size_t plane = static_cast<size_t>(h8) * w8;
+  if (maps_loc == OPB_HOST) {
+    if (ws->lo_cap < static_cast<size_t>(n) * 57 * plane) {   // grows only; earlier blocks stay owned by the workspace
+      if ((rc = dev_alloc(ctx, &ws->lo_stage, static_cast<size_t>(n) * 57 * plane, ws->allocs, false))) return rc;
+      ws->lo_cap = static_cast<size_t>(n) * 57 * plane;
+    }
+    if ((rc = copy_in(ctx, ws->lo_stage, paf_lo, sizeof(float) * n * 38 * plane, OPB_HOST))) return rc;
+    if ((rc = copy_in(ctx, ws->lo_stage + n * 38 * plane, heat_lo, sizeof(float) * n * 19 * plane, OPB_HOST))) return rc;
+    paf_lo = ws->lo_stage;
+    heat_lo = ws->lo_stage + n * 38 * plane;
+  }
+  if ((rc = run_postprocess(ctx, ws, n, h8, w8, map_h, map_w, img_len, paf_lo, heat_lo))) return rc;
+  if ((rc = copy_out(ctx, headers_out, ws->headers, sizeof(ImageHeader) * n, out_loc))) return rc;
+  if ((rc = copy_out(ctx, persons_out, ws->persons, sizeof(PersonOut) * n * ctx->prm.max_persons, out_loc))) return rc;
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return OPB_OK;
 }
 
@@ -2030,15 +2111,23 @@ int opb_time_stage(opb_ctx* ctx, const char* stage, int reps, float* ms) {
   auto run_once = [&]() -> int {
     if (s == "upsample_paf" || s == "upsample_heat" || s == "peaks" || s == "paf_integral" || s == "limb_assign" ||
         s == "group") {
-      if (!ws || !ch) { ctx->err = "no cached pipeline to time"; return OPB_ERR_STATE; }
-      const int n = ws->N, h8 = ch->H / 8, w8 = ch->W / 8;
+      if (!ws || (!ch && !ws->last_paf_lo)) { ctx->err = "no cached pipeline to time"; return OPB_ERR_STATE; }
+      const int n = ws->N, h8 = ws->last_h8 ? ws->last_h8 : ch->H / 8, w8 = ws->last_w8 ? ws->last_w8 : ch->W / 8;
       const float* plo = ws->last_paf_lo ? ws->last_paf_lo : ch->paf_lo;     // same maps as the last batch
       const float* hlo = ws->last_heat_lo ? ws->last_heat_lo : ch->heat_lo;
       const double ilen = ws->last_img_len > 0 ? ws->last_img_len : ws->W;
       if (s == "upsample_paf") { ++n_launch; return launch_upsample(ctx, plo, n * 38, h8, w8, ws->pafs, ws->H, ws->W); }
       if (s == "upsample_heat") { ++n_launch; return launch_upsample(ctx, hlo, n * 19, h8, w8, ws->heat, ws->H, ws->W); }
-      if (s == "peaks") { n_launch += 3; return launch_peaks(ctx, ws, ws->heat, n, 19, ws->H, ws->W); }
-      if (s == "paf_integral") { n_launch += 2; return launch_connections(ctx, ws, ws->pafs, n, ws->H, ws->W, ilen); }
+      if (s == "peaks") {
+        if (ctx->fused_peaks) { n_launch += 2; return launch_peaks(ctx, ws, hlo, n, 19, ws->H, ws->W, h8, w8); }
+        n_launch += 3;
+        return launch_peaks(ctx, ws, ws->heat, n, 19, ws->H, ws->W);
+      }
+      if (s == "paf_integral") {
+        n_launch += 2;
+        if (ctx->paf_lowres) return launch_connections(ctx, ws, plo, n, ws->H, ws->W, ilen, h8, w8);
+        return launch_connections(ctx, ws, ws->pafs, n, ws->H, ws->W, ilen);
+      }
       if (s == "limb_assign") {
         ++n_launch;
         dim3 g2(19, n);

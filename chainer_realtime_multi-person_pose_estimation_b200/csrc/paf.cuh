@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "peaks.cuh"
+#include "upsample.cuh"
 
 namespace opb {
 
@@ -37,26 +38,36 @@ struct PafConsts {
 
 constexpr int kAssignMaxType = 1024;  // peaks of one joint type per image handled by limb_assign
 
-// grid (chunks, 19, n_img); paf [n_img][38][H][W] f32
-__global__ void __launch_bounds__(128)
-paf_candidates_kernel(const float* __restrict__ paf, int H, int W, const PeakD* __restrict__ peaks,
-                      const int* __restrict__ idx_list, const int* __restrict__ type_start, int peaks_cap,
-                      int n_types, PafConsts K, double img_len, Candidate* __restrict__ cands,
-                      int* __restrict__ cand_counts, int cand_cap) {
-  const int l = blockIdx.y, img = blockIdx.z;
-  const int ja = K.limbs[l][0], jb = K.limbs[l][1];
-  const int* ts = type_start + img * (n_types + 1);
-  const int a0 = ts[ja], nA = ts[ja + 1] - a0;
-  const int b0 = ts[jb], nB = ts[jb + 1] - b0;
-  const long long total = static_cast<long long>(nA) * nB;
-  if (total == 0) return;
-  const PeakD* pk = peaks + static_cast<size_t>(img) * peaks_cap;
-  const int* il = idx_list + static_cast<size_t>(img) * peaks_cap;
-  const float* p0 = paf + (static_cast<size_t>(img) * 38 + 2 * l) * H * W;
-  const float* p1 = p0 + static_cast<size_t>(H) * W;
-  Candidate* out = cands + (static_cast<size_t>(img) * 19 + l) * cand_cap;
-  int* cnt = cand_counts + img * 19 + l;
+// PAF samplers: (Y, X) at map resolution -> the two float32 components, promoted to float64.
+struct PafFull {   // full-resolution planes materialised by the upsample kernel (pose_detector.py:501)
+  const float* p0;
+  const float* p1;
+  int W;
+  __device__ __forceinline__ void operator()(int Y, int X, double& q0, double& q1) const {
+    const size_t o = static_cast<size_t>(Y) * W + X;
+    q0 = static_cast<double>(__ldg(p0 + o));
+    q1 = static_cast<double>(__ldg(p1 + o));
+  }
+};
+struct PafLow {    // low-resolution planes, sampled on demand with the upsample kernel's own arithmetic
+  const float* p0;
+  const float* p1;
+  int h, w, H, W;
+  double step_x, step_y;
+  __device__ __forceinline__ void operator()(int Y, int X, double& q0, double& q1) const {
+    const AcTap t = ac_tap(ac_axis_frac(X, w, W, step_x), ac_axis_frac(Y, h, H, step_y), w);
+    q0 = static_cast<double>(ac_sample(p0, w, t));
+    q1 = static_cast<double>(ac_sample(p1, w, t));
+  }
+};
 
+// scores the nA x nB pairs of one (limb, image) and appends the candidates that pass (:135-157)
+template <class Sampler>
+__device__ __forceinline__ void paf_candidates_body(const Sampler& smp, int H, int W, const PeakD* __restrict__ pk,
+                                                    const int* __restrict__ il, int a0, int nA, int b0, int nB,
+                                                    const PafConsts& K, double img_len, Candidate* __restrict__ out,
+                                                    int* __restrict__ cnt, int cand_cap) {
+  const long long total = static_cast<long long>(nA) * nB;
   for (long long pi = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pi < total;
        pi += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int a = static_cast<int>(pi / nB), b = static_cast<int>(pi - static_cast<long long>(a) * nB);
@@ -80,8 +91,8 @@ paf_candidates_kernel(const float* __restrict__ paf, int H, int W, const PeakD* 
       }
       // peaks lie inside the map, so the clamp never changes a valid input (memory safety only)
       const int Y = min(max(__double2int_rn(ys), 0), H - 1), X = min(max(__double2int_rn(xs), 0), W - 1);
-      const size_t o = static_cast<size_t>(Y) * W + X;
-      const double q0 = static_cast<double>(__ldg(p0 + o)), q1 = static_cast<double>(__ldg(p1 + o));
+      double q0, q1;
+      smp(Y, X, q0, q1);
       ip[i] = __fma_rn(q0, ux, __dmul_rn(q1, uy));
       nvalid += (ip[i] > K.inner_product_thresh) ? 1 : 0;
     }
@@ -105,6 +116,52 @@ paf_candidates_kernel(const float* __restrict__ paf, int H, int W, const PeakD* 
       }
     }
   }
+}
+
+// grid (chunks, 19, n_img); paf [n_img][38][H][W] f32
+__global__ void __launch_bounds__(128)
+paf_candidates_kernel(const float* __restrict__ paf, int H, int W, const PeakD* __restrict__ peaks,
+                      const int* __restrict__ idx_list, const int* __restrict__ type_start, int peaks_cap,
+                      int n_types, PafConsts K, double img_len, Candidate* __restrict__ cands,
+                      int* __restrict__ cand_counts, int cand_cap) {
+  const int l = blockIdx.y, img = blockIdx.z;
+  const int ja = K.limbs[l][0], jb = K.limbs[l][1];
+  const int* ts = type_start + img * (n_types + 1);
+  const int a0 = ts[ja], nA = ts[ja + 1] - a0;
+  const int b0 = ts[jb], nB = ts[jb + 1] - b0;
+  if (static_cast<long long>(nA) * nB == 0) return;
+  PafFull smp;
+  smp.p0 = paf + (static_cast<size_t>(img) * 38 + 2 * l) * H * W;
+  smp.p1 = smp.p0 + static_cast<size_t>(H) * W;
+  smp.W = W;
+  paf_candidates_body(smp, H, W, peaks + static_cast<size_t>(img) * peaks_cap, idx_list + static_cast<size_t>(img) * peaks_cap,
+                      a0, nA, b0, nB, K, img_len, cands + (static_cast<size_t>(img) * 19 + l) * cand_cap,
+                      cand_counts + img * 19 + l, cand_cap);
+}
+
+// The same with the PAFs still at network resolution: paf_lo [n_img][38][h][w] f32, (H, W) = the map size the
+// reference upsamples to (pose_detector.py:501).  Every sample is the value F.resize_images would have produced
+// at that position, so the 38 full-resolution planes (28 MB per 320x576 image) are never written or read.
+__global__ void __launch_bounds__(128)
+paf_candidates_lowres_kernel(const float* __restrict__ paf_lo, int h, int w, int H, int W,
+                             const PeakD* __restrict__ peaks, const int* __restrict__ idx_list,
+                             const int* __restrict__ type_start, int peaks_cap, int n_types, PafConsts K, double img_len,
+                             Candidate* __restrict__ cands, int* __restrict__ cand_counts, int cand_cap) {
+  const int l = blockIdx.y, img = blockIdx.z;
+  const int ja = K.limbs[l][0], jb = K.limbs[l][1];
+  const int* ts = type_start + img * (n_types + 1);
+  const int a0 = ts[ja], nA = ts[ja + 1] - a0;
+  const int b0 = ts[jb], nB = ts[jb + 1] - b0;
+  if (static_cast<long long>(nA) * nB == 0) return;
+  PafLow smp;
+  smp.p0 = paf_lo + (static_cast<size_t>(img) * 38 + 2 * l) * h * w;
+  smp.p1 = smp.p0 + static_cast<size_t>(h) * w;
+  smp.h = h; smp.w = w; smp.H = H; smp.W = W;
+  smp.step_x = ac_step(w, W);
+  smp.step_y = ac_step(h, H);
+  paf_candidates_body(smp, H, W, peaks + static_cast<size_t>(img) * peaks_cap, idx_list + static_cast<size_t>(img) * peaks_cap,
+                      a0, nA, b0, nB, K, img_len, cands + (static_cast<size_t>(img) * 19 + l) * cand_cap,
+                      cand_counts + img * 19 + l, cand_cap);
 }
 
 // One block per (limb, image).  Exact greedy matching by descending (score, then generation

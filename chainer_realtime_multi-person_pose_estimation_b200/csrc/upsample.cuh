@@ -172,6 +172,59 @@ upsample_bilinear_ac_v4_kernel(const float* __restrict__ in, int planes, int h, 
   }
 }
 
+// ---- point sampling of the align-corners bilinear map ------------------------------------------
+// The value upsample_bilinear_ac_kernel writes at output position (Y, X), computed on demand from the
+// low-resolution plane with the same operations in the same order (bit-identical): consumers that
+// touch only a few full-resolution positions (PAF line integrals) or that stage a tile anyway (the
+// peak kernel) can then skip the materialised full-resolution map and its HBM round trip.
+struct AcAxis {
+  int i0;          // left / upper source index
+  double f0, f1;   // u - i0, (i0 + 1) - u
+};
+
+__device__ __forceinline__ double ac_step(int n_in, int n_out) {
+  return (n_out > 1) ? __ddiv_rn(static_cast<double>(n_in - 1), static_cast<double>(n_out - 1)) : 0.0;
+}
+
+// ac_axis with the (loop-invariant) linspace step hoisted
+__device__ __forceinline__ AcAxis ac_axis_frac(int i, int n_in, int n_out, double step) {
+  double u;
+  if (n_out == 1) u = 0.0;
+  else if (i == n_out - 1) u = static_cast<double>(n_in - 1);
+  else u = __dmul_rn(static_cast<double>(i), step);
+  int k = static_cast<int>(floor(u));
+  k = max(0, min(k, n_in - 2));
+  AcAxis a;
+  a.i0 = k;
+  a.f1 = __dsub_rn(static_cast<double>(k + 1), u);
+  a.f0 = __dsub_rn(u, static_cast<double>(k));
+  return a;
+}
+
+struct AcTap {
+  int o00;                 // offset of the upper-left source sample in the plane
+  float w1, w2, w3, w4;    // weights of x00, x01, x10, x11
+};
+
+__device__ __forceinline__ AcTap ac_tap(const AcAxis& ax, const AcAxis& ay, int w) {
+  AcTap t;
+  t.o00 = ay.i0 * w + ax.i0;
+  t.w1 = static_cast<float>(__dmul_rn(ax.f1, ay.f1));
+  t.w2 = static_cast<float>(__dmul_rn(ax.f0, ay.f1));
+  t.w3 = static_cast<float>(__dmul_rn(ax.f1, ay.f0));
+  t.w4 = static_cast<float>(__dmul_rn(ax.f0, ay.f0));
+  return t;
+}
+
+__device__ __forceinline__ float ac_sample(const float* __restrict__ plane, int w, const AcTap& t) {
+  const float* q = plane + t.o00;
+  float r = __fmul_rn(t.w1, __ldg(q));
+  r = __fadd_rn(r, __fmul_rn(t.w2, __ldg(q + 1)));
+  r = __fadd_rn(r, __fmul_rn(t.w3, __ldg(q + w)));
+  r = __fadd_rn(r, __fmul_rn(t.w4, __ldg(q + w + 1)));
+  return r;
+}
+
 // ---- cv2 INTER_CUBIC for float32 (A = -0.75), separable, replicate border ------------------
 __device__ __forceinline__ void cubic_taps(float t, float (&c)[4]) {
   const float A = -0.75f;

@@ -158,6 +158,18 @@ int opb_detect_batch(opb_ctx* ctx, const uint8_t* imgs, int imgs_loc, int n, int
                      int map_w, double img_len, const float* inject_paf, const float* inject_heat,
                      opb_image_header* headers_out, opb_person* persons_out, int out_loc);
 
+/* -- the post-process half of PoseDetector.__call__ on its own (pose_detector.py:501-512): network outputs
+ *    paf_lo [N,38,h8,w8] / heat_lo [N,19,h8,w8] float32 (host or device per maps_loc) -> F.resize_images to
+ *    (map_h, map_w) -> peaks -> connections -> grouping, records as in opb_detect_batch.  For callers that run
+ *    the network elsewhere, and the entry the no-GPU emulation tests drive (the conv chain cannot be emulated).
+ *    With OPB_PAF_LOWRES=1 / OPB_FUSED_PEAKS=1 in the environment at opb_create (experimental, also honoured by
+ *    opb_detect_batch / opb_detect_image / opb_stream_submit) the PAF line integrals / the peak kernel interpolate
+ *    from the low-resolution maps on demand instead of reading materialised full-resolution maps: same results
+ *    bit for bit, without the 42 MB per 320x576 image of full-resolution maps going through HBM.            */
+int opb_postprocess_batch(opb_ctx* ctx, const float* paf_lo, const float* heat_lo, int maps_loc, int n, int h8,
+                          int w8, int map_h, int map_w, double img_len, opb_image_header* headers_out,
+                          opb_person* persons_out, int out_loc);
+
 /* -- device-side ingest: replaces cv2.resize(orig_img, (input_w, input_h)) (default INTER_LINEAR on
  *    uint8 BGR, pose_detector.py:493), bit-exact with OpenCV's 8-bit fixed-point path.
  *    src [n,h0,w0,3] -> dst [n,h,w,3] uint8.                                                     */

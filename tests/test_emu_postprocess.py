@@ -34,6 +34,7 @@ from oracle import restate as R
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda_emu"))
 import build_emu  # noqa: E402
 import test_gpu_postprocess as G  # noqa: E402  (plain functions; the gpu mark belongs to that module only)
+from postprocess_batch_cases import check_batch_against_oracle, run_batch_cases  # noqa: E402
 
 
 def _load(contract):
@@ -186,3 +187,14 @@ def test_keypoints_exact_ties_and_threshold(engine):
             assert (a is None) == (b is None), (a, b)
             if a is not None:
                 assert (a[0], a[1]) == (b[0], b[1]) and np.float32(a[2]) == np.float32(b[2]), (a, b)
+
+
+@pytest.mark.parametrize("fused_peaks,paf_lowres", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_postprocess_batch_from_network_resolution_maps(emu_native, monkeypatch, fused_peaks, paf_lowres):
+    """opb_postprocess_batch = pose_detector.py:501-512 for a batch; with OPB_FUSED_PEAKS / OPB_PAF_LOWRES the peak
+    kernel / the PAF line integrals interpolate from the low-resolution maps on demand -- every variant must give the
+    oracle's peaks, connections, subsets and person records bit for bit."""
+    monkeypatch.setenv("OPB_FUSED_PEAKS", str(fused_peaks))
+    monkeypatch.setenv("OPB_PAF_LOWRES", str(paf_lowres))
+    eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params(max_peaks=4096, max_candidates=65536, max_persons=128))
+    run_batch_cases(eng)

@@ -1,0 +1,33 @@
+"""`-m gpu`: opb_postprocess_batch (the post-process half of PoseDetector.__call__, pose_detector.py:501-512, for
+a batch of network outputs) against the oracle, bit for bit -- through the C ABI on a B200.
+
+The OPB_FUSED_PEAKS / OPB_PAF_LOWRES variants (peak kernel / PAF line integrals interpolating from the
+low-resolution maps on demand) are off by default until they have been measured; their bit-exactness is covered
+without a GPU by tests/test_emu_postprocess.py, and on a B200 by running this file with OPB_TEST_EXPERIMENTAL=1."""
+import os
+
+import pytest
+
+from conftest import pkg
+from postprocess_batch_cases import run_batch_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine():
+    native = pkg("_native")
+    return native.Engine(0, pkg("pose_detector").make_opb_params(max_peaks=4096, max_candidates=65536, max_persons=128))
+
+
+def test_postprocess_batch_default_path(monkeypatch):
+    monkeypatch.delenv("OPB_FUSED_PEAKS", raising=False)
+    monkeypatch.delenv("OPB_PAF_LOWRES", raising=False)
+    run_batch_cases(_engine())
+
+
+@pytest.mark.skipif(os.environ.get("OPB_TEST_EXPERIMENTAL", "0") != "1", reason="experimental low-res variants: set OPB_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("fused_peaks,paf_lowres", [(1, 0), (0, 1), (1, 1)])
+def test_postprocess_batch_lowres_variants(monkeypatch, fused_peaks, paf_lowres):
+    monkeypatch.setenv("OPB_FUSED_PEAKS", str(fused_peaks))
+    monkeypatch.setenv("OPB_PAF_LOWRES", str(paf_lowres))
+    run_batch_cases(_engine())
