@@ -367,6 +367,22 @@ def run_ours(args):
         extra["keypoint_nets"] = kp
     except Exception as e:
         extra["keypoint_nets"] = {"error": str(e)[:200]}
+    # The precision that meets north_star's 1e-3 map tolerance (split-fp16 "parity": 1.9e-5 vs the fp32 oracle; the
+    # headline runs fp16 "fast" as BASELINE.json configs[1] names it: 2.8e-3).  Measured in a child process so that
+    # nothing it does can cost the headline line; same workload, synchronous device-resident entry.
+    if args.precision == "fast" and world == 1 and not args.no_parity_extra:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--precision", "parity", "--steps", "3", "--warmup", "3",
+                                "--no-stage-timing", "--no-cpu-baseline", "--batch", str(B), "--max-persons", str(args.max_persons)],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=150)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            d = json.loads(line[-1]) if line else None
+            extra["parity_precision"] = ({"value": d["value"], "unit": "frames/s", "ms_per_step": d["ms_per_step"],
+                                          "e2e": d["e2e"]["value"], "dtype": "split-f16 (hi+lo), 3 MMAs per K step, fp32 two-level accumulation",
+                                          "note": "meets the 1e-3 map tolerance (1.9e-5); child process, 3 steps"}
+                                         if d else {"error": (r.stderr or "no output")[-200:]})
+        except Exception as e:
+            extra["parity_precision"] = {"error": str(e)[:200]}
     # CPU baseline: the oracle port on this box's host cores, bounded sample
     cpu = None
     if not args.no_cpu_baseline and world == 1:            # rank 0 at N = 1 only
@@ -423,6 +439,7 @@ def main():
     ap.add_argument("--max-persons", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the per-stage re-launches (clean ncu launch lists)")
+    ap.add_argument("--no-parity-extra", action="store_true", help="skip the parity-precision throughput extra (child process)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
