@@ -6,6 +6,11 @@ The package never loads this library: only tests/test_emu_*.py dlopen it, to run
 plain-CUDA kernels and the C-ABI host orchestration on a box without a GPU and compare them
 bit-for-bit with the oracle.  Tensor-core kernels (inline PTX) trap under emulation.
 
+A memcheck analogue without a GPU: every "device" allocation is a host heap block, so an AddressSanitizer build of
+the emulated library reports out-of-bounds and use-after-free accesses of kernels and host code alike:
+    OPB_EMU_SANITIZE=address LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
+        ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_emu_postprocess.py -q
+
 Source rewriting (textual, into _build/src; the originals are not touched):
   kernel<<<grid, block, smem, stream>>>(args)  ->  emu::Launcher(grid, block, smem, stream).run(kernel, args)
   extern __shared__ T name[];                  ->  T* name = reinterpret_cast<T*>(emu::g_dyn_smem);
@@ -65,8 +70,11 @@ def rewrite(text):
     return text
 
 
+SANITIZE = os.environ.get("OPB_EMU_SANITIZE", "")   # "address": -fsanitize=address (run pytest under LD_PRELOAD=libasan.so)
+
+
 def lib_path(contract):
-    return os.path.join(BUILD, "libopb_emu_%s.so" % ("fma" if contract else "nofma"))
+    return os.path.join(BUILD, "libopb_emu_%s%s.so" % ("fma" if contract else "nofma", "_" + SANITIZE if SANITIZE else ""))
 
 
 def build(contract=False, force=False):
@@ -86,7 +94,8 @@ def build(contract=False, force=False):
         with open(os.path.join(src_dir, f.replace(".cu", ".cpp") if f.endswith(".cu") else f), "w") as fh:
             fh.write(text)
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-w",
-           "-ffp-contract=fast" if contract else "-ffp-contract=off"] + (["-mfma"] if contract else []) + [
+           "-ffp-contract=fast" if contract else "-ffp-contract=off"] + (["-mfma"] if contract else []) + (
+           ["-fsanitize=" + SANITIZE, "-fno-omit-frame-pointer"] if SANITIZE else []) + [
            "-I", CUDA_INC, "-I", os.path.join(ROOT, "include"), "-I", HERE, "-include", os.path.join(HERE, "cuda_emu.h"),
            os.path.join(src_dir, "opb_api.cpp"), os.path.join(HERE, "emu_runtime.cpp"), "-o", lib]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

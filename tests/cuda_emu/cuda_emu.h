@@ -69,10 +69,12 @@ inline const std::function<void()>* g_body = nullptr;
 inline int g_red_or = 0, g_red_and = 0, g_red_cnt = 0;
 inline uint64_t g_warp_buf[MAX_THREADS / 32][32];
 inline int g_warp_pred[MAX_THREADS / 32][32];
-alignas(1024) inline unsigned char g_dyn_smem[232 * 1024];
+inline unsigned char* g_dyn_smem = nullptr;   // exactly the launch's dynamic shared memory (a heap block: ASan sees overruns)
+constexpr size_t MAX_DYN_SMEM = 232448;
 inline uint3 g_tid, g_bid;
 inline dim3 g_bdim, g_gdim;
 inline long long g_launches = 0;
+inline bool g_reverse = false;
 
 #if defined(__x86_64__)
 #define EMU_FAST_SWITCH 1
@@ -135,7 +137,10 @@ inline void run_block(int nthreads, const std::function<void()>& body) {
   }
   for (;;) {
     bool ran = false;
-    for (int i = 0; i < nthreads; ++i) {
+    for (int k = 0; k < nthreads; ++k) {
+      // OPB_EMU_ORDER=reverse: highest thread first.  Code that is correct under independent thread scheduling
+      // gives the same result for any order; lane-0-first and lane-31-first bracket the usual hazards.
+      const int i = g_reverse ? nthreads - 1 - k : k;
       if (g_fibers[i].state != READY) continue;
       g_cur = i;
       g_tid = g_fibers[i].tid;
@@ -203,11 +208,15 @@ struct Launcher {
   Launcher(dim3 grid, dim3 block, size_t smem_bytes = 0, cudaStream_t = nullptr) : g(grid), b(block), smem(smem_bytes) {}
   template <class... KA, class... A>
   void run(void (*k)(KA...), A&&... a) {
-    if (smem > sizeof(g_dyn_smem)) { fprintf(stderr, "emu: %zu B of dynamic shared memory\n", smem); abort(); }
+    if (smem > MAX_DYN_SMEM) { fprintf(stderr, "emu: %zu B of dynamic shared memory\n", smem); abort(); }
+    void* dyn = nullptr;
+    if (posix_memalign(&dyn, 1024, smem ? smem : 1)) abort();
+    g_dyn_smem = static_cast<unsigned char*>(dyn);
     std::tuple<std::decay_t<KA>...> args(std::forward<A>(a)...);
     const std::function<void()> body = [&] { std::apply(k, args); };
     g_bdim = b; g_gdim = g;
     ++g_launches;
+    { const char* o = getenv("OPB_EMU_ORDER"); g_reverse = o && o[0] == 'r'; }
     const int nthreads = static_cast<int>(b.x * b.y * b.z);
     for (unsigned z = 0; z < g.z; ++z)
       for (unsigned y = 0; y < g.y; ++y)
@@ -215,6 +224,8 @@ struct Launcher {
           g_bid.x = x; g_bid.y = y; g_bid.z = z;
           run_block(nthreads, body);
         }
+    g_dyn_smem = nullptr;
+    free(dyn);
   }
 };
 

@@ -198,3 +198,15 @@ def test_postprocess_batch_from_network_resolution_maps(emu_native, monkeypatch,
     monkeypatch.setenv("OPB_PAF_LOWRES", str(paf_lowres))
     eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params(max_peaks=4096, max_candidates=65536, max_persons=128))
     run_batch_cases(eng)
+
+
+def test_results_do_not_depend_on_the_order_threads_run_in(emu_native, monkeypatch):
+    """The emulator normally runs thread 0 first; OPB_EMU_ORDER=reverse runs the highest thread first.  Code that is
+    correct under independent thread scheduling gives the same bits either way (and the convergence check must not
+    fire): the whole post-process, default and low-resolution variants."""
+    monkeypatch.setenv("OPB_EMU_ORDER", "reverse")
+    for knobs in ((0, 0), (1, 1)):
+        monkeypatch.setenv("OPB_FUSED_PEAKS", str(knobs[0]))
+        monkeypatch.setenv("OPB_PAF_LOWRES", str(knobs[1]))
+        eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params(max_peaks=4096, max_candidates=65536, max_persons=128))
+        run_batch_cases(eng)
