@@ -11,6 +11,13 @@ the emulated library reports out-of-bounds and use-after-free accesses of kernel
     OPB_EMU_SANITIZE=address LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
         ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_emu_postprocess.py -q
 
+A racecheck analogue: a ThreadSanitizer build in which every CUDA thread is a TSan fiber and barriers / warp
+primitives are the only happens-before edges (see cuda_emu.h); unsynchronised accesses of two CUDA threads to the
+same shared or global location are reported with both source lines (log files appear only if something is found):
+    OPB_EMU_SANITIZE=thread LD_PRELOAD=$(gcc -print-file-name=libtsan.so) OMP_NUM_THREADS=1 \
+        TSAN_OPTIONS="report_signal_unsafe=0 halt_on_error=0 log_path=/tmp/opb_tsan" \
+        python -m pytest tests/test_emu_postprocess.py -q -k nofma
+
 Source rewriting (textual, into _build/src; the originals are not touched):
   kernel<<<grid, block, smem, stream>>>(args)  ->  emu::Launcher(grid, block, smem, stream).run(kernel, args)
   extern __shared__ T name[];                  ->  T* name = reinterpret_cast<T*>(emu::g_dyn_smem);
@@ -93,7 +100,7 @@ def build(contract=False, force=False):
             text = rewrite(fh.read())
         with open(os.path.join(src_dir, f.replace(".cu", ".cpp") if f.endswith(".cu") else f), "w") as fh:
             fh.write(text)
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-w",
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-w", "-Wl,-Bsymbolic",   # own cuda* stubs win over a loaded libcudart
            "-ffp-contract=fast" if contract else "-ffp-contract=off"] + (["-mfma"] if contract else []) + (
            ["-fsanitize=" + SANITIZE, "-fno-omit-frame-pointer"] if SANITIZE else []) + [
            "-I", CUDA_INC, "-I", os.path.join(ROOT, "include"), "-I", HERE, "-include", os.path.join(HERE, "cuda_emu.h"),

@@ -43,6 +43,28 @@
 #undef __cluster_dims__
 #define __cluster_dims__(...)
 
+// Race detection (OPB_EMU_SANITIZE=thread): every fiber is a ThreadSanitizer fiber without implicit
+// synchronisation at switches; barriers are the only happens-before edges inside a block, so two CUDA threads
+// touching the same shared / global location without a barrier (or atomic) in between are reported as a data race --
+// a racecheck analogue that also flags warp-synchronous code relying on lockstep execution.
+#if defined(__SANITIZE_THREAD__)
+#define EMU_TSAN 1
+extern "C" {
+void* __tsan_get_current_fiber(void);
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void* fiber);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+void __tsan_acquire(void* addr);
+void __tsan_release(void* addr);
+}
+#endif
+
+#ifdef EMU_TSAN
+#define EMU_INTERNAL __attribute__((no_sanitize("thread"), noinline))   // emulator bookkeeping is not kernel code
+#else
+#define EMU_INTERNAL
+#endif
+
 namespace emu {
 
 enum { READY = 0, WAIT_BLOCK = 1, WAIT_WARP = 2, DONE = 3 };
@@ -52,12 +74,14 @@ constexpr size_t STACK_BYTES = 256 * 1024;
 struct Fiber {
   ucontext_t ctx;      // portable fallback
   void* sp = nullptr;  // x86-64 fast path: saved stack pointer (emu_switch in emu_runtime.cpp)
+  void* tsan = nullptr;  // ThreadSanitizer fiber handle (race-detection build)
   char* stack = nullptr;
   int state = DONE;
   unsigned mask = 0;
   int pred = 0;
   int site = 0;      // which warp-level primitive (and which half of it) the fiber waits in
   long long nwaits = 0;
+  long long nblock = 0;   // block-level barriers passed
   uint3 tid;
 };
 
@@ -65,6 +89,10 @@ inline Fiber g_fibers[MAX_THREADS];
 inline int g_nfib = 0, g_cur = 0;
 inline ucontext_t g_sched;
 inline void* g_sched_sp = nullptr;
+inline void* g_sched_tsan = nullptr;
+// happens-before tokens: one per barrier GENERATION (a fiber that is resumed late must not pick up what faster
+// fibers released when they arrived at the NEXT barrier); participants are at most one generation apart
+inline char g_hb_block[4], g_hb_warp[MAX_THREADS / 32][4], g_hb_done;
 inline const std::function<void()>* g_body = nullptr;
 inline int g_red_or = 0, g_red_and = 0, g_red_cnt = 0;
 inline uint64_t g_warp_buf[MAX_THREADS / 32][32];
@@ -83,33 +111,48 @@ inline bool g_reverse = false;
 extern "C" void emu_switch(void** save_sp, void* to_sp);
 #endif
 
-inline void fiber_entry() {
+EMU_INTERNAL inline void fiber_entry() {
   (*g_body)();
   g_fibers[g_cur].state = DONE;   // uc_link returns to the scheduler
 }
 
-inline void yield_wait(int state) {
+EMU_INTERNAL inline void yield_wait(int state) {
   Fiber& f = g_fibers[g_cur];
   f.state = state;
+#ifdef EMU_TSAN
+  void* hb = (state == WAIT_BLOCK) ? static_cast<void*>(&g_hb_block[f.nblock++ & 3]) : static_cast<void*>(&g_hb_warp[g_cur >> 5][f.nwaits & 3]);
+  __tsan_release(hb);                       // everything before the barrier ...
+  __tsan_switch_to_fiber(g_sched_tsan, 1);  // (1 = no implicit synchronisation at the switch)
+#endif
 #ifdef EMU_FAST_SWITCH
   emu_switch(&f.sp, g_sched_sp);
 #else
   swapcontext(&f.ctx, &g_sched);
 #endif
+#ifdef EMU_TSAN
+  __tsan_acquire(hb);                       // ... happens before everything after it, for all participants
+#endif
 }
 
 #ifdef EMU_FAST_SWITCH
-inline void fiber_trampoline() {
+EMU_INTERNAL inline void fiber_trampoline() {
   fiber_entry();
+#ifdef EMU_TSAN
+  __tsan_release(&g_hb_done);
+  __tsan_switch_to_fiber(g_sched_tsan, 1);
+#endif
   emu_switch(&g_fibers[g_cur].sp, g_sched_sp);   // never resumed
   abort();
 }
 #endif
 
-inline void run_block(int nthreads, const std::function<void()>& body) {
+EMU_INTERNAL inline void run_block(int nthreads, const std::function<void()>& body) {
   if (nthreads > MAX_THREADS) { fprintf(stderr, "emu: block of %d threads\n", nthreads); abort(); }
   g_nfib = nthreads;
   g_body = &body;
+#ifdef EMU_TSAN
+  g_sched_tsan = __tsan_get_current_fiber();
+#endif
   for (int i = 0; i < nthreads; ++i) {
     Fiber& f = g_fibers[i];
     if (!f.stack) f.stack = static_cast<char*>(malloc(STACK_BYTES));
@@ -131,6 +174,10 @@ inline void run_block(int nthreads, const std::function<void()>& body) {
 #endif
     f.state = READY;
     f.nwaits = 0;
+    f.nblock = 0;
+#ifdef EMU_TSAN
+    f.tsan = __tsan_create_fiber(0);
+#endif
     f.tid.x = i % g_bdim.x;
     f.tid.y = (i / g_bdim.x) % g_bdim.y;
     f.tid.z = i / (g_bdim.x * g_bdim.y);
@@ -144,6 +191,9 @@ inline void run_block(int nthreads, const std::function<void()>& body) {
       if (g_fibers[i].state != READY) continue;
       g_cur = i;
       g_tid = g_fibers[i].tid;
+#ifdef EMU_TSAN
+      __tsan_switch_to_fiber(g_fibers[i].tsan, 1);
+#endif
 #ifdef EMU_FAST_SWITCH
       emu_switch(&g_sched_sp, g_fibers[i].sp);
 #else
@@ -188,7 +238,13 @@ inline void run_block(int nthreads, const std::function<void()>& body) {
       ++live;
       if (f.state == WAIT_BLOCK) { ++waiting; r_or |= (f.pred != 0); r_and &= (f.pred != 0); r_cnt += (f.pred != 0); }
     }
-    if (live == 0) break;
+    if (live == 0) {
+#ifdef EMU_TSAN
+      __tsan_acquire(&g_hb_done);             // the block's writes are visible to later blocks / the host
+      for (int i = 0; i < nthreads; ++i) { __tsan_destroy_fiber(g_fibers[i].tsan); g_fibers[i].tsan = nullptr; }
+#endif
+      break;
+    }
     if (waiting == live) {
       g_red_or = r_or; g_red_and = r_and; g_red_cnt = r_cnt;
       for (int i = 0; i < nthreads; ++i) if (g_fibers[i].state == WAIT_BLOCK) g_fibers[i].state = READY;
@@ -234,16 +290,16 @@ struct Launcher {
   abort();
 }
 
-inline int lane_id() { return g_cur & 31; }
-inline int warp_id() { return g_cur >> 5; }
-inline void warp_wait(unsigned mask, int site) {
+EMU_INTERNAL inline int lane_id() { return g_cur & 31; }
+EMU_INTERNAL inline int warp_id() { return g_cur >> 5; }
+EMU_INTERNAL inline void warp_wait(unsigned mask, int site) {
   Fiber& f = g_fibers[g_cur];
   f.mask = mask; f.site = site; ++f.nwaits;
   yield_wait(WAIT_WARP);
 }
 
 template <class T>
-inline T shfl_from(unsigned mask, T v, int src_lane) {
+EMU_INTERNAL inline T shfl_from(unsigned mask, T v, int src_lane) {
   static_assert(sizeof(T) <= 8, "shuffle payload");
   uint64_t bits = 0;
   memcpy(&bits, &v, sizeof(T));
@@ -256,7 +312,7 @@ inline T shfl_from(unsigned mask, T v, int src_lane) {
   return out;
 }
 
-inline unsigned ballot(unsigned mask, int pred) {
+EMU_INTERNAL inline unsigned ballot(unsigned mask, int pred) {
   g_warp_pred[warp_id()][lane_id()] = pred != 0;
   warp_wait(mask, 3);
   unsigned r = 0;
@@ -267,7 +323,7 @@ inline unsigned ballot(unsigned mask, int pred) {
   return r;
 }
 
-inline unsigned live_mask(unsigned mask) {
+EMU_INTERNAL inline unsigned live_mask(unsigned mask) {
   unsigned r = 0;
   const int base = warp_id() * 32;
   for (int j = 0; j < 32 && base + j < g_nfib; ++j)
@@ -277,17 +333,18 @@ inline unsigned live_mask(unsigned mask) {
 
 }  // namespace emu
 
-#define threadIdx emu::g_tid
+namespace emu { EMU_INTERNAL inline uint3 tid() { return g_tid; } }
+#define threadIdx emu::tid()
 #define blockIdx emu::g_bid
 #define blockDim emu::g_bdim
 #define gridDim emu::g_gdim
 constexpr int warpSize = 32;
 
 // ---- synchronisation ---------------------------------------------------------------------------
-inline void __syncthreads() { emu::g_fibers[emu::g_cur].pred = 0; emu::yield_wait(emu::WAIT_BLOCK); }
-inline int __syncthreads_or(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_or; }
-inline int __syncthreads_and(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_and; }
-inline int __syncthreads_count(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_cnt; }
+EMU_INTERNAL inline void __syncthreads() { emu::g_fibers[emu::g_cur].pred = 0; emu::yield_wait(emu::WAIT_BLOCK); }
+EMU_INTERNAL inline int __syncthreads_or(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_or; }
+EMU_INTERNAL inline int __syncthreads_and(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_and; }
+EMU_INTERNAL inline int __syncthreads_count(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_cnt; }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_wait(mask, 1); }
 template <class T> inline T __shfl_sync(unsigned m, T v, int src, int width = 32) {
   const int l = emu::lane_id();
@@ -313,13 +370,17 @@ inline int __all_sync(unsigned m, int p) { const unsigned b = emu::ballot(m, p);
 // ---- memory ------------------------------------------------------------------------------------
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T, class U> inline void __stcs(T* p, U v) { *p = v; }
-template <class T, class U> inline T atomicAdd(T* p, U v) { const T o = *p; *p = static_cast<T>(o + v); return o; }
-template <class T, class U> inline T atomicMax(T* p, U v) { const T o = *p; if (static_cast<T>(v) > o) *p = static_cast<T>(v); return o; }
-template <class T, class U> inline T atomicMin(T* p, U v) { const T o = *p; if (static_cast<T>(v) < o) *p = static_cast<T>(v); return o; }
-template <class T, class U> inline T atomicOr(T* p, U v) { const T o = *p; *p = o | static_cast<T>(v); return o; }
-template <class T, class U> inline T atomicAnd(T* p, U v) { const T o = *p; *p = o & static_cast<T>(v); return o; }
-template <class T, class U> inline T atomicExch(T* p, U v) { const T o = *p; *p = static_cast<T>(v); return o; }
-template <class T, class U, class V> inline T atomicCAS(T* p, U c, V v) { const T o = *p; if (o == static_cast<T>(c)) *p = static_cast<T>(v); return o; }
+// relaxed atomics (one OS thread, but the race-detection build must see them as atomic accesses)
+template <class T, class U> inline T atomicAdd(T* p, U v) {
+  static_assert(std::is_integral<T>::value, "only integer atomicAdd is used by the emulated kernels");
+  return __atomic_fetch_add(p, static_cast<T>(v), __ATOMIC_RELAXED);
+}
+template <class T, class U> inline T atomicMax(T* p, U v) { T o = __atomic_load_n(p, __ATOMIC_RELAXED); if (static_cast<T>(v) > o) __atomic_store_n(p, static_cast<T>(v), __ATOMIC_RELAXED); return o; }
+template <class T, class U> inline T atomicMin(T* p, U v) { T o = __atomic_load_n(p, __ATOMIC_RELAXED); if (static_cast<T>(v) < o) __atomic_store_n(p, static_cast<T>(v), __ATOMIC_RELAXED); return o; }
+template <class T, class U> inline T atomicOr(T* p, U v) { return __atomic_fetch_or(p, static_cast<T>(v), __ATOMIC_RELAXED); }
+template <class T, class U> inline T atomicAnd(T* p, U v) { return __atomic_fetch_and(p, static_cast<T>(v), __ATOMIC_RELAXED); }
+template <class T, class U> inline T atomicExch(T* p, U v) { return __atomic_exchange_n(p, static_cast<T>(v), __ATOMIC_RELAXED); }
+template <class T, class U, class V> inline T atomicCAS(T* p, U c, V v) { T e = static_cast<T>(c); __atomic_compare_exchange_n(p, &e, static_cast<T>(v), false, __ATOMIC_RELAXED, __ATOMIC_RELAXED); return e; }
 inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
 
 // ---- single IEEE operations, fenced against contraction ---------------------------------------------

@@ -210,3 +210,29 @@ def test_results_do_not_depend_on_the_order_threads_run_in(emu_native, monkeypat
         monkeypatch.setenv("OPB_PAF_LOWRES", str(knobs[1]))
         eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params(max_peaks=4096, max_candidates=65536, max_persons=128))
         run_batch_cases(eng)
+
+
+def test_weight_loading_and_repack_host_code(emu_native):
+    """opb_load_weights x92 + opb_finalize_weights (the K-major fp16 repack, hi/lo split, concat-order permutation and
+    tensor-map construction are host code) for CocoPoseNet in both precisions and for FaceNet / HandNet, plus the error
+    paths; run under the AddressSanitizer build (see tests/cuda_emu/build_emu.py) this is the memcheck of that code."""
+    syn, PD = pkg("synthetic"), pkg("pose_detector")
+    prm = PD.make_opb_params(max_peaks=512, max_candidates=4096, max_persons=32)
+    model = pkg("models.CocoPoseNet").CocoPoseNet()
+    model.load_npz(syn.he_weights(0))
+    for prec in (emu_native.PRECISION_FAST, emu_native.PRECISION_PARITY):
+        eng = emu_native.Engine(0, prm, prec)
+        eng.load_model(model)
+        assert eng._weights_ready and eng.kp_channels == 0
+    for modname, cls, n_out in (("models.FaceNet", "FaceNet", 71), ("models.HandNet", "HandNet", 22)):
+        nm = pkg(modname)
+        net = getattr(nm, cls)()
+        net.load_npz(syn.he_weights(0, layers=nm.LAYERS))
+        eng = emu_native.Engine(0, prm, emu_native.PRECISION_FAST)
+        eng.load_model(net)
+        assert eng.kp_channels == n_out
+    eng = emu_native.Engine(0, prm)
+    with pytest.raises(emu_native.OpbError):
+        eng._check(eng.lib.opb_finalize_weights(eng.ctx, 0))          # nothing loaded yet
+    with pytest.raises(emu_native.OpbError):
+        eng._check(eng.lib.opb_load_weights(eng.ctx, b"conv1_1", None, (C.c_int64 * 4)(64, 3, 3, 3), None))
