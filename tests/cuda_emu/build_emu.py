@@ -22,6 +22,8 @@ Source rewriting (textual, into _build/src; the originals are not touched):
   kernel<<<grid, block, smem, stream>>>(args)  ->  emu::Launcher(grid, block, smem, stream).run(kernel, args)
   extern __shared__ T name[];                  ->  T* name = reinterpret_cast<T*>(emu::g_dyn_smem);
   asm volatile(...);                           ->  emu::unsupported_ptx();
+  csrc/ptx.cuh (inline-PTX wrappers)           ->  ptx_emu.cuh: functional model of mbarrier / TMA / tcgen05 + TMEM, so
+                                                   the tensor-core conv kernels run too (CTA-pair kernels excepted)
 """
 import os
 import re
@@ -91,13 +93,20 @@ def build(contract=False, force=False):
     os.makedirs(src_dir, exist_ok=True)
     lib = lib_path(contract)
     deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [
-        os.path.join(HERE, f) for f in ("cuda_emu.h", "emu_runtime.cpp", "build_emu.py")] + [
+        os.path.join(HERE, f) for f in ("cuda_emu.h", "ptx_emu.cuh", "emu_tmap.h", "emu_runtime.cpp", "build_emu.py")] + [
         os.path.join(ROOT, "include", "opb.h")]
     if not force and os.path.isfile(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
         return lib
     for f in sorted(os.listdir(CSRC)):
         with open(os.path.join(CSRC, f)) as fh:
-            text = rewrite(fh.read())
+            text = fh.read()
+        if f == "ptx.cuh":
+            # the inline-PTX wrappers are replaced by the functional model in ptx_emu.cuh; the UMMA descriptor
+            # encoders (plain C++) are taken from the original so that the kernels' own encodings are what runs
+            desc = text[text.index("// K-major operand, 128-byte swizzle"):text.index("}  // namespace ptx")]
+            with open(os.path.join(HERE, "ptx_emu.cuh")) as fh:
+                text = fh.read().replace("// @@DESCRIPTORS@@", desc)
+        text = rewrite(text)
         with open(os.path.join(src_dir, f.replace(".cu", ".cpp") if f.endswith(".cu") else f), "w") as fh:
             fh.write(text)
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-w", "-Wl,-Bsymbolic",   # own cuda* stubs win over a loaded libcudart

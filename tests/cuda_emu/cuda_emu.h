@@ -15,8 +15,8 @@
 //     the emulated build may be compiled with -ffp-contract=fast to expose any arithmetic that
 //     would depend on nvcc's FMA contraction.
 //
-// The tensor-core kernels (tcgen05 / TMA inline PTX) compile to traps here: they cannot be
-// emulated and are only ever validated on a B200 (tests marked gpu).
+// The inline-PTX wrappers (csrc/ptx.cuh: mbarrier, TMA, tcgen05) are replaced by a functional model in
+// ptx_emu.cuh; only the CTA-pair (cta_group::2) wrappers trap.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -99,6 +99,8 @@ inline uint64_t g_warp_buf[MAX_THREADS / 32][32];
 inline int g_warp_pred[MAX_THREADS / 32][32];
 inline unsigned char* g_dyn_smem = nullptr;   // exactly the launch's dynamic shared memory (a heap block: ASan sees overruns)
 constexpr size_t MAX_DYN_SMEM = 232448;
+inline size_t g_dyn_smem_bytes = 0;
+inline uintptr_t g_static_smem_hi = 0;   // 256 KB-aligned host block holding the static __shared__ operands of this launch
 inline uint3 g_tid, g_bid;
 inline dim3 g_bdim, g_gdim;
 inline long long g_launches = 0;
@@ -265,9 +267,11 @@ struct Launcher {
   template <class... KA, class... A>
   void run(void (*k)(KA...), A&&... a) {
     if (smem > MAX_DYN_SMEM) { fprintf(stderr, "emu: %zu B of dynamic shared memory\n", smem); abort(); }
-    void* dyn = nullptr;
-    if (posix_memalign(&dyn, 1024, smem ? smem : 1)) abort();
+    void* dyn = nullptr;   // 256 KB-aligned: the low 18 bits of a pointer into it are its shared-window address
+    if (posix_memalign(&dyn, 262144, smem ? smem : 1)) abort();
     g_dyn_smem = static_cast<unsigned char*>(dyn);
+    g_dyn_smem_bytes = smem;
+    g_static_smem_hi = 0;
     std::tuple<std::decay_t<KA>...> args(std::forward<A>(a)...);
     const std::function<void()> body = [&] { std::apply(k, args); };
     g_bdim = b; g_gdim = g;

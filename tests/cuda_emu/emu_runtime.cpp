@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "emu_tmap.h"
+
 extern "C" {
 
 static int g_dummy_handles = 0;
@@ -71,10 +73,33 @@ cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
 cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t*, const void*, void**) { return cudaErrorNotSupported; }
 cudaError_t cudaLaunchKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { return cudaErrorNotSupported; }
 
-// cuTensorMapEncodeTiled & co: accept and leave the (unused) descriptor zeroed
+// cuTensorMapEncodeTiled: record the map for the emulated TMA (ptx_emu.cuh); the 128-byte CUtensorMap holds a
+// pointer to the record (never freed: a few hundred maps per test process)
+static CUresult emu_cuTensorMapEncodeTiled(CUtensorMap* tm, CUtensorMapDataType dtype, cuuint32_t rank, void* base,
+                                           const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                                           const cuuint32_t* estr, CUtensorMapInterleave, CUtensorMapSwizzle swizzle,
+                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+  static const uint32_t kBytes[] = {1, 2, 4, 4, 8, 8, 2, 4, 8, 2, 4, 4, 4};
+  if (rank < 1 || rank > 5 || static_cast<unsigned>(dtype) >= sizeof(kBytes) / sizeof(kBytes[0])) return CUDA_ERROR_INVALID_VALUE;
+  emu::TensorMapRec* r = new emu::TensorMapRec();
+  r->magic = emu::TMAP_MAGIC;
+  r->base = base; r->rank = rank; r->elem_bytes = kBytes[dtype]; r->swizzle = static_cast<uint32_t>(swizzle);
+  for (cuuint32_t d = 0; d < rank; ++d) {
+    r->dims[d] = dims[d];
+    r->strides[d] = d ? strides[d - 1] : r->elem_bytes;
+    r->box[d] = box[d];
+    r->estr[d] = estr[d];
+    if (box[d] == 0 || box[d] > 256 || (d && (strides[d - 1] % 16))) { delete r; return CUDA_ERROR_INVALID_VALUE; }
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16) { delete r; return CUDA_ERROR_INVALID_VALUE; }
+  memset(tm, 0, sizeof(*tm));
+  memcpy(tm, &r, sizeof(r));
+  return CUDA_SUCCESS;
+}
 static CUresult emu_driver_stub(...) { return CUDA_SUCCESS; }
-cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
-  *fn = reinterpret_cast<void*>(&emu_driver_stub);
+cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
+  *fn = !strcmp(name, "cuTensorMapEncodeTiled") ? reinterpret_cast<void*>(&emu_cuTensorMapEncodeTiled)
+                                                : reinterpret_cast<void*>(&emu_driver_stub);
   if (q) *q = cudaDriverEntryPointSuccess;
   return cudaSuccess;
 }

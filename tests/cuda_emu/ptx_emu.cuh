@@ -1,0 +1,275 @@
+// ptx_emu.cuh -- TEST INFRASTRUCTURE ONLY.  Replaces csrc/ptx.cuh in the emulated build (build_emu.py): the same
+// opb::ptx:: wrappers, implemented as a functional model of the sm_100a features the conv kernels use, so that the
+// tcgen05 / TMA kernels themselves (descriptor arithmetic, swizzled layouts, pipeline phases, TMEM addressing,
+// epilogues) run on a box without a GPU and can be checked against the oracle.
+//
+// Model (what the kernels are entitled to assume, executed adversarially where that is cheap):
+//   mbarrier   64-bit word = {phase, expected arrivals, pending arrivals, pending transaction bytes}; a phase completes
+//              when both pending counts reach zero; try_wait(parity) is true once the phase of that parity has
+//              completed; a failing try_wait yields to the other threads of the block.
+//   TMA        cuTensorMapEncodeTiled (emu_runtime.cpp) records the map; a load copies the box element by element
+//              (out-of-bounds -> zero fill), writes it with the 128-byte swizzle (16-byte chunk index ^= bits 7..9 of
+//              the shared address) and completes `box bytes` on the mbarrier at once.
+//   tcgen05    TMEM = 128 lanes x 512 fp32 columns per CTA.  tcgen05.mma is QUEUED and executed only when the issuing
+//              thread commits (tcgen05.commit) -- "as late as legal": a kernel that recycles an operand stage or
+//              reads an accumulator before the corresponding commit sees stale data and fails its parity test.
+//              Operands are fetched through the UMMA shared-memory descriptors (K-major, SWIZZLE_128B: start address,
+//              stride between 8-row groups, address-bit swizzle), fp16 x fp16 products accumulated in fp32.
+//              tcgen05.ld.32x32b checks that a warp only touches its own lane quadrant.
+//   cluster    CTA pairs (cta_group::2, multicast, mapa) are not modelled: those wrappers trap (run with OPB_PAIR=0).
+// Accumulation order inside an MMA is unspecified on hardware; here it is k-ascending in fp32, so results agree with the
+// GPU to rounding, not bit for bit -- the conv parity tests use the same tolerances on both.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "emu_tmap.h"
+
+namespace emu {
+
+// Shared-window addresses (what cvta.to.shared yields on the GPU; UMMA descriptors keep 18 bits of them): a pointer
+// into the launch's dynamic shared memory maps to its offset (the block is 256 KB-aligned); a pointer to a static
+// __shared__ array maps to the low 18 bits of its host address, which requires that all static operands of one launch
+// lie in one 256 KB-aligned host block (checked).
+EMU_INTERNAL inline uint32_t smem_addr_of(const void* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p), d = reinterpret_cast<uintptr_t>(g_dyn_smem);
+  if (g_dyn_smem_bytes && a >= d && a < d + g_dyn_smem_bytes) return static_cast<uint32_t>(a - d);
+  const uintptr_t hi = a & ~static_cast<uintptr_t>(0x3FFFF);
+  if (!g_static_smem_hi) g_static_smem_hi = hi;
+  if (hi != g_static_smem_hi) { fprintf(stderr, "emu: static __shared__ operands straddle a 256 KB host boundary (emulation limit)\n"); abort(); }
+  return static_cast<uint32_t>(a & 0x3FFFF);
+}
+EMU_INTERNAL inline unsigned char* smem_ptr(uint32_t addr) {
+  if (addr < g_dyn_smem_bytes) return g_dyn_smem + addr;
+  if (!g_static_smem_hi) { fprintf(stderr, "emu: shared-window address 0x%x outside the launch's shared memory\n", addr); abort(); }
+  return reinterpret_cast<unsigned char*>(g_static_smem_hi | addr);
+}
+
+inline const TensorMapRec* tmap_rec(const CUtensorMap* m) {
+  const TensorMapRec* r = *reinterpret_cast<TensorMapRec* const*>(m);
+  if (!r || r->magic != TMAP_MAGIC) { fprintf(stderr, "emu: TMA with a tensor map that was not encoded\n"); abort(); }
+  return r;
+}
+
+struct MBar {              // layout of the 64-bit mbarrier word in the emulation
+  uint32_t phase : 1;
+  uint32_t expected : 15;
+  uint32_t pending : 16;
+  int32_t tx;
+};
+static_assert(sizeof(MBar) == 8, "mbarrier word");
+
+EMU_INTERNAL inline void mbar_check(MBar* b) {
+  if (b->pending == 0 && b->tx == 0) { b->phase ^= 1u; b->pending = b->expected; }
+}
+EMU_INTERNAL inline void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+  MBar* b = reinterpret_cast<MBar*>(bar);
+  if (b->pending < n) { fprintf(stderr, "emu: more arrivals than the mbarrier expects (block %u thread %d)\n", g_bid.x, g_cur); abort(); }
+  b->pending -= n;
+  mbar_check(b);
+}
+EMU_INTERNAL inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
+  MBar* b = reinterpret_cast<MBar*>(bar);
+  b->tx -= static_cast<int32_t>(bytes);
+  mbar_check(b);
+}
+
+struct QueuedMma { uint32_t tmem_d; uint64_t adesc, bdesc; uint32_t idesc; uint32_t accumulate; };
+inline std::vector<QueuedMma> g_mma_queue[MAX_THREADS];   // per issuing thread, flushed by its tcgen05.commit
+inline float g_tmem[128][512];
+inline bool g_tmem_allocated = false;
+inline long long g_mma_count = 0, g_tma_count = 0;
+
+EMU_INTERNAL inline uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
+
+EMU_INTERNAL inline float half_at(uint32_t addr) {
+  __half h;
+  memcpy(&h, smem_ptr(swz128(addr)), 2);
+  return __half2float(h);
+}
+
+__attribute__((optimize("O3"))) EMU_INTERNAL inline void execute_mma(const QueuedMma& q) {
+  const int N = static_cast<int>((q.idesc >> 17) & 0x3f) << 3, M = static_cast<int>((q.idesc >> 24) & 0x1f) << 4;
+  if (M != 128 || N < 8 || N > 256 || ((q.idesc >> 15) & 3u) != 0 || ((q.idesc >> 4) & 3u) != 1) {
+    fprintf(stderr, "emu: unsupported tcgen05.mma instruction descriptor 0x%x (M=%d N=%d)\n", q.idesc, M, N); abort();
+  }
+  if ((q.adesc >> 61) != 2 || (q.bdesc >> 61) != 2) { fprintf(stderr, "emu: only SWIZZLE_128B K-major operands are modelled\n"); abort(); }
+  const uint32_t a0 = static_cast<uint32_t>(q.adesc & 0x3FFF) << 4, b0 = static_cast<uint32_t>(q.bdesc & 0x3FFF) << 4;
+  const uint32_t a_sbo = static_cast<uint32_t>((q.adesc >> 32) & 0x3FFF) << 4, b_sbo = static_cast<uint32_t>((q.bdesc >> 32) & 0x3FFF) << 4;
+  const uint32_t dcol = q.tmem_d & 0xffff, dlane = q.tmem_d >> 16;
+  if (dlane != 0 || dcol + N > 512) { fprintf(stderr, "emu: tcgen05.mma accumulator outside TMEM (lane %u col %u N %d)\n", dlane, dcol, N); abort(); }
+  static float A[128][16], Bt[16][256];
+  for (int m = 0; m < 128; ++m)
+    for (int k = 0; k < 16; ++k) A[m][k] = half_at(a0 + (m >> 3) * a_sbo + (m & 7) * 128 + 2 * k);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < 16; ++k) Bt[k][n] = half_at(b0 + (n >> 3) * b_sbo + (n & 7) * 128 + 2 * k);
+  for (int m = 0; m < 128; ++m) {      // per element: acc = (((d + a0*b0) + a1*b1) + ...), k ascending; vectorises over n
+    float* d = &g_tmem[m][dcol];
+    if (!q.accumulate) for (int n = 0; n < N; ++n) d[n] = 0.f;
+    for (int k = 0; k < 16; ++k) {
+      const float a = A[m][k];
+      const float* b = Bt[k];
+      for (int n = 0; n < N; ++n) d[n] += a * b[n];
+    }
+  }
+  ++g_mma_count;
+}
+
+EMU_INTERNAL inline void yield_ready() {   // spin-wait: let the other threads of the block run
+  Fiber& f = g_fibers[g_cur];
+  f.state = READY;
+#ifdef EMU_FAST_SWITCH
+  emu_switch(&f.sp, g_sched_sp);
+#else
+  swapcontext(&f.ctx, &g_sched);
+#endif
+}
+
+EMU_INTERNAL inline void tma_load(void* smem_dst, const CUtensorMap* m, uint64_t* bar, const int* c, int rank) {
+  const TensorMapRec* r = tmap_rec(m);
+  if (static_cast<int>(r->rank) != rank) { fprintf(stderr, "emu: %dD TMA load through a %uD tensor map\n", rank, r->rank); abort(); }
+  if (r->swizzle != 3 /* CU_TENSOR_MAP_SWIZZLE_128B */ || r->box[0] * r->elem_bytes != 128) {
+    fprintf(stderr, "emu: only SWIZZLE_128B boxes with 128-byte inner rows are modelled (swizzle %u, inner %u B)\n", r->swizzle, r->box[0] * r->elem_bytes);
+    abort();
+  }
+  const uint32_t dst = smem_addr_of(smem_dst);
+  uint32_t rows = 1;
+  for (int d = 1; d < rank; ++d) rows *= r->box[d];
+  const uint32_t eb = r->elem_bytes;
+  for (uint32_t row = 0; row < rows; ++row) {
+    // coordinates of this row in dims 1..rank-1
+    uint32_t rem = row;
+    long long off = 0;
+    bool oob_row = false;
+    for (int d = 1; d < rank; ++d) {
+      const uint32_t bi = rem % r->box[d];
+      rem /= r->box[d];
+      const long long g = static_cast<long long>(c[d]) + static_cast<long long>(bi) * r->estr[d];
+      if (g < 0 || g >= static_cast<long long>(r->dims[d])) oob_row = true;
+      off += g * static_cast<long long>(r->strides[d]);
+    }
+    for (uint32_t e = 0; e < r->box[0]; ++e) {
+      const long long g0 = static_cast<long long>(c[0]) + static_cast<long long>(e) * r->estr[0];
+      unsigned char* d8 = smem_ptr(swz128(dst + row * 128 + e * eb));
+      if (oob_row || g0 < 0 || g0 >= static_cast<long long>(r->dims[0])) memset(d8, 0, eb);
+      else memcpy(d8, static_cast<const unsigned char*>(r->base) + off + g0 * static_cast<long long>(eb), eb);
+    }
+  }
+  ++g_tma_count;
+  mbar_complete_tx(bar, rows * 128);
+}
+
+}  // namespace emu
+
+namespace opb {
+namespace ptx {
+
+EMU_INTERNAL inline uint32_t smem_u32(const void* p) { return emu::smem_addr_of(p); }
+
+// ---------------------------------------------------------------- mbarrier
+EMU_INTERNAL inline void mbar_init(uint64_t* bar, uint32_t count) {
+  emu::MBar b;
+  b.phase = 0; b.expected = count; b.pending = count; b.tx = 0;
+  memcpy(bar, &b, 8);
+}
+inline void fence_barrier_init() {}
+inline void fence_proxy_async_smem() {}
+EMU_INTERNAL inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  reinterpret_cast<emu::MBar*>(bar)->tx += static_cast<int32_t>(bytes);
+  emu::mbar_arrive_n(bar, 1);
+}
+EMU_INTERNAL inline void mbar_arrive(uint64_t* bar) { emu::mbar_arrive_n(bar, 1); }
+EMU_INTERNAL inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  if (reinterpret_cast<emu::MBar*>(bar)->phase != (parity & 1u)) return true;
+  emu::yield_ready();
+  return reinterpret_cast<emu::MBar*>(bar)->phase != (parity & 1u);
+}
+EMU_INTERNAL inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  long long spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > 2000000) {   // every other thread of the block had two million turns: a protocol deadlock
+      fprintf(stderr, "emu: mbarrier wait never satisfied: block %u thread %d bar +%u parity %u\n", emu::g_bid.x, emu::g_cur,
+              smem_u32(bar), parity);
+      abort();
+    }
+  }
+}
+
+// ---------------------------------------------------------------- TMA
+inline void prefetch_tensormap(const CUtensorMap*) {}
+EMU_INTERNAL inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  const int c[2] = {c0, c1};
+  emu::tma_load(smem_dst, m, bar, c, 2);
+}
+EMU_INTERNAL inline void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  const int c[4] = {c0, c1, c2, c3};
+  emu::tma_load(smem_dst, m, bar, c, 4);
+}
+
+// ---------------------------------------------------------------- tcgen05
+template <int kCols>
+EMU_INTERNAL inline void tmem_alloc(uint32_t* smem_result) {
+  if (emu::lane_id() == 0) {   // .sync.aligned: one allocation per warp-wide call
+    if (emu::g_tmem_allocated) { fprintf(stderr, "emu: second tcgen05.alloc in one CTA\n"); abort(); }
+    emu::g_tmem_allocated = true;
+    for (auto& row : emu::g_tmem) for (float& v : row) v = __builtin_nanf("");   // fresh TMEM holds garbage
+    *smem_result = 0;
+  }
+}
+template <int kCols>
+EMU_INTERNAL inline void tmem_dealloc(uint32_t) {
+  if (emu::lane_id() == 0) {
+    for (int t = 0; t < emu::g_nfib; ++t)
+      if (!emu::g_mma_queue[t].empty()) { fprintf(stderr, "emu: %zu tcgen05.mma issued by thread %d were never committed\n", emu::g_mma_queue[t].size(), t); abort(); }
+    emu::g_tmem_allocated = false;
+  }
+}
+inline void tc_fence_before() {}
+inline void tc_fence_after() {}
+EMU_INTERNAL inline void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, accumulate});
+}
+EMU_INTERNAL inline void mma_f16_ss_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, 1u});
+}
+EMU_INTERNAL inline void mma_commit(uint64_t* bar) {
+  for (const emu::QueuedMma& q : emu::g_mma_queue[emu::g_cur]) emu::execute_mma(q);
+  emu::g_mma_queue[emu::g_cur].clear();
+  emu::mbar_arrive_n(bar, 1);
+}
+template <int NCOL>
+EMU_INTERNAL inline void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
+  const uint32_t lane0 = taddr >> 16, col = taddr & 0xffff;
+  if (lane0 != 32u * (static_cast<uint32_t>(emu::warp_id()) & 3u) || col + NCOL > 512) {
+    fprintf(stderr, "emu: tcgen05.ld outside the warp's lane quadrant / TMEM (warp %d lane base %u col %u)\n", emu::warp_id(), lane0, col);
+    abort();
+  }
+  const float* src = &emu::g_tmem[lane0 + static_cast<uint32_t>(emu::lane_id())][col];
+  memcpy(r, src, 4 * NCOL);
+}
+EMU_INTERNAL inline void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_cols<32>(taddr, r); }
+EMU_INTERNAL inline void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_cols<16>(taddr, r); }
+inline void tmem_ld_wait() {}
+
+// ---------------------------------------------------------------- CTA pairs: not modelled
+inline uint32_t cluster_ctarank() { return 0; }
+inline void cluster_sync_all() { emu::unsupported_ptx(); }
+inline uint32_t mapa_u32(uint32_t, uint32_t) { emu::unsupported_ptx(); }
+inline void mbar_arrive_cluster(uint32_t) { emu::unsupported_ptx(); }
+inline void tma_load_2d_pair(void*, const CUtensorMap*, uint32_t, int, int) { emu::unsupported_ptx(); }
+inline void tma_load_4d_pair(void*, const CUtensorMap*, uint32_t, int, int, int, int) { emu::unsupported_ptx(); }
+template <int kCols> inline void tmem_alloc_pair(uint32_t*) { emu::unsupported_ptx(); }
+template <int kCols> inline void tmem_dealloc_pair(uint32_t) { emu::unsupported_ptx(); }
+inline void mma_f16_ss_pair(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { emu::unsupported_ptx(); }
+inline void mma_f16_ss_pair_acc(uint32_t, uint64_t, uint64_t, uint32_t) { emu::unsupported_ptx(); }
+inline void mma_commit_pair(uint64_t*) { emu::unsupported_ptx(); }
+
+// descriptor encodings: the kernels' own (pasted from csrc/ptx.cuh by build_emu.py)
+// @@DESCRIPTORS@@
+
+}  // namespace ptx
+}  // namespace opb

@@ -1,0 +1,107 @@
+"""CPU (`-m "not gpu"`): the tcgen05 / TMA convolution kernels themselves, run WITHOUT a GPU.
+
+tests/cuda_emu/ptx_emu.cuh replaces the inline-PTX wrappers of csrc/ptx.cuh by a functional model of what the kernels
+use of sm_100a -- mbarrier phases and transaction counts, TMA tiled loads with out-of-bounds zero fill and the
+128-byte swizzle, UMMA shared-memory descriptors, tcgen05.mma into TMEM (queued until the issuing thread commits, i.e.
+executed as late as the kernel's own synchronisation allows), tcgen05.ld lane quadrants -- so the unmodified kernel
+sources (descriptor arithmetic, swizzled operand layouts, pipeline phase bookkeeping, role-swapped and fused variants,
+epilogues, max-pool fusion, split-fp16 two-level accumulation) execute on the CPU and are compared with a torch fp32
+conv2d / the oracle's forward pass under the SAME tolerances as tests/test_gpu_conv.py.
+
+Not modelled: CTA pairs (cta_group::2) -- OPB_PAIR=0 selects the single-CTA kernel for the fused 7x7 N=256 launch;
+timing, bank conflicts, and the hardware's accumulation order inside one MMA (results agree to rounding).
+Test infrastructure only: the package never loads the emulated library."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import pkg
+from oracle import restate as R
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda_emu"))
+import build_emu  # noqa: E402
+import test_gpu_conv as G  # noqa: E402  (plain helpers; the gpu mark belongs to that module only)
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    native = pkg("_native")
+    lib = C.CDLL(build_emu.build(contract=False))
+    for name, (res, args) in native._SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+@pytest.fixture()
+def emu_native(emu_lib, monkeypatch):
+    native = pkg("_native")
+    monkeypatch.setattr(native, "_lib", emu_lib)
+    monkeypatch.setenv("OPB_PAIR", "0")          # CTA-pair kernels are not modelled
+    return native
+
+
+@pytest.fixture()
+def engine(emu_native):
+    return emu_native.Engine(0, pkg("pose_detector").make_opb_params())
+
+
+CASES = [
+    # n, h, w, cin, cout, ks, relu   (small versions of every kernel family of tests/test_gpu_conv.py)
+    (1, 24, 30, 128, 128, 7, 1),     # role-swapped 7x7 kernel, W % 16 == 14
+    (2, 23, 19, 128, 128, 7, 0),     # ... two images, last row tile trimmed (23 rows), 8-px edge tile
+    (2, 24, 24, 185, 256, 7, 1),     # fused Mconv1 shape (Cin 185 -> 192, N = 256) on the single-CTA kernel
+    (2, 23, 31, 64, 64, 3, 1),       # conv1_2-like, partial tiles in x and y
+    (1, 24, 24, 256, 512, 3, 1),     # two N blocks
+    (1, 24, 40, 128, 512, 1, 1),     # conv5_4-like 1x1
+    (2, 30, 17, 512, 38, 1, 0),      # PAF head (N = 48 tile, 38 valid)
+    (1, 24, 24, 128, 19, 1, 0),      # heat head
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "n%d_%dx%d_c%d_o%d_k%d" % c[:6])
+@pytest.mark.parametrize("mode", ["fast", "parity"])
+def test_conv_vs_torch(engine, emu_native, case, mode):
+    n, h, w, cin, cout, ks, relu = case
+    rs = np.random.RandomState(sum(case))
+    x = rs.standard_normal((n, h, w, cin)).astype(np.float32)
+    W = (rs.standard_normal((cout, cin, ks, ks)) * np.sqrt(2.0 / (cin * ks * ks))).astype(np.float32)
+    b = (rs.standard_normal(cout) * 0.1).astype(np.float32)
+    prec = emu_native.PRECISION_FAST if mode == "fast" else emu_native.PRECISION_PARITY
+    y = engine.test_conv(x, W, b, relu, prec)
+    ref = G._ref_conv(x, W, b, relu, quantize=(mode == "fast"))
+    scale = np.abs(ref).max()
+    err = np.abs(y - ref).max()
+    tol = (2e-3 if mode == "fast" else 1e-4) * scale
+    assert err <= tol, "max abs err %.3e > tol %.3e (scale %.3f)" % (err, tol, scale)
+
+
+def test_conv_zero_padding_borders(engine):
+    G.test_conv_zero_padding_borders(engine)
+
+
+@pytest.mark.parametrize("mode", ["fast", "parity"])
+def test_conv_fused_maxpool(engine, mode):
+    G.test_conv_fused_maxpool(engine, (2, 24, 40, 64, 64, 3), mode)
+
+
+@pytest.mark.parametrize("mode,tol", [("fast", 1e-2), ("parity", 1e-4)])
+def test_whole_network_forward(emu_native, he_weights, mode, tol):
+    """All 92 convolutions of CocoPoseNet (3 fused max-pools, concat-by-slice, fused 1x1 pairs, conv1_1 on tensor
+    cores in fast precision / the split-fp16 DRAIN kernels in parity precision) on a 176x128 frame -- the smallest the
+    7x7 TMA boxes admit -- against the oracle's torch-CPU fp32 forward.  north_star's tolerance is 1e-3 (parity)."""
+    syn = pkg("synthetic")
+    model = pkg("models.CocoPoseNet").CocoPoseNet()
+    model.load_npz(syn.he_weights(0))
+    img = syn.procedural_image(176, 128, seed=4)
+    ref_paf, ref_heat = R.forward(he_weights, R.preprocess(img))
+    eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params(),
+                            emu_native.PRECISION_FAST if mode == "fast" else emu_native.PRECISION_PARITY)
+    eng.load_model(model)
+    paf, heat = eng.forward(img[None])
+    err = max(float(np.abs(paf[0] - ref_paf[0]).max()), float(np.abs(heat[0] - ref_heat[0]).max()))
+    assert err <= tol, err

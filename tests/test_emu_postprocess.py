@@ -12,8 +12,8 @@ warp-synchronous code that diverges when lanes are not executed in lockstep (it 
 of a warp one after another between synchronisation points), i.e. on races that independent
 thread scheduling is allowed to expose.
 
-What it cannot cover: the tcgen05 / TMA convolution kernels (inline PTX traps here), memory
-coalescing, occupancy, timing.  Those are `-m gpu` tests on a B200.
+What it cannot cover: memory coalescing, occupancy, timing (the tcgen05 / TMA convolution kernels run under a
+functional model of their PTX: tests/test_emu_conv.py).
 
 The same test bodies as tests/test_gpu_postprocess.py are reused with the emulated engine;
 every case runs against two builds of the emulated library: -ffp-contract=off and
