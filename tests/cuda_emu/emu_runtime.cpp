@@ -37,7 +37,9 @@ cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {   // macro-renamed to _v2 by the header
   memset(p, 0, sizeof(*p));
   strcpy(p->name, "cuda_emu (CPU fibers, tests only)");
-  p->major = 10; p->minor = 0; p->multiProcessorCount = 148;
+  p->major = 10; p->minor = 0;
+  // OPB_EMU_SMS: a small SM count makes every persistent CTA loop over many tiles (pipeline wrap-around, phase parity)
+  p->multiProcessorCount = getenv("OPB_EMU_SMS") ? atoi(getenv("OPB_EMU_SMS")) : 148;
   p->sharedMemPerBlockOptin = 232448; p->warpSize = 32;
   return cudaSuccess;
 }

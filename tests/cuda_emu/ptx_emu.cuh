@@ -29,6 +29,25 @@
 
 #include "emu_tmap.h"
 
+#ifdef EMU_TSAN
+extern "C" {
+void __tsan_read_range(void* addr, unsigned long size);
+void __tsan_write_range(void* addr, unsigned long size);
+}
+// Race detection for the asynchronous agents: an mbarrier is a happens-before token (every arrive / expect_tx /
+// complete_tx releases it, a successful wait acquires it); TMA writes, tcgen05.mma operand reads and TMEM accesses
+// are reported to ThreadSanitizer as accesses of the fiber that caused them, at the time the model performs them.
+#define EMU_HB_RELEASE(p) __tsan_release(p)
+#define EMU_HB_ACQUIRE(p) __tsan_acquire(p)
+#define EMU_RACE_READ(p, n) __tsan_read_range(const_cast<void*>(static_cast<const void*>(p)), n)
+#define EMU_RACE_WRITE(p, n) __tsan_write_range(static_cast<void*>(p), n)
+#else
+#define EMU_HB_RELEASE(p)
+#define EMU_HB_ACQUIRE(p)
+#define EMU_RACE_READ(p, n)
+#define EMU_RACE_WRITE(p, n)
+#endif
+
 namespace emu {
 
 // Shared-window addresses (what cvta.to.shared yields on the GPU; UMMA descriptors keep 18 bits of them): a pointer
@@ -70,11 +89,13 @@ EMU_INTERNAL inline void mbar_arrive_n(uint64_t* bar, uint32_t n) {
   MBar* b = reinterpret_cast<MBar*>(bar);
   if (b->pending < n) { fprintf(stderr, "emu: more arrivals than the mbarrier expects (block %u thread %d)\n", g_bid.x, g_cur); abort(); }
   b->pending -= n;
+  EMU_HB_RELEASE(bar);
   mbar_check(b);
 }
 EMU_INTERNAL inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
   MBar* b = reinterpret_cast<MBar*>(bar);
   b->tx -= static_cast<int32_t>(bytes);
+  EMU_HB_RELEASE(bar);
   mbar_check(b);
 }
 
@@ -88,6 +109,7 @@ EMU_INTERNAL inline uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7)
 
 EMU_INTERNAL inline float half_at(uint32_t addr) {
   __half h;
+  EMU_RACE_READ(smem_ptr(swz128(addr)), 2);
   memcpy(&h, smem_ptr(swz128(addr)), 2);
   return __half2float(h);
 }
@@ -109,6 +131,7 @@ __attribute__((optimize("O3"))) EMU_INTERNAL inline void execute_mma(const Queue
     for (int k = 0; k < 16; ++k) Bt[k][n] = half_at(b0 + (n >> 3) * b_sbo + (n & 7) * 128 + 2 * k);
   for (int m = 0; m < 128; ++m) {      // per element: acc = (((d + a0*b0) + a1*b1) + ...), k ascending; vectorises over n
     float* d = &g_tmem[m][dcol];
+    EMU_RACE_WRITE(d, 4ul * N);
     if (!q.accumulate) for (int n = 0; n < N; ++n) d[n] = 0.f;
     for (int k = 0; k < 16; ++k) {
       const float a = A[m][k];
@@ -122,6 +145,9 @@ __attribute__((optimize("O3"))) EMU_INTERNAL inline void execute_mma(const Queue
 EMU_INTERNAL inline void yield_ready() {   // spin-wait: let the other threads of the block run
   Fiber& f = g_fibers[g_cur];
   f.state = READY;
+#ifdef EMU_TSAN
+  __tsan_switch_to_fiber(g_sched_tsan, 1);
+#endif
 #ifdef EMU_FAST_SWITCH
   emu_switch(&f.sp, g_sched_sp);
 #else
@@ -155,6 +181,7 @@ EMU_INTERNAL inline void tma_load(void* smem_dst, const CUtensorMap* m, uint64_t
     for (uint32_t e = 0; e < r->box[0]; ++e) {
       const long long g0 = static_cast<long long>(c[0]) + static_cast<long long>(e) * r->estr[0];
       unsigned char* d8 = smem_ptr(swz128(dst + row * 128 + e * eb));
+      EMU_RACE_WRITE(d8, eb);
       if (oob_row || g0 < 0 || g0 >= static_cast<long long>(r->dims[0])) memset(d8, 0, eb);
       else memcpy(d8, static_cast<const unsigned char*>(r->base) + off + g0 * static_cast<long long>(eb), eb);
     }
@@ -184,9 +211,10 @@ EMU_INTERNAL inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 EMU_INTERNAL inline void mbar_arrive(uint64_t* bar) { emu::mbar_arrive_n(bar, 1); }
 EMU_INTERNAL inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  if (reinterpret_cast<emu::MBar*>(bar)->phase != (parity & 1u)) return true;
-  emu::yield_ready();
-  return reinterpret_cast<emu::MBar*>(bar)->phase != (parity & 1u);
+  if (reinterpret_cast<emu::MBar*>(bar)->phase == (parity & 1u)) emu::yield_ready();
+  const bool done = reinterpret_cast<emu::MBar*>(bar)->phase != (parity & 1u);
+  if (done) EMU_HB_ACQUIRE(bar);
+  return done;
 }
 EMU_INTERNAL inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   long long spins = 0;
@@ -249,6 +277,7 @@ EMU_INTERNAL inline void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
     abort();
   }
   const float* src = &emu::g_tmem[lane0 + static_cast<uint32_t>(emu::lane_id())][col];
+  EMU_RACE_READ(src, 4ul * NCOL);
   memcpy(r, src, 4 * NCOL);
 }
 EMU_INTERNAL inline void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_cols<32>(taddr, r); }

@@ -42,6 +42,9 @@ def emu_native(emu_lib, monkeypatch):
     native = pkg("_native")
     monkeypatch.setattr(native, "_lib", emu_lib)
     monkeypatch.setenv("OPB_PAIR", "0")          # CTA-pair kernels are not modelled
+    # 3 "SMs": every persistent CTA loops over many tiles, so operand / accumulator stages wrap around and the phase
+    # parities of all mbarrier pipelines flip repeatedly (with 148 SMs these small cases give each CTA one tile)
+    monkeypatch.setenv("OPB_EMU_SMS", "3")
     return native
 
 
