@@ -67,8 +67,9 @@ void __tsan_release(void* addr);
 
 namespace emu {
 
-enum { READY = 0, WAIT_BLOCK = 1, WAIT_WARP = 2, DONE = 3 };
-constexpr int MAX_THREADS = 1024;
+enum { READY = 0, WAIT_BLOCK = 1, WAIT_WARP = 2, DONE = 3, WAIT_CLUSTER = 4 };
+constexpr int MAX_CTAS = 2;               // CTAs of one thread-block cluster resident together (CTA pairs)
+constexpr int MAX_THREADS = 1024 * MAX_CTAS;
 constexpr size_t STACK_BYTES = 256 * 1024;
 
 struct Fiber {
@@ -79,9 +80,11 @@ struct Fiber {
   int state = DONE;
   unsigned mask = 0;
   int pred = 0;
+  int cta = 0;       // CTA of the cluster this thread belongs to
   int site = 0;      // which warp-level primitive (and which half of it) the fiber waits in
   long long nwaits = 0;
   long long nblock = 0;   // block-level barriers passed
+  long long ncluster = 0; // cluster-level barriers passed
   uint3 tid;
 };
 
@@ -92,9 +95,14 @@ inline void* g_sched_sp = nullptr;
 inline void* g_sched_tsan = nullptr;
 // happens-before tokens: one per barrier GENERATION (a fiber that is resumed late must not pick up what faster
 // fibers released when they arrived at the NEXT barrier); participants are at most one generation apart
-inline char g_hb_block[4], g_hb_warp[MAX_THREADS / 32][4], g_hb_done;
+inline char g_hb_block[MAX_CTAS][4], g_hb_warp[MAX_THREADS / 32][4], g_hb_cluster[4], g_hb_done;
 inline const std::function<void()>* g_body = nullptr;
-inline int g_red_or = 0, g_red_and = 0, g_red_cnt = 0;
+inline int g_red_or[MAX_CTAS], g_red_and[MAX_CTAS], g_red_cnt[MAX_CTAS];
+struct CtaCtx { uint3 bid; unsigned char* dyn = nullptr; };
+inline CtaCtx g_cta[MAX_CTAS];
+inline int g_ncta = 1, g_cur_cta = 0, g_cta_threads = 0;
+inline long long g_cluster_launches = 0;
+inline int g_cluster_request = 0;   // set by a cluster primitive reached in a non-cluster launch: rerun as CTA pairs
 inline uint64_t g_warp_buf[MAX_THREADS / 32][32];
 inline int g_warp_pred[MAX_THREADS / 32][32];
 inline unsigned char* g_dyn_smem = nullptr;   // exactly the launch's dynamic shared memory (a heap block: ASan sees overruns)
@@ -122,7 +130,9 @@ EMU_INTERNAL inline void yield_wait(int state) {
   Fiber& f = g_fibers[g_cur];
   f.state = state;
 #ifdef EMU_TSAN
-  void* hb = (state == WAIT_BLOCK) ? static_cast<void*>(&g_hb_block[f.nblock++ & 3]) : static_cast<void*>(&g_hb_warp[g_cur >> 5][f.nwaits & 3]);
+  void* hb = (state == WAIT_BLOCK)     ? static_cast<void*>(&g_hb_block[f.cta][f.nblock++ & 3])
+             : (state == WAIT_CLUSTER) ? static_cast<void*>(&g_hb_cluster[f.ncluster++ & 3])
+                                       : static_cast<void*>(&g_hb_warp[g_cur >> 5][f.nwaits & 3]);   // (a warp never spans CTAs: threads per CTA % 32 == 0 in cluster launches)
   __tsan_release(hb);                       // everything before the barrier ...
   __tsan_switch_to_fiber(g_sched_tsan, 1);  // (1 = no implicit synchronisation at the switch)
 #endif
@@ -148,14 +158,18 @@ EMU_INTERNAL inline void fiber_trampoline() {
 }
 #endif
 
-EMU_INTERNAL inline void run_block(int nthreads, const std::function<void()>& body) {
-  if (nthreads > MAX_THREADS) { fprintf(stderr, "emu: block of %d threads\n", nthreads); abort(); }
-  g_nfib = nthreads;
+// Runs the g_ncta CTAs of one cluster (1, or 2 for CTA pairs) to completion: nthreads threads each.  Returns false
+// when a thread reached a cluster primitive in a non-cluster launch (the launch is then repeated as CTA pairs).
+EMU_INTERNAL inline bool run_block(int nthreads, const std::function<void()>& body) {
+  const int total = nthreads * g_ncta;
+  if (total > MAX_THREADS || (g_ncta > 1 && (nthreads & 31))) { fprintf(stderr, "emu: %d CTA(s) of %d threads\n", g_ncta, nthreads); abort(); }
+  g_nfib = total;
+  g_cta_threads = nthreads;
   g_body = &body;
 #ifdef EMU_TSAN
   g_sched_tsan = __tsan_get_current_fiber();
 #endif
-  for (int i = 0; i < nthreads; ++i) {
+  for (int i = 0; i < total; ++i) {
     Fiber& f = g_fibers[i];
     if (!f.stack) f.stack = static_cast<char*>(malloc(STACK_BYTES));
 #ifdef EMU_FAST_SWITCH
@@ -177,22 +191,28 @@ EMU_INTERNAL inline void run_block(int nthreads, const std::function<void()>& bo
     f.state = READY;
     f.nwaits = 0;
     f.nblock = 0;
+    f.ncluster = 0;
+    f.cta = i / nthreads;
 #ifdef EMU_TSAN
     f.tsan = __tsan_create_fiber(0);
 #endif
-    f.tid.x = i % g_bdim.x;
-    f.tid.y = (i / g_bdim.x) % g_bdim.y;
-    f.tid.z = i / (g_bdim.x * g_bdim.y);
+    const int t = i % nthreads;
+    f.tid.x = t % g_bdim.x;
+    f.tid.y = (t / g_bdim.x) % g_bdim.y;
+    f.tid.z = t / (g_bdim.x * g_bdim.y);
   }
   for (;;) {
     bool ran = false;
-    for (int k = 0; k < nthreads; ++k) {
+    for (int k = 0; k < total; ++k) {
       // OPB_EMU_ORDER=reverse: highest thread first.  Code that is correct under independent thread scheduling
       // gives the same result for any order; lane-0-first and lane-31-first bracket the usual hazards.
-      const int i = g_reverse ? nthreads - 1 - k : k;
+      const int i = g_reverse ? total - 1 - k : k;
       if (g_fibers[i].state != READY) continue;
       g_cur = i;
       g_tid = g_fibers[i].tid;
+      g_cur_cta = g_fibers[i].cta;
+      g_bid = g_cta[g_cur_cta].bid;
+      g_dyn_smem = g_cta[g_cur_cta].dyn;
 #ifdef EMU_TSAN
       __tsan_switch_to_fiber(g_fibers[i].tsan, 1);
 #endif
@@ -202,22 +222,29 @@ EMU_INTERNAL inline void run_block(int nthreads, const std::function<void()>& bo
       swapcontext(&g_sched, &g_fibers[i].ctx);
 #endif
       ran = true;
+      if (g_cluster_request && g_ncta == 1) {   // abandon this attempt (nothing but shared memory was touched yet)
+#ifdef EMU_TSAN
+        for (int q = 0; q < total; ++q) { __tsan_destroy_fiber(g_fibers[q].tsan); g_fibers[q].tsan = nullptr; }
+#endif
+        return false;
+      }
     }
     // warp-level barriers: release a group when every live lane of its mask waits
     bool released = false;
-    for (int base = 0; base < nthreads; base += 32) {
-      for (int l = 0; l < 32 && base + l < nthreads; ++l) {
+    for (int base = 0; base < total; base += 32) {
+      const int wend = std::min(base + 32, (base / nthreads + 1) * nthreads);   // a warp never spans two CTAs
+      for (int l = 0; base + l < wend; ++l) {
         Fiber& f = g_fibers[base + l];
         if (f.state != WAIT_WARP) continue;
         bool all = true;
-        for (int j = 0; j < 32 && base + j < nthreads; ++j) {
+        for (int j = 0; base + j < wend; ++j) {
           if (!((f.mask >> j) & 1u)) continue;
-          const int s = g_fibers[base + j].state;
-          if (s == DONE) continue;
-          if (s != WAIT_WARP || g_fibers[base + j].mask != f.mask) { all = false; break; }
+          const int st = g_fibers[base + j].state;
+          if (st == DONE) continue;
+          if (st != WAIT_WARP || g_fibers[base + j].mask != f.mask) { all = false; break; }
         }
         if (!all) continue;
-        for (int j = 0; j < 32 && base + j < nthreads; ++j) {   // convergence check: same primitive, same count
+        for (int j = 0; base + j < wend; ++j) {   // convergence check: same primitive, same count
           const Fiber& o = g_fibers[base + j];
           if (!((f.mask >> j) & 1u) || o.state != WAIT_WARP) continue;
           if (o.site != f.site || o.nwaits != f.nwaits) {
@@ -227,34 +254,46 @@ EMU_INTERNAL inline void run_block(int nthreads, const std::function<void()>& bo
           }
         }
         const unsigned m = f.mask;
-        for (int j = 0; j < 32 && base + j < nthreads; ++j)
+        for (int j = 0; base + j < wend; ++j)
           if (((m >> j) & 1u) && g_fibers[base + j].state == WAIT_WARP) g_fibers[base + j].state = READY;
         released = true;
       }
     }
     if (released) continue;
-    int live = 0, waiting = 0, r_or = 0, r_and = 1, r_cnt = 0;
-    for (int i = 0; i < nthreads; ++i) {
-      const Fiber& f = g_fibers[i];
-      if (f.state == DONE) continue;
-      ++live;
-      if (f.state == WAIT_BLOCK) { ++waiting; r_or |= (f.pred != 0); r_and &= (f.pred != 0); r_cnt += (f.pred != 0); }
+    // block-level barriers, per CTA; the cluster barrier over all CTAs
+    int live_all = 0, at_cluster = 0, at_block_all = 0;
+    for (int c = 0; c < g_ncta; ++c) {
+      int live = 0, waiting = 0, r_or = 0, r_and = 1, r_cnt = 0;
+      for (int i = c * nthreads; i < (c + 1) * nthreads; ++i) {
+        const Fiber& f = g_fibers[i];
+        if (f.state == DONE) continue;
+        ++live;
+        if (f.state == WAIT_CLUSTER) ++at_cluster;
+        if (f.state == WAIT_BLOCK) { ++waiting; r_or |= (f.pred != 0); r_and &= (f.pred != 0); r_cnt += (f.pred != 0); }
+      }
+      live_all += live;
+      at_block_all += waiting;
+      if (live && waiting == live) {
+        g_red_or[c] = r_or; g_red_and[c] = r_and; g_red_cnt[c] = r_cnt;
+        for (int i = c * nthreads; i < (c + 1) * nthreads; ++i) if (g_fibers[i].state == WAIT_BLOCK) g_fibers[i].state = READY;
+        released = true;
+      }
     }
-    if (live == 0) {
+    if (live_all == 0) {
 #ifdef EMU_TSAN
       __tsan_acquire(&g_hb_done);             // the block's writes are visible to later blocks / the host
-      for (int i = 0; i < nthreads; ++i) { __tsan_destroy_fiber(g_fibers[i].tsan); g_fibers[i].tsan = nullptr; }
+      for (int i = 0; i < total; ++i) { __tsan_destroy_fiber(g_fibers[i].tsan); g_fibers[i].tsan = nullptr; }
 #endif
-      break;
+      return true;
     }
-    if (waiting == live) {
-      g_red_or = r_or; g_red_and = r_and; g_red_cnt = r_cnt;
-      for (int i = 0; i < nthreads; ++i) if (g_fibers[i].state == WAIT_BLOCK) g_fibers[i].state = READY;
+    if (released) continue;
+    if (at_cluster == live_all) {
+      for (int i = 0; i < total; ++i) if (g_fibers[i].state == WAIT_CLUSTER) g_fibers[i].state = READY;
       continue;
     }
     if (!ran) {
-      fprintf(stderr, "emu: deadlock in block (%u,%u,%u): %d live, %d at __syncthreads, rest at divergent warp barriers\n",
-              g_bid.x, g_bid.y, g_bid.z, live, waiting);
+      fprintf(stderr, "emu: deadlock in block (%u,%u,%u): %d live threads, %d at __syncthreads, %d at the cluster barrier, rest at "
+              "divergent warp barriers\n", g_bid.x, g_bid.y, g_bid.z, live_all, at_block_all, at_cluster);
       abort();
     }
   }
@@ -267,25 +306,40 @@ struct Launcher {
   template <class... KA, class... A>
   void run(void (*k)(KA...), A&&... a) {
     if (smem > MAX_DYN_SMEM) { fprintf(stderr, "emu: %zu B of dynamic shared memory\n", smem); abort(); }
-    void* dyn = nullptr;   // 256 KB-aligned: the low 18 bits of a pointer into it are its shared-window address
-    if (posix_memalign(&dyn, 262144, smem ? smem : 1)) abort();
-    g_dyn_smem = static_cast<unsigned char*>(dyn);
-    g_dyn_smem_bytes = smem;
-    g_static_smem_hi = 0;
     std::tuple<std::decay_t<KA>...> args(std::forward<A>(a)...);
     const std::function<void()> body = [&] { std::apply(k, args); };
     g_bdim = b; g_gdim = g;
     ++g_launches;
     { const char* o = getenv("OPB_EMU_ORDER"); g_reverse = o && o[0] == 'r'; }
     const int nthreads = static_cast<int>(b.x * b.y * b.z);
-    for (unsigned z = 0; z < g.z; ++z)
-      for (unsigned y = 0; y < g.y; ++y)
-        for (unsigned x = 0; x < g.x; ++x) {
-          g_bid.x = x; g_bid.y = y; g_bid.z = z;
-          run_block(nthreads, body);
-        }
-    g_dyn_smem = nullptr;
-    free(dyn);
+    g_cluster_request = 0;
+    // A kernel declared with __cluster_dims__(2, 1, 1) reveals itself by reaching a cluster primitive: the first
+    // attempt is then abandoned and the grid is run as CTA pairs (both CTAs of a pair resident together).
+    for (int ncta = 1; ncta <= MAX_CTAS; ++ncta) {
+      g_ncta = ncta;
+      if (g.x % ncta) { fprintf(stderr, "emu: grid of %u blocks launched in clusters of %d\n", g.x, ncta); abort(); }
+      void* dyn[MAX_CTAS] = {nullptr, nullptr};   // 256 KB-aligned: the low 18 bits of a pointer into a block are its shared-window address
+      for (int c = 0; c < ncta; ++c) {
+        if (posix_memalign(&dyn[c], 262144, smem ? smem : 1)) abort();
+        g_cta[c].dyn = static_cast<unsigned char*>(dyn[c]);
+      }
+      g_dyn_smem_bytes = smem;
+      g_static_smem_hi = 0;
+      bool ok = true;
+      for (unsigned z = 0; z < g.z && ok; ++z)
+        for (unsigned y = 0; y < g.y && ok; ++y)
+          for (unsigned x = 0; x < g.x && ok; x += ncta) {
+            for (int c = 0; c < ncta; ++c) { g_cta[c].bid.x = x + c; g_cta[c].bid.y = y; g_cta[c].bid.z = z; }
+            g_bid = g_cta[0].bid;
+            g_dyn_smem = g_cta[0].dyn;
+            ok = run_block(nthreads, body);
+          }
+      g_dyn_smem = nullptr;
+      for (int c = 0; c < ncta; ++c) free(dyn[c]);
+      if (ok) { if (ncta > 1) ++g_cluster_launches; break; }
+      if (ncta == MAX_CTAS) { fprintf(stderr, "emu: cluster launch could not be completed\n"); abort(); }
+    }
+    g_ncta = 1;
   }
 };
 
@@ -294,8 +348,9 @@ struct Launcher {
   abort();
 }
 
-EMU_INTERNAL inline int lane_id() { return g_cur & 31; }
-EMU_INTERNAL inline int warp_id() { return g_cur >> 5; }
+EMU_INTERNAL inline int lane_id() { return (g_cur % g_cta_threads) & 31; }
+EMU_INTERNAL inline int warp_id() { return (g_cur % g_cta_threads) >> 5; }          // within the CTA
+EMU_INTERNAL inline int warp_slot() { return g_cur / g_cta_threads * ((g_cta_threads + 31) >> 5) + warp_id(); }   // exchange-buffer row
 EMU_INTERNAL inline void warp_wait(unsigned mask, int site) {
   Fiber& f = g_fibers[g_cur];
   f.mask = mask; f.site = site; ++f.nwaits;
@@ -307,9 +362,9 @@ EMU_INTERNAL inline T shfl_from(unsigned mask, T v, int src_lane) {
   static_assert(sizeof(T) <= 8, "shuffle payload");
   uint64_t bits = 0;
   memcpy(&bits, &v, sizeof(T));
-  g_warp_buf[warp_id()][lane_id()] = bits;
+  g_warp_buf[warp_slot()][lane_id()] = bits;
   warp_wait(mask, 10 + static_cast<int>(sizeof(T)));
-  const uint64_t r = g_warp_buf[warp_id()][src_lane & 31];
+  const uint64_t r = g_warp_buf[warp_slot()][src_lane & 31];
   warp_wait(mask, 20 + static_cast<int>(sizeof(T)));
   T out;
   memcpy(&out, &r, sizeof(T));
@@ -317,20 +372,20 @@ EMU_INTERNAL inline T shfl_from(unsigned mask, T v, int src_lane) {
 }
 
 EMU_INTERNAL inline unsigned ballot(unsigned mask, int pred) {
-  g_warp_pred[warp_id()][lane_id()] = pred != 0;
+  g_warp_pred[warp_slot()][lane_id()] = pred != 0;
   warp_wait(mask, 3);
   unsigned r = 0;
-  const int base = warp_id() * 32;
-  for (int j = 0; j < 32 && base + j < g_nfib; ++j)
-    if (((mask >> j) & 1u) && g_fibers[base + j].state != DONE && g_warp_pred[warp_id()][j]) r |= 1u << j;
+  const int base = g_cur - lane_id(), wend = (g_cur / g_cta_threads + 1) * g_cta_threads;
+  for (int j = 0; j < 32 && base + j < wend; ++j)
+    if (((mask >> j) & 1u) && g_fibers[base + j].state != DONE && g_warp_pred[warp_slot()][j]) r |= 1u << j;
   warp_wait(mask, 4);
   return r;
 }
 
 EMU_INTERNAL inline unsigned live_mask(unsigned mask) {
   unsigned r = 0;
-  const int base = warp_id() * 32;
-  for (int j = 0; j < 32 && base + j < g_nfib; ++j)
+  const int base = g_cur - lane_id(), wend = (g_cur / g_cta_threads + 1) * g_cta_threads;
+  for (int j = 0; j < 32 && base + j < wend; ++j)
     if (((mask >> j) & 1u) && g_fibers[base + j].state != DONE) r |= 1u << j;
   return r;
 }
@@ -346,9 +401,9 @@ constexpr int warpSize = 32;
 
 // ---- synchronisation ---------------------------------------------------------------------------
 EMU_INTERNAL inline void __syncthreads() { emu::g_fibers[emu::g_cur].pred = 0; emu::yield_wait(emu::WAIT_BLOCK); }
-EMU_INTERNAL inline int __syncthreads_or(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_or; }
-EMU_INTERNAL inline int __syncthreads_and(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_and; }
-EMU_INTERNAL inline int __syncthreads_count(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_cnt; }
+EMU_INTERNAL inline int __syncthreads_or(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_or[emu::g_cur_cta]; }
+EMU_INTERNAL inline int __syncthreads_and(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_and[emu::g_cur_cta]; }
+EMU_INTERNAL inline int __syncthreads_count(int p) { emu::g_fibers[emu::g_cur].pred = p; emu::yield_wait(emu::WAIT_BLOCK); return emu::g_red_cnt[emu::g_cur_cta]; }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_wait(mask, 1); }
 template <class T> inline T __shfl_sync(unsigned m, T v, int src, int width = 32) {
   const int l = emu::lane_id();

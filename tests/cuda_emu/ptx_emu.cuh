@@ -16,7 +16,9 @@
 //              Operands are fetched through the UMMA shared-memory descriptors (K-major, SWIZZLE_128B: start address,
 //              stride between 8-row groups, address-bit swizzle), fp16 x fp16 products accumulated in fp32.
 //              tcgen05.ld.32x32b checks that a warp only touches its own lane quadrant.
-//   cluster    CTA pairs (cta_group::2, multicast, mapa) are not modelled: those wrappers trap (run with OPB_PAIR=0).
+//   cluster    CTA pairs: both CTAs of a pair are resident together (cuda_emu.h); mapa / remote mbarrier arrive /
+//              cta_group::2 TMA crediting the leader's barriers / M = 256 MMA over both CTAs' operands and TMEM /
+//              multicast commit are modelled.  Larger clusters and TMA multicast are not.
 // Accumulation order inside an MMA is unspecified on hardware; here it is k-ascending in fp32, so results agree with the
 // GPU to rounding, not bit for bit -- the conv parity tests use the same tolerances on both.
 #pragma once
@@ -62,8 +64,8 @@ EMU_INTERNAL inline uint32_t smem_addr_of(const void* p) {
   if (hi != g_static_smem_hi) { fprintf(stderr, "emu: static __shared__ operands straddle a 256 KB host boundary (emulation limit)\n"); abort(); }
   return static_cast<uint32_t>(a & 0x3FFFF);
 }
-EMU_INTERNAL inline unsigned char* smem_ptr(uint32_t addr) {
-  if (addr < g_dyn_smem_bytes) return g_dyn_smem + addr;
+EMU_INTERNAL inline unsigned char* smem_ptr(uint32_t addr, int cta = -1) {   // cta < 0: the running thread's CTA
+  if (addr < g_dyn_smem_bytes) return (cta < 0 ? g_dyn_smem : g_cta[cta].dyn) + addr;
   if (!g_static_smem_hi) { fprintf(stderr, "emu: shared-window address 0x%x outside the launch's shared memory\n", addr); abort(); }
   return reinterpret_cast<unsigned char*>(g_static_smem_hi | addr);
 }
@@ -99,47 +101,80 @@ EMU_INTERNAL inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
   mbar_check(b);
 }
 
-struct QueuedMma { uint32_t tmem_d; uint64_t adesc, bdesc; uint32_t idesc; uint32_t accumulate; };
+struct QueuedMma { uint32_t tmem_d; uint64_t adesc, bdesc; uint32_t idesc; uint32_t accumulate; int pair; };
 inline std::vector<QueuedMma> g_mma_queue[MAX_THREADS];   // per issuing thread, flushed by its tcgen05.commit
-inline float g_tmem[128][512];
-inline bool g_tmem_allocated = false;
+inline float g_tmem[MAX_CTAS][128][512];
+inline bool g_tmem_allocated[MAX_CTAS] = {false, false};
 inline long long g_mma_count = 0, g_tma_count = 0;
 
 EMU_INTERNAL inline uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
 
-EMU_INTERNAL inline float half_at(uint32_t addr) {
+EMU_INTERNAL inline float half_at(uint32_t addr, int cta) {
   __half h;
-  EMU_RACE_READ(smem_ptr(swz128(addr)), 2);
-  memcpy(&h, smem_ptr(swz128(addr)), 2);
+  EMU_RACE_READ(smem_ptr(swz128(addr), cta), 2);
+  memcpy(&h, smem_ptr(swz128(addr), cta), 2);
   return __half2float(h);
 }
 
-__attribute__((optimize("O3"))) EMU_INTERNAL inline void execute_mma(const QueuedMma& q) {
+// cta_group::1: D[128 x N] in the issuing CTA's TMEM.  cta_group::2 (pair): M = 256 -- rows 0..127 are CTA 0's A operand
+// and accumulate in CTA 0's TMEM, rows 128..255 CTA 1's; the B operand's rows 0..N/2-1 come from CTA 0's shared memory and
+// rows N/2..N-1 from CTA 1's, each through the same descriptor.
+__attribute__((optimize("O3"))) EMU_INTERNAL inline void execute_mma(const QueuedMma& q, int issuer_cta) {
   const int N = static_cast<int>((q.idesc >> 17) & 0x3f) << 3, M = static_cast<int>((q.idesc >> 24) & 0x1f) << 4;
-  if (M != 128 || N < 8 || N > 256 || ((q.idesc >> 15) & 3u) != 0 || ((q.idesc >> 4) & 3u) != 1) {
-    fprintf(stderr, "emu: unsupported tcgen05.mma instruction descriptor 0x%x (M=%d N=%d)\n", q.idesc, M, N); abort();
+  if (M != (q.pair ? 256 : 128) || N < 8 || N > 256 || (q.pair && (N & 15)) || ((q.idesc >> 15) & 3u) != 0 || ((q.idesc >> 4) & 3u) != 1) {
+    fprintf(stderr, "emu: unsupported tcgen05.mma instruction descriptor 0x%x (M=%d N=%d cta_group::%d)\n", q.idesc, M, N, q.pair ? 2 : 1); abort();
   }
   if ((q.adesc >> 61) != 2 || (q.bdesc >> 61) != 2) { fprintf(stderr, "emu: only SWIZZLE_128B K-major operands are modelled\n"); abort(); }
+  if (q.pair && (issuer_cta != 0 || g_ncta != 2)) { fprintf(stderr, "emu: cta_group::2 MMA must be issued by the leader CTA of a pair\n"); abort(); }
   const uint32_t a0 = static_cast<uint32_t>(q.adesc & 0x3FFF) << 4, b0 = static_cast<uint32_t>(q.bdesc & 0x3FFF) << 4;
   const uint32_t a_sbo = static_cast<uint32_t>((q.adesc >> 32) & 0x3FFF) << 4, b_sbo = static_cast<uint32_t>((q.bdesc >> 32) & 0x3FFF) << 4;
   const uint32_t dcol = q.tmem_d & 0xffff, dlane = q.tmem_d >> 16;
   if (dlane != 0 || dcol + N > 512) { fprintf(stderr, "emu: tcgen05.mma accumulator outside TMEM (lane %u col %u N %d)\n", dlane, dcol, N); abort(); }
   static float A[128][16], Bt[16][256];
-  for (int m = 0; m < 128; ++m)
-    for (int k = 0; k < 16; ++k) A[m][k] = half_at(a0 + (m >> 3) * a_sbo + (m & 7) * 128 + 2 * k);
-  for (int n = 0; n < N; ++n)
-    for (int k = 0; k < 16; ++k) Bt[k][n] = half_at(b0 + (n >> 3) * b_sbo + (n & 7) * 128 + 2 * k);
-  for (int m = 0; m < 128; ++m) {      // per element: acc = (((d + a0*b0) + a1*b1) + ...), k ascending; vectorises over n
-    float* d = &g_tmem[m][dcol];
-    EMU_RACE_WRITE(d, 4ul * N);
-    if (!q.accumulate) for (int n = 0; n < N; ++n) d[n] = 0.f;
-    for (int k = 0; k < 16; ++k) {
-      const float a = A[m][k];
-      const float* b = Bt[k];
-      for (int n = 0; n < N; ++n) d[n] += a * b[n];
+  const int nhalf = q.pair ? N / 2 : N;
+  for (int n = 0; n < N; ++n) {
+    const int src_cta = q.pair ? n / nhalf : issuer_cta, row = q.pair ? n % nhalf : n;
+    for (int k = 0; k < 16; ++k) Bt[k][n] = half_at(b0 + (row >> 3) * b_sbo + (row & 7) * 128 + 2 * k, src_cta);
+  }
+  for (int half = 0; half < (q.pair ? 2 : 1); ++half) {
+    const int cta = q.pair ? half : issuer_cta;
+    for (int m = 0; m < 128; ++m)
+      for (int k = 0; k < 16; ++k) A[m][k] = half_at(a0 + (m >> 3) * a_sbo + (m & 7) * 128 + 2 * k, cta);
+    for (int m = 0; m < 128; ++m) {    // per element: acc = (((d + a0*b0) + a1*b1) + ...), k ascending; vectorises over n
+      float* d = &g_tmem[cta][m][dcol];
+      EMU_RACE_WRITE(d, 4ul * N);
+      if (!q.accumulate) for (int n = 0; n < N; ++n) d[n] = 0.f;
+      for (int k = 0; k < 16; ++k) {
+        const float a = A[m][k];
+        const float* b = Bt[k];
+        for (int n = 0; n < N; ++n) d[n] += a * b[n];
+      }
     }
   }
   ++g_mma_count;
+}
+
+// shared::cluster addresses (mapa): bits 28.. = CTA rank + 1, low bits = the shared-window address inside that CTA
+EMU_INTERNAL inline uint32_t cluster_addr(uint32_t local, uint32_t rank) { return ((rank + 1u) << 28) | local; }
+EMU_INTERNAL inline uint64_t* cluster_bar(uint32_t caddr) {
+  const int rank = static_cast<int>(caddr >> 28) - 1;
+  if (rank < 0 || rank >= g_ncta) { fprintf(stderr, "emu: bad shared::cluster address 0x%x\n", caddr); abort(); }
+  return reinterpret_cast<uint64_t*>(smem_ptr(caddr & 0x0FFFFFFFu, rank));
+}
+EMU_INTERNAL inline void need_cluster() {   // a cluster primitive in a single-CTA attempt: ask the launcher for CTA pairs
+  if (g_ncta > 1) return;
+  g_cluster_request = 2;
+  Fiber& f = g_fibers[g_cur];
+  f.state = DONE;
+#ifdef EMU_TSAN
+  __tsan_switch_to_fiber(g_sched_tsan, 1);
+#endif
+#ifdef EMU_FAST_SWITCH
+  emu_switch(&f.sp, g_sched_sp);
+#else
+  swapcontext(&f.ctx, &g_sched);
+#endif
+  abort();   // never resumed
 }
 
 EMU_INTERNAL inline void yield_ready() {   // spin-wait: let the other threads of the block run
@@ -242,30 +277,30 @@ EMU_INTERNAL inline void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint6
 template <int kCols>
 EMU_INTERNAL inline void tmem_alloc(uint32_t* smem_result) {
   if (emu::lane_id() == 0) {   // .sync.aligned: one allocation per warp-wide call
-    if (emu::g_tmem_allocated) { fprintf(stderr, "emu: second tcgen05.alloc in one CTA\n"); abort(); }
-    emu::g_tmem_allocated = true;
-    for (auto& row : emu::g_tmem) for (float& v : row) v = __builtin_nanf("");   // fresh TMEM holds garbage
+    if (emu::g_tmem_allocated[emu::g_cur_cta]) { fprintf(stderr, "emu: second tcgen05.alloc in one CTA\n"); abort(); }
+    emu::g_tmem_allocated[emu::g_cur_cta] = true;
+    for (auto& row : emu::g_tmem[emu::g_cur_cta]) for (float& v : row) v = __builtin_nanf("");   // fresh TMEM holds garbage
     *smem_result = 0;
   }
 }
 template <int kCols>
 EMU_INTERNAL inline void tmem_dealloc(uint32_t) {
   if (emu::lane_id() == 0) {
-    for (int t = 0; t < emu::g_nfib; ++t)
+    for (int t = emu::g_cur_cta * emu::g_cta_threads; t < (emu::g_cur_cta + 1) * emu::g_cta_threads; ++t)
       if (!emu::g_mma_queue[t].empty()) { fprintf(stderr, "emu: %zu tcgen05.mma issued by thread %d were never committed\n", emu::g_mma_queue[t].size(), t); abort(); }
-    emu::g_tmem_allocated = false;
+    emu::g_tmem_allocated[emu::g_cur_cta] = false;
   }
 }
 inline void tc_fence_before() {}
 inline void tc_fence_after() {}
 EMU_INTERNAL inline void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, accumulate});
+  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, accumulate, 0});
 }
 EMU_INTERNAL inline void mma_f16_ss_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, 1u});
+  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, 1u, 0});
 }
 EMU_INTERNAL inline void mma_commit(uint64_t* bar) {
-  for (const emu::QueuedMma& q : emu::g_mma_queue[emu::g_cur]) emu::execute_mma(q);
+  for (const emu::QueuedMma& q : emu::g_mma_queue[emu::g_cur]) emu::execute_mma(q, emu::g_cur_cta);
   emu::g_mma_queue[emu::g_cur].clear();
   emu::mbar_arrive_n(bar, 1);
 }
@@ -276,7 +311,7 @@ EMU_INTERNAL inline void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
     fprintf(stderr, "emu: tcgen05.ld outside the warp's lane quadrant / TMEM (warp %d lane base %u col %u)\n", emu::warp_id(), lane0, col);
     abort();
   }
-  const float* src = &emu::g_tmem[lane0 + static_cast<uint32_t>(emu::lane_id())][col];
+  const float* src = &emu::g_tmem[emu::g_cur_cta][lane0 + static_cast<uint32_t>(emu::lane_id())][col];
   EMU_RACE_READ(src, 4ul * NCOL);
   memcpy(r, src, 4 * NCOL);
 }
@@ -284,21 +319,46 @@ EMU_INTERNAL inline void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
 EMU_INTERNAL inline void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_cols<16>(taddr, r); }
 inline void tmem_ld_wait() {}
 
-// ---------------------------------------------------------------- CTA pairs: not modelled
-inline uint32_t cluster_ctarank() { return 0; }
-inline void cluster_sync_all() { emu::unsupported_ptx(); }
-inline uint32_t mapa_u32(uint32_t, uint32_t) { emu::unsupported_ptx(); }
-inline void mbar_arrive_cluster(uint32_t) { emu::unsupported_ptx(); }
-inline void tma_load_2d_pair(void*, const CUtensorMap*, uint32_t, int, int) { emu::unsupported_ptx(); }
-inline void tma_load_4d_pair(void*, const CUtensorMap*, uint32_t, int, int, int, int) { emu::unsupported_ptx(); }
-template <int kCols> inline void tmem_alloc_pair(uint32_t*) { emu::unsupported_ptx(); }
-template <int kCols> inline void tmem_dealloc_pair(uint32_t) { emu::unsupported_ptx(); }
-inline void mma_f16_ss_pair(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { emu::unsupported_ptx(); }
-inline void mma_f16_ss_pair_acc(uint32_t, uint64_t, uint64_t, uint32_t) { emu::unsupported_ptx(); }
-inline void mma_commit_pair(uint64_t*) { emu::unsupported_ptx(); }
+// ---------------------------------------------------------------- CTA pairs (cta_group::2): both CTAs resident
+EMU_INTERNAL inline uint32_t cluster_ctarank() { emu::need_cluster(); return static_cast<uint32_t>(emu::g_cur_cta); }
+EMU_INTERNAL inline void cluster_sync_all() { emu::need_cluster(); emu::yield_wait(emu::WAIT_CLUSTER); }
+EMU_INTERNAL inline uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) { emu::need_cluster(); return emu::cluster_addr(local_addr, rank); }
+EMU_INTERNAL inline void mbar_arrive_cluster(uint32_t cluster_addr) { emu::mbar_arrive_n(emu::cluster_bar(cluster_addr), 1); }
+// data lands in the ISSUING CTA's shared memory, the bytes are credited to the barrier at the cluster address
+EMU_INTERNAL inline void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int c0, int c1) {
+  const int c[2] = {c0, c1};
+  emu::tma_load(smem_dst, m, emu::cluster_bar(mbar_cluster_addr), c, 2);
+}
+EMU_INTERNAL inline void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int c0, int c1, int c2,
+                                          int c3) {
+  const int c[4] = {c0, c1, c2, c3};
+  emu::tma_load(smem_dst, m, emu::cluster_bar(mbar_cluster_addr), c, 4);
+}
+template <int kCols>
+EMU_INTERNAL inline void tmem_alloc_pair(uint32_t* smem_result) { emu::need_cluster(); tmem_alloc<kCols>(smem_result); }
+template <int kCols>
+EMU_INTERNAL inline void tmem_dealloc_pair(uint32_t taddr) { tmem_dealloc<kCols>(taddr); }
+EMU_INTERNAL inline void mma_f16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, accumulate, 1});
+}
+EMU_INTERNAL inline void mma_f16_ss_pair_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, 1u, 1});
+}
+// multicast commit: arrive (count 1) on the barrier at this offset in BOTH CTAs once the queued MMAs have run
+EMU_INTERNAL inline void mma_commit_pair(uint64_t* bar) {
+  for (const emu::QueuedMma& q : emu::g_mma_queue[emu::g_cur]) emu::execute_mma(q, emu::g_cur_cta);
+  emu::g_mma_queue[emu::g_cur].clear();
+  const uint32_t off = emu::smem_addr_of(bar);
+  for (int c = 0; c < emu::g_ncta; ++c) emu::mbar_arrive_n(reinterpret_cast<uint64_t*>(emu::smem_ptr(off, c)), 1);
+}
 
 // descriptor encodings: the kernels' own (pasted from csrc/ptx.cuh by build_emu.py)
 // @@DESCRIPTORS@@
 
 }  // namespace ptx
 }  // namespace opb
+
+// counters for the tests: [0] kernel launches, [1] of them as CTA pairs, [2] tcgen05.mma executed, [3] TMA loads
+extern "C" void opb_emu_stats(long long* out) {
+  out[0] = emu::g_launches; out[1] = emu::g_cluster_launches; out[2] = emu::g_mma_count; out[3] = emu::g_tma_count;
+}

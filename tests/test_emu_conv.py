@@ -8,8 +8,9 @@ sources (descriptor arithmetic, swizzled operand layouts, pipeline phase bookkee
 epilogues, max-pool fusion, split-fp16 two-level accumulation) execute on the CPU and are compared with a torch fp32
 conv2d / the oracle's forward pass under the SAME tolerances as tests/test_gpu_conv.py.
 
-Not modelled: CTA pairs (cta_group::2) -- OPB_PAIR=0 selects the single-CTA kernel for the fused 7x7 N=256 launch;
-timing, bank conflicts, and the hardware's accumulation order inside one MMA (results agree to rounding).
+CTA pairs (cta_group::2: the fused 7x7 N=256 launch) run with both CTAs of a pair resident together: remote mbarrier
+arrives, pair TMA crediting the leader's barriers, M=256 MMAs over both CTAs' operands / TMEM, multicast commits.
+Not modelled: timing, bank conflicts, and the hardware's accumulation order inside one MMA (results agree to rounding).
 Test infrastructure only: the package never loads the emulated library."""
 import ctypes as C
 import os
@@ -41,7 +42,6 @@ def emu_lib():
 def emu_native(emu_lib, monkeypatch):
     native = pkg("_native")
     monkeypatch.setattr(native, "_lib", emu_lib)
-    monkeypatch.setenv("OPB_PAIR", "0")          # CTA-pair kernels are not modelled
     # 3 "SMs": every persistent CTA loops over many tiles, so operand / accumulator stages wrap around and the phase
     # parities of all mbarrier pipelines flip repeatedly (with 148 SMs these small cases give each CTA one tile)
     monkeypatch.setenv("OPB_EMU_SMS", "3")
@@ -81,6 +81,32 @@ def test_conv_vs_torch(engine, emu_native, case, mode):
     err = np.abs(y - ref).max()
     tol = (2e-3 if mode == "fast" else 1e-4) * scale
     assert err <= tol, "max abs err %.3e > tol %.3e (scale %.3f)" % (err, tol, scale)
+
+
+def _emu_stats(lib):
+    st = (C.c_longlong * 4)()
+    lib.opb_emu_stats(st)
+    return dict(launches=st[0], cluster_launches=st[1], mma=st[2], tma=st[3])
+
+
+@pytest.mark.parametrize("case", [(2, 24, 24, 185, 256, 7, 1), (1, 25, 28, 128, 256, 7, 1), (1, 24, 24, 256, 256, 3, 1),
+                                  (1, 24, 40, 128, 512, 1, 1)], ids=lambda c: "n%d_%dx%d_c%d_o%d_k%d" % c[:6])
+def test_cta_pair_kernel(emu_native, emu_lib, monkeypatch, case):
+    """conv_tcgen05_pair_kernel (cta_group::2) for every kernel family (OPB_PAIR=7; by default only the fused 7x7
+    N=256 launch uses it), fast precision; the emulator's counters prove that the launch really ran as CTA pairs."""
+    monkeypatch.setenv("OPB_PAIR", "7")
+    n, h, w, cin, cout, ks, relu = case
+    rs = np.random.RandomState(sum(case))
+    x = rs.standard_normal((n, h, w, cin)).astype(np.float32)
+    W = (rs.standard_normal((cout, cin, ks, ks)) * np.sqrt(2.0 / (cin * ks * ks))).astype(np.float32)
+    b = (rs.standard_normal(cout) * 0.1).astype(np.float32)
+    eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params())
+    before = _emu_stats(emu_lib)
+    y = eng.test_conv(x, W, b, relu, emu_native.PRECISION_FAST)
+    after = _emu_stats(emu_lib)
+    assert after["cluster_launches"] == before["cluster_launches"] + 1 and after["mma"] > before["mma"] and after["tma"] > before["tma"]
+    ref = G._ref_conv(x, W, b, relu, quantize=True)
+    assert np.abs(y - ref).max() <= 2e-3 * np.abs(ref).max()
 
 
 def test_conv_zero_padding_borders(engine):
