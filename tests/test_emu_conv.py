@@ -134,3 +134,31 @@ def test_whole_network_forward(emu_native, he_weights, mode, tol):
     paf, heat = eng.forward(img[None])
     err = max(float(np.abs(paf[0] - ref_paf[0]).max()), float(np.abs(heat[0] - ref_heat[0]).max()))
     assert err <= tol, err
+
+
+def test_pose_detector_call_end_to_end(emu_native, monkeypatch):
+    """PoseDetector.__call__ (pose_detector.py:484-517) entirely under emulation: upload -> device cv2-exact resize ->
+    92-conv chain (CTA-pair kernel included) -> upsample -> peaks -> PAF integrals -> assignment -> grouping -> records
+    -> host rescale.  The network runs at a reduced inference size (176 instead of 368; the emulated tensor core does
+    ~4 GMAC/s) and in fast precision; the reference result is the oracle's post-process applied to the maps the same
+    engine returns from opb_forward for the same resized frame, so every stage after the network must agree bit for
+    bit, whatever fp16 rounding did to the maps."""
+    import cv2
+    entity, PD, syn = pkg("entity"), pkg("pose_detector"), pkg("synthetic")
+    monkeypatch.setitem(entity.params, "inference_img_size", 176)
+    monkeypatch.setitem(entity.params, "heatmap_size", 160)
+    monkeypatch.setenv("OPB_GRAPH", "0")
+    model = pkg("models.CocoPoseNet").CocoPoseNet()
+    model.load_npz(syn.he_weights(0))
+    det = PD.PoseDetector(model=model, device=0, precision="fast")
+    img = syn.procedural_image(150, 205, seed=9)                       # short side -> 176 (network input), 160 (maps)
+    poses, scores = det(img)
+    in_w, in_h = det.compute_optimal_size(img, 176)
+    map_w, map_h = det.compute_optimal_size(img, 160)
+    assert in_h == 176 and in_w % 8 == 0 and map_h == 160 and map_w % 8 == 0
+    paf_lo, heat_lo = det.engine.forward(cv2.resize(img, (in_w, in_h))[None])
+    pafs = R.resize_bilinear_align_corners(paf_lo, (map_h, map_w))[0]
+    heat = R.resize_bilinear_align_corners(heat_lo, (map_h, map_w))[0]
+    ref_poses, ref_scores = R.postprocess_fast(pafs, heat, map_w, img.shape[1], img.shape[0], map_h)
+    assert len(scores) > 0, "random-weight maps at this size give some 'persons'; an empty result tests nothing"
+    assert np.array_equal(scores, ref_scores) and np.array_equal(poses, ref_poses)
