@@ -188,7 +188,8 @@ struct opb_ctx {
   int two_streams = 1;             // OPB_TWO_STREAMS=0: both streaming slots share `stream` and one set of buffers
   int use_graphs = 1;              // OPB_GRAPH=0: streaming mode launches kernel by kernel
   // Experimental (default off until measured on a B200; bit-exactness is covered by tests/test_emu_postprocess.py):
-  int fused_peaks = 0;             // OPB_FUSED_PEAKS=1: the peak kernel interpolates its tiles from the low-res heat maps
+  int fused_peaks = 0;             // OPB_FUSED_PEAKS=1: the peak kernel interpolates its tiles from the low-res heat maps;
+                                   // =2: materialised maps, but the tile-skip bound comes from the low-res maps (no cell_max pass)
   int paf_lowres = 0;              // OPB_PAF_LOWRES=1: PAF line integrals sample the low-res PAFs on demand
   int conn_cap = kAssignMaxType;
   bool profile = false;                       // OPB_PROFILE=1: cudaEvent after every launch of a batch
@@ -956,8 +957,10 @@ int launch_upsample(opb_ctx* ctx, const float* in, int planes, int h, int w, flo
 // heat: [n][c_total][H][W]; fills ws->peaks / idx_list / type_start / peak_counts.
 // h_lo > 0: `heat` is the network-resolution map [n][c_total][h_lo][w_lo] and the peak kernel interpolates its tiles
 // from it (smooth_nms_lowres_kernel): the same peaks as upsampling to (H, W) first, without the full-resolution map.
+// heat_full != nullptr (with h_lo > 0): the materialised maps are read as usual and only the tile-skip bound comes from the
+// low-resolution maps (smooth_nms_loskip_kernel).
 int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total, int H, int W, int h_lo = 0,
-                 int w_lo = 0) {
+                 int w_lo = 0, const float* heat_full = nullptr) {
   const opb_params& p = ctx->prm;
   OPB_CUDA(ctx, cudaMemsetAsync(ws->peak_counts, 0, sizeof(int) * n, ctx->stream));
   OPB_CUDA(ctx, cudaMemsetAsync(ws->status, 0, sizeof(int) * n, ctx->stream));
@@ -976,10 +979,21 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
     if (!attr3) {
       OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_lowres_kernel<PK_R_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_lowres_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_loskip_kernel<PK_R_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_loskip_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr3 = true;
     }
     if (h_lo < 2 || w_lo < 2) OPB_FAIL(ctx, OPB_ERR_ARG, "low-resolution maps need at least 2 x 2 samples");
-    if (ctx->taps.radius == PK_R_FAST)
+    if (heat_full) {   // materialised maps, tile-skip bound from the low-resolution maps (no cell_max pass)
+      if (ctx->taps.radius == PK_R_FAST)
+        smooth_nms_loskip_kernel<PK_R_FAST><<<grid, PK_THREADS, smem, ctx->stream>>>(
+            heat_full, heat, c_total, c_use, h_lo, w_lo, H, W, ctx->taps, static_cast<float>(p.heatmap_peak_thresh),
+            ws->keys, ws->peak_counts, p.max_peaks);
+      else
+        smooth_nms_loskip_kernel<0><<<grid, PK_THREADS, smem, ctx->stream>>>(
+            heat_full, heat, c_total, c_use, h_lo, w_lo, H, W, ctx->taps, static_cast<float>(p.heatmap_peak_thresh),
+            ws->keys, ws->peak_counts, p.max_peaks);
+    } else if (ctx->taps.radius == PK_R_FAST)
       smooth_nms_lowres_kernel<PK_R_FAST><<<grid, PK_THREADS, smem, ctx->stream>>>(
           heat, c_total, c_use, h_lo, w_lo, H, W, ctx->taps, static_cast<float>(p.heatmap_peak_thresh), ws->keys,
           ws->peak_counts, p.max_peaks);
@@ -1580,8 +1594,12 @@ static int run_postprocess(opb_ctx* ctx, PostWs* ws, int n, int h8, int w8, int 
     if ((rc = launch_upsample(ctx, paf_lo, n * 38, h8, w8, ws->pafs, map_h, map_w))) return rc;
     prof_mark(ctx, "upsample_paf");
   }
-  if (ctx->fused_peaks) {
+  if (ctx->fused_peaks == 1) {
     if ((rc = launch_peaks(ctx, ws, heat_lo, n, 19, map_h, map_w, h8, w8))) return rc;
+  } else if (ctx->fused_peaks == 2) {
+    if ((rc = launch_upsample(ctx, heat_lo, n * 19, h8, w8, ws->heat, map_h, map_w))) return rc;
+    prof_mark(ctx, "upsample_heat");
+    if ((rc = launch_peaks(ctx, ws, heat_lo, n, 19, map_h, map_w, h8, w8, ws->heat))) return rc;
   } else {
     if ((rc = launch_upsample(ctx, heat_lo, n * 19, h8, w8, ws->heat, map_h, map_w))) return rc;
     prof_mark(ctx, "upsample_heat");
@@ -2119,7 +2137,8 @@ int opb_time_stage(opb_ctx* ctx, const char* stage, int reps, float* ms) {
       if (s == "upsample_paf") { ++n_launch; return launch_upsample(ctx, plo, n * 38, h8, w8, ws->pafs, ws->H, ws->W); }
       if (s == "upsample_heat") { ++n_launch; return launch_upsample(ctx, hlo, n * 19, h8, w8, ws->heat, ws->H, ws->W); }
       if (s == "peaks") {
-        if (ctx->fused_peaks) { n_launch += 2; return launch_peaks(ctx, ws, hlo, n, 19, ws->H, ws->W, h8, w8); }
+        if (ctx->fused_peaks == 1) { n_launch += 2; return launch_peaks(ctx, ws, hlo, n, 19, ws->H, ws->W, h8, w8); }
+        if (ctx->fused_peaks == 2) { n_launch += 2; return launch_peaks(ctx, ws, hlo, n, 19, ws->H, ws->W, h8, w8, ws->heat); }
         n_launch += 3;
         return launch_peaks(ctx, ws, ws->heat, n, 19, ws->H, ws->W);
       }

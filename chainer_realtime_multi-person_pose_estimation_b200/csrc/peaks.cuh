@@ -96,6 +96,9 @@ cell_max_kernel(const float* __restrict__ heat, int c_total, int c_use, int H, i
 #define OPB_PK_LOWRES 1
 #include "peaks_smooth_nms.inc"
 #undef OPB_PK_LOWRES
+#define OPB_PK_LOWRES 2
+#include "peaks_smooth_nms.inc"
+#undef OPB_PK_LOWRES
 
 inline size_t smooth_nms_smem_bytes(int radius) {
   const int IN_W = PK_TX + 2 + 2 * radius, IN_H = PK_TY + 2 + 2 * radius;

@@ -162,7 +162,7 @@ int opb_detect_batch(opb_ctx* ctx, const uint8_t* imgs, int imgs_loc, int n, int
  *    paf_lo [N,38,h8,w8] / heat_lo [N,19,h8,w8] float32 (host or device per maps_loc) -> F.resize_images to
  *    (map_h, map_w) -> peaks -> connections -> grouping, records as in opb_detect_batch.  For callers that run
  *    the network elsewhere, and the entry the no-GPU emulation tests drive (the conv chain cannot be emulated).
- *    With OPB_PAF_LOWRES=1 / OPB_FUSED_PEAKS=1 in the environment at opb_create (experimental, also honoured by
+ *    With OPB_PAF_LOWRES=1 / OPB_FUSED_PEAKS=1|2 in the environment at opb_create (experimental, also honoured by
  *    opb_detect_batch / opb_detect_image / opb_stream_submit) the PAF line integrals / the peak kernel interpolate
  *    from the low-resolution maps on demand instead of reading materialised full-resolution maps: same results
  *    bit for bit, without the 42 MB per 320x576 image of full-resolution maps going through HBM.            */

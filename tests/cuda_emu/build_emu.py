@@ -92,12 +92,14 @@ def build(contract=False, force=False):
     src_dir = os.path.join(BUILD, "src")
     os.makedirs(src_dir, exist_ok=True)
     lib = lib_path(contract)
-    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [
+    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if os.path.isfile(os.path.join(CSRC, f))] + [
         os.path.join(HERE, f) for f in ("cuda_emu.h", "ptx_emu.cuh", "emu_tmap.h", "emu_runtime.cpp", "build_emu.py")] + [
         os.path.join(ROOT, "include", "opb.h")]
     if not force and os.path.isfile(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
         return lib
     for f in sorted(os.listdir(CSRC)):
+        if not os.path.isfile(os.path.join(CSRC, f)):
+            continue
         with open(os.path.join(CSRC, f)) as fh:
             text = fh.read()
         if f == "ptx.cuh":

@@ -26,7 +26,7 @@ def test_postprocess_batch_default_path(monkeypatch):
 
 
 @pytest.mark.skipif(os.environ.get("OPB_TEST_EXPERIMENTAL", "0") != "1", reason="experimental low-res variants: set OPB_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("fused_peaks,paf_lowres", [(1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("fused_peaks,paf_lowres", [(1, 0), (2, 0), (0, 1), (1, 1), (2, 1)])
 def test_postprocess_batch_lowres_variants(monkeypatch, fused_peaks, paf_lowres):
     monkeypatch.setenv("OPB_FUSED_PEAKS", str(fused_peaks))
     monkeypatch.setenv("OPB_PAF_LOWRES", str(paf_lowres))

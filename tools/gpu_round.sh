@@ -17,7 +17,7 @@ for s in $STAGES; do
     batch) timeout 900 python -m pytest tests/test_gpu_postprocess_batch.py -m gpu -q --timeout 600 > gpurun_out/batch.log 2>&1; tail -n 10 gpurun_out/batch.log ;;
     lowres_ab)  # the experimental low-resolution post-process variants: parity on the GPU, then bench A/B (value, e2e, stage_ms)
            OPB_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_postprocess_batch.py -m gpu -q --timeout 600 > gpurun_out/lowres_parity.log 2>&1; tail -n 5 gpurun_out/lowres_parity.log
-           for K in "0 0" "1 0" "0 1" "1 1"; do set -- $K
+           for K in "0 0" "1 0" "2 0" "0 1" "1 1" "2 1"; do set -- $K
              OPB_FUSED_PEAKS=$1 OPB_PAF_LOWRES=$2 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity-extra > gpurun_out/bench_lowres_$1$2.log 2>&1
              python - "$1" "$2" <<'PY'
 import json, sys
