@@ -118,7 +118,7 @@ def test_conv_fused_maxpool(engine, mode):
     G.test_conv_fused_maxpool(engine, (2, 24, 40, 64, 64, 3), mode)
 
 
-@pytest.mark.parametrize("mode,tol", [("fast", 1e-2), ("parity", 1e-4)])
+@pytest.mark.parametrize("mode,tol", [("parity", 1e-4)])   # fast precision: test_pose_detector_call_end_to_end
 def test_whole_network_forward(emu_native, he_weights, mode, tol):
     """All 92 convolutions of CocoPoseNet (3 fused max-pools, concat-by-slice, fused 1x1 pairs, conv1_1 on tensor
     cores in fast precision / the split-fp16 DRAIN kernels in parity precision) on a 176x128 frame -- the smallest the

@@ -203,10 +203,16 @@ def test_postprocess_batch_from_network_resolution_maps(emu_native, monkeypatch,
     run_batch_cases(eng)
 
 
-def test_results_do_not_depend_on_the_order_threads_run_in(emu_native, monkeypatch):
+def _nofma_only(request):
+    if request.node.callspec.params["emu_lib"] == "fma":
+        pytest.skip("one build is enough for this case (suite time)")
+
+
+def test_results_do_not_depend_on_the_order_threads_run_in(emu_native, monkeypatch, request):
     """The emulator normally runs thread 0 first; OPB_EMU_ORDER=reverse runs the highest thread first.  Code that is
     correct under independent thread scheduling gives the same bits either way (and the convergence check must not
     fire): the whole post-process, default and low-resolution variants."""
+    _nofma_only(request)
     monkeypatch.setenv("OPB_EMU_ORDER", "reverse")
     for knobs in ((0, 0), (1, 1)):
         monkeypatch.setenv("OPB_FUSED_PEAKS", str(knobs[0]))
@@ -215,10 +221,11 @@ def test_results_do_not_depend_on_the_order_threads_run_in(emu_native, monkeypat
         run_batch_cases(eng)
 
 
-def test_weight_loading_and_repack_host_code(emu_native):
+def test_weight_loading_and_repack_host_code(emu_native, request):
     """opb_load_weights x92 + opb_finalize_weights (the K-major fp16 repack, hi/lo split, concat-order permutation and
     tensor-map construction are host code) for CocoPoseNet in both precisions and for FaceNet / HandNet, plus the error
     paths; run under the AddressSanitizer build (see tests/cuda_emu/build_emu.py) this is the memcheck of that code."""
+    _nofma_only(request)
     syn, PD = pkg("synthetic"), pkg("pose_detector")
     prm = PD.make_opb_params(max_peaks=512, max_candidates=4096, max_persons=32)
     model = pkg("models.CocoPoseNet").CocoPoseNet()
