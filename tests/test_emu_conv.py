@@ -162,3 +162,31 @@ def test_pose_detector_call_end_to_end(emu_native, monkeypatch):
     ref_poses, ref_scores = R.postprocess_fast(pafs, heat, map_w, img.shape[1], img.shape[0], map_h)
     assert len(scores) > 0, "random-weight maps at this size give some 'persons'; an empty result tests nothing"
     assert np.array_equal(scores, ref_scores) and np.array_equal(poses, ref_poses)
+
+
+@pytest.mark.parametrize("modname,cls,n_kp", [("models.FaceNet", "FaceNet", 70), ("models.HandNet", "HandNet", 21)])
+def test_face_and_hand_detectors_end_to_end(emu_native, modname, cls, n_kp):
+    """opb_keypoints_detect (face_detector.py:28-67 / hand_detector.py:28-77) under emulation: device cv2-exact resize of
+    the crop, the FaceNet / HandNet chain (7x7 (128+C)->128 concat layers, role-swapped 7x7, 1x1 pairs), F.resize_images to
+    the crop size, exact Gaussian passes and arg-max.  Network size reduced to 176 (emulation speed), fast precision: the
+    maps agree with the oracle's fp32 forward to fp16 accuracy, and the keypoints are exactly what the oracle's peak
+    finder returns for the device's own maps."""
+    syn = pkg("synthetic")
+    nm = pkg(modname)
+    wd = syn.he_weights(0, layers=nm.LAYERS)
+    net = getattr(nm, cls)()
+    net.load_npz(wd)
+    eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params(), emu_native.PRECISION_FAST)
+    eng.load_model(net)
+    crop = syn.procedural_image(120, 140, seed=21)
+    kps, maps = eng.keypoints_detect(crop, 176, 0.1, mirror=False, return_maps=True)
+    assert len(kps) == n_kp and sum(k is not None for k in kps) > 0
+    weights = {n: (wd[n + "/W"], wd[n + "/b"]) for n, _, _, _ in nm.LAYERS}
+    lo = R.keypoint_forward(weights, R.keypoint_preprocess(R.cv2_resize_linear_u8(np.ascontiguousarray(crop), (176, 176))))
+    ref_maps = R.resize_bilinear_align_corners(lo, crop.shape[:2])[0]
+    assert np.abs(maps - ref_maps[:-1]).max() <= 1e-2
+    full = np.concatenate([maps, np.zeros((1,) + maps.shape[1:], np.float32)])
+    for a, b in zip(kps, R.keypoints_from_heatmaps(full, 0.1)):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert (a[0], a[1]) == (b[0], b[1]) and np.float32(a[2]) == np.float32(b[2])
