@@ -191,6 +191,7 @@ struct opb_ctx {
   int fused_peaks = 0;             // OPB_FUSED_PEAKS=1: the peak kernel interpolates its tiles from the low-res heat maps;
                                    // =2: materialised maps, but the tile-skip bound comes from the low-res maps (no cell_max pass)
   int paf_lowres = 0;              // OPB_PAF_LOWRES=1: PAF line integrals sample the low-res PAFs on demand
+  int peaks_v2 = 0;                // OPB_PEAKS_V2=1 (with OPB_FUSED_PEAKS=2): smoothing passes spread over all 256 threads
   int conn_cap = kAssignMaxType;
   bool profile = false;                       // OPB_PROFILE=1: cudaEvent after every launch of a batch
   std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -984,7 +985,16 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
       attr3 = true;
     }
     if (h_lo < 2 || w_lo < 2) OPB_FAIL(ctx, OPB_ERR_ARG, "low-resolution maps need at least 2 x 2 samples");
-    if (heat_full) {   // materialised maps, tile-skip bound from the low-resolution maps (no cell_max pass)
+    if (heat_full && ctx->peaks_v2 && ctx->taps.radius == PK_R_FAST) {   // + both smoothing passes on all threads
+      static bool attr4 = false;
+      if (!attr4) {
+        OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_loskip_kernel_v2<PK_R_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr4 = true;
+      }
+      smooth_nms_loskip_kernel_v2<PK_R_FAST><<<grid, PK_THREADS, smem, ctx->stream>>>(
+          heat_full, heat, c_total, c_use, h_lo, w_lo, H, W, ctx->taps, static_cast<float>(p.heatmap_peak_thresh),
+          ws->keys, ws->peak_counts, p.max_peaks);
+    } else if (heat_full) {   // materialised maps, tile-skip bound from the low-resolution maps (no cell_max pass)
       if (ctx->taps.radius == PK_R_FAST)
         smooth_nms_loskip_kernel<PK_R_FAST><<<grid, PK_THREADS, smem, ctx->stream>>>(
             heat_full, heat, c_total, c_use, h_lo, w_lo, H, W, ctx->taps, static_cast<float>(p.heatmap_peak_thresh),
@@ -1179,6 +1189,7 @@ int opb_create(opb_ctx** out, int device, const opb_params* params) {
   if (const char* g = getenv("OPB_TWO_STREAMS")) ctx->two_streams = atoi(g);
   if (const char* g = getenv("OPB_FUSED_PEAKS")) ctx->fused_peaks = atoi(g);
   if (const char* g = getenv("OPB_PAF_LOWRES")) ctx->paf_lowres = atoi(g);
+  if (const char* g = getenv("OPB_PEAKS_V2")) ctx->peaks_v2 = atoi(g);
   *out = ctx;
   return OPB_OK;
 }

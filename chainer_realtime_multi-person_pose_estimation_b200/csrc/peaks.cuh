@@ -90,6 +90,9 @@ cell_max_kernel(const float* __restrict__ heat, int c_total, int c_use, int H, i
 //      order, float32 store between the passes) of the pixel and its four neighbours, and
 //      the reference's strict comparisons decide.  Results are bit-identical to the
 //      all-float64 kernel; B200's scalar fp64 rate (~1/8 of fp32) is paid only per candidate.
+// mode 0 with the default passes: exactly the profiled token stream (its SASS is pinned with tools/sass_diff.py)
+#define OPB_PK_NAME(n) n
+#define OPB_PK_SPLIT 0
 #define OPB_PK_LOWRES 0
 #include "peaks_smooth_nms.inc"
 #undef OPB_PK_LOWRES
@@ -99,6 +102,16 @@ cell_max_kernel(const float* __restrict__ heat, int c_total, int c_use, int H, i
 #define OPB_PK_LOWRES 2
 #include "peaks_smooth_nms.inc"
 #undef OPB_PK_LOWRES
+#undef OPB_PK_SPLIT
+#undef OPB_PK_NAME
+// experimental: both smoothing passes on all threads (OPB_PEAKS_V2=1), for the materialised-map modes
+#define OPB_PK_NAME(n) n##_v2
+#define OPB_PK_SPLIT 1
+#define OPB_PK_LOWRES 2
+#include "peaks_smooth_nms.inc"
+#undef OPB_PK_LOWRES
+#undef OPB_PK_SPLIT
+#undef OPB_PK_NAME
 
 inline size_t smooth_nms_smem_bytes(int radius) {
   const int IN_W = PK_TX + 2 + 2 * radius, IN_H = PK_TY + 2 + 2 * radius;

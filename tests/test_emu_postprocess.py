@@ -246,3 +246,14 @@ def test_weight_loading_and_repack_host_code(emu_native, request):
         eng._check(eng.lib.opb_finalize_weights(eng.ctx, 0))          # nothing loaded yet
     with pytest.raises(emu_native.OpbError):
         eng._check(eng.lib.opb_load_weights(eng.ctx, b"conv1_1", None, (C.c_int64 * 4)(64, 3, 3, 3), None))
+
+
+def test_peak_kernel_v2_same_bits(emu_native, monkeypatch, request):
+    """OPB_PEAKS_V2=1 (with OPB_FUSED_PEAKS=2): the float32 smoothing passes of the peak kernel spread over all 256
+    threads -- same sums in the same order, so every result must stay bit-identical."""
+    _nofma_only(request)
+    monkeypatch.setenv("OPB_FUSED_PEAKS", "2")
+    monkeypatch.setenv("OPB_PAF_LOWRES", "1")
+    monkeypatch.setenv("OPB_PEAKS_V2", "1")
+    eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params(max_peaks=4096, max_candidates=65536, max_persons=128))
+    run_batch_cases(eng)

@@ -31,3 +31,11 @@ def test_postprocess_batch_lowres_variants(monkeypatch, fused_peaks, paf_lowres)
     monkeypatch.setenv("OPB_FUSED_PEAKS", str(fused_peaks))
     monkeypatch.setenv("OPB_PAF_LOWRES", str(paf_lowres))
     run_batch_cases(_engine())
+
+
+@pytest.mark.skipif(os.environ.get("OPB_TEST_EXPERIMENTAL", "0") != "1", reason="experimental: set OPB_TEST_EXPERIMENTAL=1")
+def test_postprocess_batch_peak_kernel_v2(monkeypatch):
+    monkeypatch.setenv("OPB_FUSED_PEAKS", "2")
+    monkeypatch.setenv("OPB_PAF_LOWRES", "1")
+    monkeypatch.setenv("OPB_PEAKS_V2", "1")
+    run_batch_cases(_engine())

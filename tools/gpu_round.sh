@@ -28,7 +28,9 @@ try:
 except Exception as e:
     print("FUSED_PEAKS=%s PAF_LOWRES=%s failed: %s" % (a, b, e))
 PY
-           done ;;
+           done
+           OPB_FUSED_PEAKS=2 OPB_PAF_LOWRES=1 OPB_PEAKS_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity-extra > gpurun_out/bench_lowres_21_v2.log 2>&1
+           tail -c 400 gpurun_out/bench_lowres_21_v2.log ;;
     smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -n 5 gpurun_out/smoke.log ;;
     bench) timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; tail -n 3 gpurun_out/bench.log ;;
     benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -n 2 gpurun_out/bench_ref.log ;;
