@@ -108,7 +108,7 @@ inline int g_warp_pred[MAX_THREADS / 32][32];
 inline unsigned char* g_dyn_smem = nullptr;   // exactly the launch's dynamic shared memory (a heap block: ASan sees overruns)
 constexpr size_t MAX_DYN_SMEM = 232448;
 inline size_t g_dyn_smem_bytes = 0;
-inline uintptr_t g_static_smem_hi = 0;   // 256 KB-aligned host block holding the static __shared__ operands of this launch
+inline uintptr_t g_static_smem_hi = 0;   // host address that maps to the first shared-window address behind the dynamic window (static operands)
 inline uint3 g_tid, g_bid;
 inline dim3 g_bdim, g_gdim;
 inline long long g_launches = 0;

@@ -53,21 +53,27 @@ void __tsan_write_range(void* addr, unsigned long size);
 namespace emu {
 
 // Shared-window addresses (what cvta.to.shared yields on the GPU; UMMA descriptors keep 18 bits of them): a pointer
-// into the launch's dynamic shared memory maps to its offset (the block is 256 KB-aligned); a pointer to a static
-// __shared__ array maps to the low 18 bits of its host address, which requires that all static operands of one launch
-// lie in one 256 KB-aligned host block (checked).
+// into the launch's dynamic shared memory maps to its offset; static __shared__ arrays (host globals here) are mapped
+// behind the dynamic window, host-contiguously and 1024-byte congruent (the 128-byte swizzle depends on address bits
+// 7..9), centred on the first static pointer the launch converts -- all static operands of one launch must lie within the
+// remaining window (checked).
+EMU_INTERNAL inline uint32_t static_window_base() { return (static_cast<uint32_t>(g_dyn_smem_bytes) + 1023u) & ~1023u; }
 EMU_INTERNAL inline uint32_t smem_addr_of(const void* p) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p), d = reinterpret_cast<uintptr_t>(g_dyn_smem);
   if (g_dyn_smem_bytes && a >= d && a < d + g_dyn_smem_bytes) return static_cast<uint32_t>(a - d);
-  const uintptr_t hi = a & ~static_cast<uintptr_t>(0x3FFFF);
-  if (!g_static_smem_hi) g_static_smem_hi = hi;
-  if (hi != g_static_smem_hi) { fprintf(stderr, "emu: static __shared__ operands straddle a 256 KB host boundary (emulation limit)\n"); abort(); }
-  return static_cast<uint32_t>(a & 0x3FFFF);
+  const uint32_t win0 = static_window_base(), span = 0x40000u - win0;
+  if (!g_static_smem_hi) g_static_smem_hi = (a & ~static_cast<uintptr_t>(1023)) - ((span / 2) & ~1023u);
+  if (a < g_static_smem_hi || a - g_static_smem_hi >= span) {
+    fprintf(stderr, "emu: static __shared__ operands of one launch span more than the %u KB shared window left by its dynamic "
+            "shared memory (emulation limit)\n", span >> 10);
+    abort();
+  }
+  return win0 + static_cast<uint32_t>(a - g_static_smem_hi);
 }
 EMU_INTERNAL inline unsigned char* smem_ptr(uint32_t addr, int cta = -1) {   // cta < 0: the running thread's CTA
   if (addr < g_dyn_smem_bytes) return (cta < 0 ? g_dyn_smem : g_cta[cta].dyn) + addr;
-  if (!g_static_smem_hi) { fprintf(stderr, "emu: shared-window address 0x%x outside the launch's shared memory\n", addr); abort(); }
-  return reinterpret_cast<unsigned char*>(g_static_smem_hi | addr);
+  if (!g_static_smem_hi || addr < static_window_base()) { fprintf(stderr, "emu: shared-window address 0x%x outside the launch's shared memory\n", addr); abort(); }
+  return reinterpret_cast<unsigned char*>(g_static_smem_hi + (addr - static_window_base()));
 }
 
 inline const TensorMapRec* tmap_rec(const CUtensorMap* m) {
