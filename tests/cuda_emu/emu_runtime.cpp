@@ -91,9 +91,15 @@ static CUresult emu_cuTensorMapEncodeTiled(CUtensorMap* tm, CUtensorMapDataType 
     r->strides[d] = d ? strides[d - 1] : r->elem_bytes;
     r->box[d] = box[d];
     r->estr[d] = estr[d];
-    if (box[d] == 0 || box[d] > 256 || (d && (strides[d - 1] % 16))) { delete r; return CUDA_ERROR_INVALID_VALUE; }
+    // the documented constraints of the real encoder (cuda.h): box <= 256, traversal stride 1..8, strides multiples
+    // of 16 bytes and < 2^40, non-empty dimensions <= 2^32
+    if (box[d] == 0 || box[d] > 256 || estr[d] == 0 || estr[d] > 8 || dims[d] == 0 || dims[d] > (1ull << 32) ||
+        (d && ((strides[d - 1] % 16) || strides[d - 1] >= (1ull << 40)))) { delete r; return CUDA_ERROR_INVALID_VALUE; }
   }
-  if (reinterpret_cast<uintptr_t>(base) % 16) { delete r; return CUDA_ERROR_INVALID_VALUE; }
+  static const uint32_t kSwizzleSpan[] = {0, 32, 64, 128};       // NONE, 32B, 64B, 128B: inner box bytes must fit the span
+  const uint32_t inner = box[0] * r->elem_bytes;
+  if (reinterpret_cast<uintptr_t>(base) % 16 || inner % 16 ||
+      (r->swizzle >= 1 && r->swizzle <= 3 && inner > kSwizzleSpan[r->swizzle])) { delete r; return CUDA_ERROR_INVALID_VALUE; }
   memset(tm, 0, sizeof(*tm));
   memcpy(tm, &r, sizeof(r));
   return CUDA_SUCCESS;
