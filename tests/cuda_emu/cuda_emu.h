@@ -1,22 +1,23 @@
 // cuda_emu.h -- TEST INFRASTRUCTURE ONLY (never loaded by the package).
 //
-// A single-OS-thread emulation of the CUDA execution model, just large enough to run the
-// library's plain-CUDA kernels (post-process, resize, keypoints) from the *unmodified* kernel
-// sources on a box without a GPU, so that `pytest -m "not gpu"` can check their arithmetic
-// bit-for-bit against the oracle:
+// A single-OS-thread emulation of the CUDA execution model, large enough to run the library's *unmodified* kernel
+// sources (post-process, resize, keypoints, and -- with ptx_emu.cuh -- the tcgen05 / TMA convolution kernels) on a box
+// without a GPU, so that `pytest -m "not gpu"` can check device code against the oracle:
 //
-//   * every CUDA thread of a block is a ucontext fiber; blocks run one after another;
-//   * __syncthreads / __syncthreads_or / __syncwarp / shuffles / ballots are cooperative
-//     yields to a scheduler that releases a barrier when all live participants wait on it;
-//   * __shared__ variables become function statics (one block is resident at a time), the
-//     dynamic shared memory window is one static buffer;
-//   * atomics are plain read-modify-writes (one OS thread), __ldg/__stcs plain accesses;
-//   * the _rn arithmetic intrinsics are single IEEE operations fenced against contraction, so
-//     the emulated build may be compiled with -ffp-contract=fast to expose any arithmetic that
-//     would depend on nvcc's FMA contraction.
+//   * every CUDA thread is a fiber (hand-written x86-64 context switch, ucontext elsewhere); the CTAs of a grid run one
+//     after another, the two CTAs of a CTA pair together;
+//   * __syncthreads* / __syncwarp / shuffles / votes / the cluster barrier are cooperative yields to a scheduler that
+//     releases a barrier when all live participants wait on it, checks that the lanes of a warp wait in the SAME
+//     primitive (code that only works under lockstep execution aborts), and detects deadlocks;
+//   * __shared__ variables become function statics (one CTA per cluster slot is resident at a time), the dynamic shared
+//     memory window of a launch is an exact-size heap block;
+//   * atomics are relaxed atomics, __ldg/__stcs plain accesses;
+//   * the _rn arithmetic intrinsics are single IEEE operations fenced against contraction, so the emulated build may be
+//     compiled with -ffp-contract=fast to expose arithmetic that would depend on nvcc's FMA contraction;
+//   * OPB_EMU_SANITIZE=address|thread (build_emu.py) turn AddressSanitizer / ThreadSanitizer into memcheck / racecheck
+//     analogues: under TSan every fiber is a TSan fiber and barriers are the only happens-before edges.
 //
-// The inline-PTX wrappers (csrc/ptx.cuh: mbarrier, TMA, tcgen05) are replaced by a functional model in
-// ptx_emu.cuh; only the CTA-pair (cta_group::2) wrappers trap.
+// Environment: OPB_EMU_ORDER=reverse (highest thread first), OPB_EMU_SMS=n (emulated SM count), OPB_EMU_BACKTRACE=1.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
