@@ -1,9 +1,11 @@
 """`-m gpu`: opb_postprocess_batch (the post-process half of PoseDetector.__call__, pose_detector.py:501-512, for
 a batch of network outputs) against the oracle, bit for bit -- through the C ABI on a B200.
 
-The OPB_FUSED_PEAKS / OPB_PAF_LOWRES variants (peak kernel / PAF line integrals interpolating from the
-low-resolution maps on demand) are off by default until they have been measured; their bit-exactness is covered
-without a GPU by tests/test_emu_postprocess.py, and on a B200 by running this file with OPB_TEST_EXPERIMENTAL=1."""
+The entry point and the OPB_FUSED_PEAKS / OPB_PAF_LOWRES / OPB_PEAKS_V2 variants (peak kernel / PAF line integrals
+interpolating from the low-resolution maps on demand) were written after round 1's GPU budget was spent.  Their
+bit-exactness is covered without a GPU by tests/test_emu_postprocess.py; every test of this file runs on a B200 with
+OPB_TEST_EXPERIMENTAL=1 (first thing next round: tools/gpu_round.sh lowres_ab), and the default-path test loses its
+skip marker once it has passed there."""
 import os
 
 import pytest
@@ -19,6 +21,14 @@ def _engine():
     return native.Engine(0, pkg("pose_detector").make_opb_params(max_peaks=4096, max_candidates=65536, max_persons=128))
 
 
+_NOT_YET_ON_GPU = pytest.mark.skipif(
+    os.environ.get("OPB_TEST_EXPERIMENTAL", "0") != "1",
+    reason="opb_postprocess_batch was written after this round's GPU budget was spent: validated on the CPU under emulation "
+           "(tests/test_emu_postprocess.py, incl. AddressSanitizer / ThreadSanitizer builds); first B200 run: "
+           "OPB_TEST_EXPERIMENTAL=1 (tools/gpu_round.sh lowres_ab)")
+
+
+@_NOT_YET_ON_GPU
 def test_postprocess_batch_default_path(monkeypatch):
     monkeypatch.delenv("OPB_FUSED_PEAKS", raising=False)
     monkeypatch.delenv("OPB_PAF_LOWRES", raising=False)
