@@ -1,6 +1,8 @@
 #!/bin/bash
 # One GPU-box session: build check, probes, tests, bench.  Everything is logged to gpurun_out/.
 # usage: tools/gpu_round.sh [stage ...]   stages: probe post conv kp pipe batch smoke bench benchref sanitize ncu lowres_ab
+# first call of a round (parity of everything incl. the opt-in tests, bench, A/B of the experimental knobs):
+#   gpurun --timeout 2400 -- 'bash tools/gpu_round.sh post conv kp pipe smoke bench lowres_ab'
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
