@@ -9,7 +9,8 @@
 //              completed; a failing try_wait yields to the other threads of the block.
 //   TMA        cuTensorMapEncodeTiled (emu_runtime.cpp) records the map; a load copies the box element by element
 //              (out-of-bounds -> zero fill), writes it with the 128-byte swizzle (16-byte chunk index ^= bits 7..9 of
-//              the shared address) and completes `box bytes` on the mbarrier at once.
+//              the shared address) and completes `box bytes` on the mbarrier -- DEFERRED until a thread next polls that
+//              mbarrier, so a stage read without waiting on its full barrier still holds its previous contents.
 //   tcgen05    TMEM = 128 lanes x 512 fp32 columns per CTA.  tcgen05.mma is QUEUED and executed only when the issuing
 //              thread commits (tcgen05.commit) -- "as late as legal": a kernel that recycles an operand stage or
 //              reads an accumulator before the corresponding commit sees stale data and fails its parity test.
@@ -196,8 +197,7 @@ EMU_INTERNAL inline void yield_ready() {   // spin-wait: let the other threads o
 #endif
 }
 
-EMU_INTERNAL inline void tma_load(void* smem_dst, const CUtensorMap* m, uint64_t* bar, const int* c, int rank) {
-  const TensorMapRec* r = tmap_rec(m);
+EMU_INTERNAL inline void tma_execute(void* smem_dst, const TensorMapRec* r, uint64_t* bar, const int* c, int rank) {
   if (static_cast<int>(r->rank) != rank) { fprintf(stderr, "emu: %dD TMA load through a %uD tensor map\n", rank, r->rank); abort(); }
   if (r->swizzle != 3 /* CU_TENSOR_MAP_SWIZZLE_128B */ || r->box[0] * r->elem_bytes != 128) {
     fprintf(stderr, "emu: only SWIZZLE_128B boxes with 128-byte inner rows are modelled (swizzle %u, inner %u B)\n", r->swizzle, r->box[0] * r->elem_bytes);
@@ -231,6 +231,32 @@ EMU_INTERNAL inline void tma_load(void* smem_dst, const CUtensorMap* m, uint64_t
   mbar_complete_tx(bar, rows * 128);
 }
 
+// TMA loads are DEFERRED: the copy and its complete_tx happen only when some thread next polls the mbarrier the load
+// signals (or at tcgen05.dealloc / kernel end) -- "as late as legal", like the queued MMAs: a consumer that reads an
+// operand stage without waiting on its full barrier sees the stage's previous contents and fails its parity test.
+struct PendingTma { uint64_t* bar; void* dst; const TensorMapRec* rec; int c[5]; int rank; int cta; };
+inline std::vector<PendingTma> g_tma_pending;
+EMU_INTERNAL inline void tma_load(void* smem_dst, const CUtensorMap* m, uint64_t* bar, const int* c, int rank) {
+  PendingTma t;
+  t.bar = bar; t.dst = smem_dst; t.rec = tmap_rec(m); t.rank = rank; t.cta = g_cur_cta;
+  for (int d = 0; d < 5; ++d) t.c[d] = d < rank ? c[d] : 0;
+  g_tma_pending.push_back(t);
+}
+EMU_INTERNAL inline void tma_flush(uint64_t* bar) {   // bar == nullptr: everything
+  if (g_tma_pending.empty()) return;
+  std::vector<PendingTma> keep;
+  std::vector<PendingTma> run;
+  for (const PendingTma& t : g_tma_pending) (bar == nullptr || t.bar == bar ? run : keep).push_back(t);
+  g_tma_pending.swap(keep);
+  unsigned char* const saved_dyn = g_dyn_smem;
+  const int saved_cta = g_cur_cta;
+  for (const PendingTma& t : run) {        // the destination is in the ISSUING CTA's shared memory
+    g_cur_cta = t.cta; g_dyn_smem = g_cta[t.cta].dyn;
+    tma_execute(t.dst, t.rec, t.bar, t.c, t.rank);
+  }
+  g_cur_cta = saved_cta; g_dyn_smem = saved_dyn;
+}
+
 }  // namespace emu
 
 namespace opb {
@@ -252,6 +278,7 @@ EMU_INTERNAL inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 EMU_INTERNAL inline void mbar_arrive(uint64_t* bar) { emu::mbar_arrive_n(bar, 1); }
 EMU_INTERNAL inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  emu::tma_flush(bar);
   if (reinterpret_cast<emu::MBar*>(bar)->phase == (parity & 1u)) emu::yield_ready();
   const bool done = reinterpret_cast<emu::MBar*>(bar)->phase != (parity & 1u);
   if (done) EMU_HB_ACQUIRE(bar);
@@ -292,6 +319,7 @@ EMU_INTERNAL inline void tmem_alloc(uint32_t* smem_result) {
 template <int kCols>
 EMU_INTERNAL inline void tmem_dealloc(uint32_t) {
   if (emu::lane_id() == 0) {
+    emu::tma_flush(nullptr);
     for (int t = emu::g_cur_cta * emu::g_cta_threads; t < (emu::g_cur_cta + 1) * emu::g_cta_threads; ++t)
       if (!emu::g_mma_queue[t].empty()) { fprintf(stderr, "emu: %zu tcgen05.mma issued by thread %d were never committed\n", emu::g_mma_queue[t].size(), t); abort(); }
     emu::g_tmem_allocated[emu::g_cur_cta] = false;
