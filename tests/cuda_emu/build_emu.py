@@ -20,7 +20,7 @@ same shared or global location are reported with both source lines (log files ap
 
 Source rewriting (textual, into _build/src; the originals are not touched):
   kernel<<<grid, block, smem, stream>>>(args)  ->  emu::Launcher(grid, block, smem, stream).run(kernel, args)
-  extern __shared__ T name[];                  ->  T* name = reinterpret_cast<T*>(emu::g_dyn_smem);
+  extern __shared__ T name[];                  ->  T* name = reinterpret_cast<T*>(emu::dyn_smem());
   asm volatile(...);                           ->  emu::unsupported_ptx();
   csrc/ptx.cuh (inline-PTX wrappers)           ->  ptx_emu.cuh: functional model of mbarrier / TMA / tcgen05 + TMEM, so
                                                    the tensor-core conv kernels run too (CTA-pair kernels excepted)
@@ -75,7 +75,7 @@ def rewrite(text):
     text = _strip_asm(text)
     text = text.replace('#include "../../include/opb.h"', '#include "opb.h"')
     text = _LAUNCH.sub(lambda m: "emu::Launcher(%s).run(%s, " % (m.group(2), m.group(1)), text)
-    text = _DYN_SMEM.sub(lambda m: "%s* %s = reinterpret_cast<%s*>(emu::g_dyn_smem);" % (m.group(1), m.group(2), m.group(1)), text)
+    text = _DYN_SMEM.sub(lambda m: "%s* %s = reinterpret_cast<%s*>(emu::dyn_smem());" % (m.group(1), m.group(2), m.group(1)), text)
     return text
 
 

@@ -393,7 +393,10 @@ EMU_INTERNAL inline unsigned live_mask(unsigned mask) {
 
 }  // namespace emu
 
-namespace emu { EMU_INTERNAL inline uint3 tid() { return g_tid; } }
+namespace emu {
+EMU_INTERNAL inline uint3 tid() { return g_tid; }
+EMU_INTERNAL inline unsigned char* dyn_smem() { return g_dyn_smem; }   // what `extern __shared__` arrays are rewritten to
+}
 #define threadIdx emu::tid()
 #define blockIdx emu::g_bid
 #define blockDim emu::g_bdim

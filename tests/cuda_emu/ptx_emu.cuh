@@ -28,8 +28,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include <vector>
-
 #include "emu_tmap.h"
 
 #ifdef EMU_TSAN
@@ -109,7 +107,18 @@ EMU_INTERNAL inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
 }
 
 struct QueuedMma { uint32_t tmem_d; uint64_t adesc, bdesc; uint32_t idesc; uint32_t accumulate; int pair; };
-inline std::vector<QueuedMma> g_mma_queue[MAX_THREADS];   // per issuing thread, flushed by its tcgen05.commit
+// MMAs issued and not yet committed, per CTA (one thread per CTA issues them; plain arrays touched only inside
+// EMU_INTERNAL functions so that the racecheck build does not see the emulator's own bookkeeping)
+constexpr int MAX_QUEUED_MMA = 4096;
+inline QueuedMma g_mma_queue[MAX_CTAS][MAX_QUEUED_MMA];
+inline int g_n_mma_queued[MAX_CTAS] = {0, 0}, g_mma_issuer[MAX_CTAS] = {-1, -1};
+EMU_INTERNAL inline void mma_enqueue(const QueuedMma& q) {
+  const int c = g_cur_cta;
+  if (g_n_mma_queued[c] && g_mma_issuer[c] != g_cur) { fprintf(stderr, "emu: tcgen05.mma issued by two threads of one CTA between commits (threads %d and %d)\n", g_mma_issuer[c], g_cur); abort(); }
+  if (g_n_mma_queued[c] == MAX_QUEUED_MMA) { fprintf(stderr, "emu: %d tcgen05.mma issued without a commit\n", MAX_QUEUED_MMA); abort(); }
+  g_mma_issuer[c] = g_cur;
+  g_mma_queue[c][g_n_mma_queued[c]++] = q;
+}
 inline float g_tmem[MAX_CTAS][128][512];
 inline bool g_tmem_allocated[MAX_CTAS] = {false, false};
 inline long long g_mma_count = 0, g_tma_count = 0;
@@ -159,6 +168,13 @@ __attribute__((optimize("O3"))) EMU_INTERNAL inline void execute_mma(const Queue
     }
   }
   ++g_mma_count;
+}
+
+EMU_INTERNAL inline void mma_flush() {   // the committing thread's queued MMAs run now
+  const int c = g_cur_cta;
+  if (g_n_mma_queued[c] && g_mma_issuer[c] != g_cur) { fprintf(stderr, "emu: tcgen05.commit by thread %d while thread %d has uncommitted MMAs\n", g_cur, g_mma_issuer[c]); abort(); }
+  for (int i = 0; i < g_n_mma_queued[c]; ++i) execute_mma(g_mma_queue[c][i], c);
+  g_n_mma_queued[c] = 0;
 }
 
 // shared::cluster addresses (mapa): bits 28.. = CTA rank + 1, low bits = the shared-window address inside that CTA
@@ -235,25 +251,30 @@ EMU_INTERNAL inline void tma_execute(void* smem_dst, const TensorMapRec* r, uint
 // signals (or at tcgen05.dealloc / kernel end) -- "as late as legal", like the queued MMAs: a consumer that reads an
 // operand stage without waiting on its full barrier sees the stage's previous contents and fails its parity test.
 struct PendingTma { uint64_t* bar; void* dst; const TensorMapRec* rec; int c[5]; int rank; int cta; };
-inline std::vector<PendingTma> g_tma_pending;
+// (a plain array, touched only inside EMU_INTERNAL functions: the racecheck build must not see the emulator's own
+// bookkeeping, and std::vector's member functions would be instrumented)
+constexpr int MAX_PENDING_TMA = 1024;
+inline PendingTma g_tma_pending[MAX_PENDING_TMA];
+inline int g_n_tma_pending = 0;
 EMU_INTERNAL inline void tma_load(void* smem_dst, const CUtensorMap* m, uint64_t* bar, const int* c, int rank) {
-  PendingTma t;
+  if (g_n_tma_pending == MAX_PENDING_TMA) { fprintf(stderr, "emu: %d TMA loads in flight whose mbarriers nobody polls\n", MAX_PENDING_TMA); abort(); }
+  PendingTma& t = g_tma_pending[g_n_tma_pending++];
   t.bar = bar; t.dst = smem_dst; t.rec = tmap_rec(m); t.rank = rank; t.cta = g_cur_cta;
   for (int d = 0; d < 5; ++d) t.c[d] = d < rank ? c[d] : 0;
-  g_tma_pending.push_back(t);
 }
 EMU_INTERNAL inline void tma_flush(uint64_t* bar) {   // bar == nullptr: everything
-  if (g_tma_pending.empty()) return;
-  std::vector<PendingTma> keep;
-  std::vector<PendingTma> run;
-  for (const PendingTma& t : g_tma_pending) (bar == nullptr || t.bar == bar ? run : keep).push_back(t);
-  g_tma_pending.swap(keep);
+  if (g_n_tma_pending == 0) return;
   unsigned char* const saved_dyn = g_dyn_smem;
   const int saved_cta = g_cur_cta;
-  for (const PendingTma& t : run) {        // the destination is in the ISSUING CTA's shared memory
-    g_cur_cta = t.cta; g_dyn_smem = g_cta[t.cta].dyn;
+  int kept = 0;
+  const int n = g_n_tma_pending;
+  for (int i = 0; i < n; ++i) {
+    const PendingTma t = g_tma_pending[i];
+    if (bar != nullptr && t.bar != bar) { g_tma_pending[kept++] = t; continue; }
+    g_cur_cta = t.cta; g_dyn_smem = g_cta[t.cta].dyn;     // the destination is in the ISSUING CTA's shared memory
     tma_execute(t.dst, t.rec, t.bar, t.c, t.rank);
   }
+  g_n_tma_pending = kept;
   g_cur_cta = saved_cta; g_dyn_smem = saved_dyn;
 }
 
@@ -320,22 +341,20 @@ template <int kCols>
 EMU_INTERNAL inline void tmem_dealloc(uint32_t) {
   if (emu::lane_id() == 0) {
     emu::tma_flush(nullptr);
-    for (int t = emu::g_cur_cta * emu::g_cta_threads; t < (emu::g_cur_cta + 1) * emu::g_cta_threads; ++t)
-      if (!emu::g_mma_queue[t].empty()) { fprintf(stderr, "emu: %zu tcgen05.mma issued by thread %d were never committed\n", emu::g_mma_queue[t].size(), t); abort(); }
+    if (emu::g_n_mma_queued[emu::g_cur_cta]) { fprintf(stderr, "emu: %d tcgen05.mma issued by thread %d were never committed\n", emu::g_n_mma_queued[emu::g_cur_cta], emu::g_mma_issuer[emu::g_cur_cta]); abort(); }
     emu::g_tmem_allocated[emu::g_cur_cta] = false;
   }
 }
 inline void tc_fence_before() {}
 inline void tc_fence_after() {}
 EMU_INTERNAL inline void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, accumulate, 0});
+  emu::mma_enqueue(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, accumulate, 0});
 }
 EMU_INTERNAL inline void mma_f16_ss_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, 1u, 0});
+  emu::mma_enqueue(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, 1u, 0});
 }
 EMU_INTERNAL inline void mma_commit(uint64_t* bar) {
-  for (const emu::QueuedMma& q : emu::g_mma_queue[emu::g_cur]) emu::execute_mma(q, emu::g_cur_cta);
-  emu::g_mma_queue[emu::g_cur].clear();
+  emu::mma_flush();
   emu::mbar_arrive_n(bar, 1);
 }
 template <int NCOL>
@@ -373,15 +392,14 @@ EMU_INTERNAL inline void tmem_alloc_pair(uint32_t* smem_result) { emu::need_clus
 template <int kCols>
 EMU_INTERNAL inline void tmem_dealloc_pair(uint32_t taddr) { tmem_dealloc<kCols>(taddr); }
 EMU_INTERNAL inline void mma_f16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, accumulate, 1});
+  emu::mma_enqueue(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, accumulate, 1});
 }
 EMU_INTERNAL inline void mma_f16_ss_pair_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  emu::g_mma_queue[emu::g_cur].push_back(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, 1u, 1});
+  emu::mma_enqueue(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, 1u, 1});
 }
 // multicast commit: arrive (count 1) on the barrier at this offset in BOTH CTAs once the queued MMAs have run
 EMU_INTERNAL inline void mma_commit_pair(uint64_t* bar) {
-  for (const emu::QueuedMma& q : emu::g_mma_queue[emu::g_cur]) emu::execute_mma(q, emu::g_cur_cta);
-  emu::g_mma_queue[emu::g_cur].clear();
+  emu::mma_flush();
   const uint32_t off = emu::smem_addr_of(bar);
   for (int c = 0; c < emu::g_ncta; ++c) emu::mbar_arrive_n(reinterpret_cast<uint64_t*>(emu::smem_ptr(off, c)), 1);
 }
