@@ -367,6 +367,33 @@ def run_ours(args):
         extra["keypoint_nets"] = kp
     except Exception as e:
         extra["keypoint_nets"] = {"error": str(e)[:200]}
+    # the PAF gather alone under a dense-candidate load -- 64 peaks of every joint type per frame (an 8 x 8
+    # grid of impulses in each low-resolution heat map) => 64 x 64 x 19 = 77 824 candidate pairs per frame, 80 B of
+    # 4-byte gathers each.  Times paf_candidates + limb_assign on the full-resolution PAFs of that batch.
+    try:
+        hl = np.zeros((19, H // 8, W // 8), np.float32)
+        for c in range(18):
+            for i in range(8):
+                for j in range(8):
+                    hl[c, 2 + 5 * i + (c % 3), 3 + 9 * j + (c % 5)] = 1.0
+        pl = (np.random.RandomState(1).standard_normal((38, H // 8, W // 8)) * 0.02).astype(np.float32)   # below the 0.05 threshold: every pair is scored, none accepted
+        d_p2 = torch.from_numpy(np.repeat(pl[None], B, 0)).cuda()
+        d_h2 = torch.from_numpy(np.repeat(hl[None], B, 0)).cuda()
+        eng._check(eng.lib.opb_detect_batch(eng.ctx, C.c_void_p(imgs_dev.data_ptr()), native.OPB_DEVICE, B, H, W, MAP_H, MAP_W,
+                                            float(MAP_W), C.c_void_p(d_p2.data_ptr()), C.c_void_p(d_h2.data_ptr()),
+                                            C.c_void_p(hdr_host.ctypes.data), C.c_void_p(per_host.ctypes.data), native.OPB_HOST))
+        pk = eng.image_detail(0)[0]
+        per_type = np.bincount(pk[:, 0].astype(int), minlength=18)
+        limbs = pkg("entity").params["limbs_point"]
+        pairs = int(sum(int(per_type[int(a)]) * int(per_type[int(b)]) for a, b in limbs))
+        ms_dense = eng.time_stage("paf_integral", reps=10)
+        extra["paf_gather_dense"] = {"peaks_per_frame": int(len(pk)), "pairs_per_frame": pairs, "ms": ms_dense,
+                                     "gather_bytes": 80 * pairs * B,
+                                     "achieved_gbs": 80.0 * pairs * B / (ms_dense * 1e-3) / 1e9,
+                                     "note": "paf_candidates + limb_assign; 4-byte gathers use 1/8 of each 32 B sector, "
+                                             "so sector traffic is ~8x the algorithmic bytes (latency-bound, not an HBM roofline)"}
+    except Exception as e:
+        extra["paf_gather_dense"] = {"error": str(e)[:200]}
     # The precision that meets north_star's 1e-3 map tolerance (split-fp16 "parity": 1.9e-5 vs the fp32 oracle; the
     # headline runs fp16 "fast" as BASELINE.json configs[1] names it: 2.8e-3).  Measured in a child process so that
     # nothing it does can cost the headline line; same workload, synchronous device-resident entry.
