@@ -55,6 +55,19 @@ def emu_lib(request):
     return _load(request.param == "fma")
 
 
+# the FMA-contracting build repeats the arithmetic-heavy cases only (suite time); everything else runs once
+_FMA_CASES = ("test_upsample_bilinear_bit_exact", "test_full_postprocess_synth8", "test_postprocess_batch_from_network_resolution_maps",
+              "test_device_resize_linear_u8_bit_exact_vs_cv2", "test_keypoints_exact_ties_and_threshold",
+              "test_upsample_bicubic_vs_cv2", "test_candidate_connections_single_limb", "test_emulated_library_is_not_the_product")
+
+
+@pytest.fixture(autouse=True)
+def _fma_build_only_where_it_matters(request):
+    cs = getattr(request.node, "callspec", None)
+    if cs is not None and cs.params.get("emu_lib") == "fma" and request.node.originalname not in _FMA_CASES:
+        pytest.skip("one build is enough for this case (suite time)")
+
+
 @pytest.fixture()
 def emu_native(emu_lib, monkeypatch):
     """For the duration of one test, Engine() binds the emulated library instead of libopb.so."""
