@@ -29,8 +29,15 @@
 // OPB_PRECISION_PARITY stores x = hi + lo (two fp16 planes) and accumulates
 // hi*Whi + lo*Whi + hi*Wlo into the same TMEM accumulator: the K loop just walks a table of
 // (activation-channel-offset, weight-k-offset) chunk pairs, so both modes run this kernel.
+// OPB_PRECISION_COMP ("compensated") keeps the fp16 main product and adds the two first-order rounding
+// corrections as 8-bit-float MMAs at twice the fp16 rate: per 64-channel chunk one extra K = 128 row
+//   [ e5m2(x_lo * 2^11) | e5m2(x) ]  .  [ e4m3(W * 2^kW) | e4m3(W_lo * 2^S) ],   S = kW + 11,
+// accumulated into the SAME TMEM accumulator as x_hi . (W_hi * 2^S) (the fp16 weights are pre-scaled by
+// the per-layer power of two 2^S, which is exact; the epilogue multiplies by 2^-S).  Cost: 2 MMAs per
+// k-step instead of 3 + two-level accumulation; map error ~1e-4 (tolerance 1e-3).
 #pragma once
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "ptx.cuh"
 
@@ -56,6 +63,7 @@ struct ConvProblem {
   int cout_valid;       // real number of output channels
   int relu;
   int pool;             // 1: fuse F.max_pooling_2d(2,2) -- `out` is the [N][H/2][W/2] pooled tensor
+  float acc_scale;      // accumulator scale (2^-S in compensated precision, else 1)
 };
 
 struct ConvParams {
@@ -66,6 +74,7 @@ struct ConvParams {
   int n_problems;        // 1 or 2 (grouped launch: the L1 / L2 branches of one stage)
   int b_tap_stride;      // K elements per filter tap in the packed weights
   int pad_edge8;         // swap kernel: the last tile of a row is 8 (not 16) pixels wide
+  int comp;              // compensated precision: odd chunk pairs are the 8-bit-float correction rows
   int a_off[kMaxPairs];  // activation channel offset of chunk pair j
   int b_off[kMaxPairs];  // weight k offset (inside one tap) of chunk pair j
   ConvProblem prob[2];
@@ -85,6 +94,68 @@ struct ConvCfg {
 };
 
 
+// ---- 8-bit float helpers (compensated precision) ----
+constexpr float kCompLoScale = 2048.f;   // x_lo is stored as e5m2(x_lo * 2^11): |x_lo| <= 2^-11 |x|, so no overflow
+__host__ __device__ __forceinline__ uint8_t f32_to_e5m2(float v) {
+  return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2));
+}
+__host__ __device__ __forceinline__ uint8_t f32_to_e4m3(float v) {
+  return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3));
+}
+__host__ __device__ __forceinline__ uint32_t f32x4_to_e5m2x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E5M2);
+  return lo | (hi << 16);
+}
+// byte address of tensor channel t in the correction plane of one pixel: [chunk t/64][x_lo 64 B | x 64 B]
+__host__ __device__ __forceinline__ int comp_byte_off(int t) { return ((t >> 6) << 7) + (t & 63); }
+
+// hi (fp16) + correction bytes of CW consecutive output channels of one pixel; f = final fp32 values.
+// o = address of the hi plane value of the first channel, corr = base of the pixel's correction plane, t0 = tensor
+// channel of the first value.
+template <int CW>
+__device__ __forceinline__ void comp_store(const float (&f)[CW], __half* o, uint8_t* corr, int t0, int nvalid) {
+  const bool vec = (nvalid == CW) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) && ((t0 & 15) == 0);
+  if (vec) {
+#pragma unroll
+    for (int g = 0; g < CW / 16; ++g) {
+      uint32_t h[8], xl[4], x8[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __half2 t = __floats2half2_rn(f[g * 16 + 2 * i], f[g * 16 + 2 * i + 1]);
+        h[i] = *reinterpret_cast<const uint32_t*>(&t);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float v = f[g * 16 + 4 * i + k];
+          l[k] = (v - __half2float(__float2half_rn(v))) * kCompLoScale;
+        }
+        xl[i] = f32x4_to_e5m2x4(l[0], l[1], l[2], l[3]);
+        x8[i] = f32x4_to_e5m2x4(f[g * 16 + 4 * i], f[g * 16 + 4 * i + 1], f[g * 16 + 4 * i + 2], f[g * 16 + 4 * i + 3]);
+      }
+      *reinterpret_cast<uint4*>(o + g * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(o + g * 16 + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+      uint8_t* c = corr + comp_byte_off(t0 + g * 16);
+      *reinterpret_cast<uint4*>(c) = make_uint4(xl[0], xl[1], xl[2], xl[3]);
+      *reinterpret_cast<uint4*>(c + 64) = make_uint4(x8[0], x8[1], x8[2], x8[3]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      if (i < nvalid) {
+        const __half hi = __float2half_rn(f[i]);
+        o[i] = hi;
+        uint8_t* c = corr + comp_byte_off(t0 + i);
+        c[0] = f32_to_e5m2((f[i] - __half2float(hi)) * kCompLoScale);
+        c[64] = f32_to_e5m2(f[i]);
+      }
+    }
+  }
+}
+
 // bias + ReLU (+ fused 2x2 max-pool) + fp16 (hi[/lo]) store of CW consecutive output channels of
 // one pixel.  Must be called by all 32 lanes of the warp (the pool uses shuffles): lane =
 // (y%4)*8 + x%8 of a 4-row x 8-column patch, so the 2x2 partners are lane^1 and lane^8.
@@ -100,10 +171,11 @@ __device__ __forceinline__ void epilogue_store_group(const ConvProblem& pr, cons
 #pragma unroll
   for (int i = 0; i < CW / 4; ++i) {
     const float4 b = *reinterpret_cast<const float4*>(bias + 4 * i);
-    f[4 * i + 0] = acc[4 * i + 0] + b.x;
-    f[4 * i + 1] = acc[4 * i + 1] + b.y;
-    f[4 * i + 2] = acc[4 * i + 2] + b.z;
-    f[4 * i + 3] = acc[4 * i + 3] + b.w;
+    const float sc = pr.acc_scale;          // 1 (fmaf(a, 1, b) == a + b) or the exact power of two 2^-S
+    f[4 * i + 0] = fmaf(acc[4 * i + 0], sc, b.x);
+    f[4 * i + 1] = fmaf(acc[4 * i + 1], sc, b.y);
+    f[4 * i + 2] = fmaf(acc[4 * i + 2], sc, b.z);
+    f[4 * i + 3] = fmaf(acc[4 * i + 3], sc, b.w);
   }
   if (pr.relu) {
 #pragma unroll
@@ -166,7 +238,19 @@ __device__ __forceinline__ void epilogue_store_group(const ConvProblem& pr, cons
       for (int i = 0; i < CW; ++i)
         if (i < nvalid) pr.out32[((static_cast<size_t>(n) * pr.cout_valid + ch0 + i) * oH + oy) * oW + ox] = f[i];
     }
-    if (pr.out) {
+    if (pr.out && pr.out_lo_off) {   // compensated precision (warp-uniform): pool on the fp32 values, then hi + correction bytes
+      if (pr.pool) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+          f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
+          f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 8));
+        }
+      }
+      if (!valid) return;
+      const size_t pix = (static_cast<size_t>(n) * oH + oy) * oW + ox;
+      __half* px = pr.out + pix * pr.out_cstride;
+      comp_store<CW>(f, px + pr.out_coff + ch0, reinterpret_cast<uint8_t*>(px + pr.out_lo_off), pr.out_coff + ch0, nvalid);
+    } else if (pr.out) {
       uint32_t h[CW / 2];        // packed half2, kept in registers (no address-taken arrays)
 #pragma unroll
       for (int i = 0; i < CW / 2; ++i) {
@@ -240,6 +324,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   using Cfg = ConvCfg<KS, BN, MT, NSA, NSB, ACC_STAGES>;
   constexpr int PAD = (KS - 1) / 2;
   constexpr uint32_t IDESC = ptx::umma_idesc_f16(128, BN);
+  constexpr uint32_t IDESC8 = ptx::umma_idesc_f8(128, BN, 1 /*A: activations e5m2*/, 0 /*B: weights e4m3*/);
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment
@@ -348,6 +433,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
         uint32_t accumulate = 0;
         for (int j = 0; j < P.n_pairs; ++j) {
+          const bool f8 = !DRAIN && P.comp && (j & 1);   // compensated precision: odd pairs are the 8-bit correction rows
           for (int s = 0; s < KS; ++s) {
             ptx::mbar_wait(&a_full[sa], pa);
             if (DRAIN) {   // two-level accumulation: a fresh TMEM accumulator per A stage
@@ -369,9 +455,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 if (mt < n_sub) {
                   const uint32_t d = tmem_base + (acc * MT + mt) * BN;
                   const uint64_t ad0 = a_st + static_cast<uint64_t>((mt * Cfg::A_SUB_BYTES + r * 1024) >> 4);
-                  ptx::mma_f16_ss(d, ad0, b_st, IDESC, accumulate);
+                  if (f8) {
+                    ptx::mma_f8_ss(d, ad0, b_st, IDESC8, accumulate);
 #pragma unroll
-                  for (int k = 1; k < 4; ++k) ptx::mma_f16_ss_acc(d, ad0 + (k * 32 >> 4), b_st + (k * 32 >> 4), IDESC);
+                    for (int k = 1; k < 4; ++k) ptx::mma_f8_ss(d, ad0 + (k * 32 >> 4), b_st + (k * 32 >> 4), IDESC8, 1u);
+                  } else {
+                    ptx::mma_f16_ss(d, ad0, b_st, IDESC, accumulate);
+#pragma unroll
+                    for (int k = 1; k < 4; ++k) ptx::mma_f16_ss_acc(d, ad0 + (k * 32 >> 4), b_st + (k * 32 >> 4), IDESC);
+                  }
                 }
               }
               accumulate = 1;

@@ -44,6 +44,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
   using Cfg = ConvPairCfg<KS, BN, MT, NSA, NSB, ACC_STAGES>;
   constexpr int PAD = (KS - 1) / 2;
   constexpr uint32_t IDESC = ptx::umma_idesc_f16(256, BN);
+  constexpr uint32_t IDESC8 = ptx::umma_idesc_f8(256, BN, 1 /*A: activations e5m2*/, 0 /*B: weights e4m3*/);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -149,6 +150,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
         ptx::tc_fence_after();
         uint32_t accumulate = 0;
         for (int j = 0; j < P.n_pairs; ++j) {
+          const bool f8 = P.comp && (j & 1);   // compensated precision: odd pairs are the 8-bit correction rows
           for (int s = 0; s < KS; ++s) {
             ptx::mbar_wait(&a_full[sa], pa);
             ptx::tc_fence_after();
@@ -163,10 +165,17 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
                 if (mt < n_mma) {
                   const uint32_t d = tmem_base + (acc * MT + mt) * BN;
                   const uint64_t ad0 = a_st + static_cast<uint64_t>((mt * Cfg::A_SUB_BYTES + r * 1024) >> 4);
-                  ptx::mma_f16_ss_pair(d, ad0, b_st, IDESC, accumulate);
+                  if (f8) {
+                    ptx::mma_f8_ss_pair(d, ad0, b_st, IDESC8, accumulate);
 #pragma unroll
-                  for (int k = 1; k < 4; ++k)
-                    ptx::mma_f16_ss_pair_acc(d, ad0 + (k * 32 >> 4), b_st + (k * 32 >> 4), IDESC);
+                    for (int k = 1; k < 4; ++k)
+                      ptx::mma_f8_ss_pair(d, ad0 + (k * 32 >> 4), b_st + (k * 32 >> 4), IDESC8, 1u);
+                  } else {
+                    ptx::mma_f16_ss_pair(d, ad0, b_st, IDESC, accumulate);
+#pragma unroll
+                    for (int k = 1; k < 4; ++k)
+                      ptx::mma_f16_ss_pair_acc(d, ad0 + (k * 32 >> 4), b_st + (k * 32 >> 4), IDESC);
+                  }
                 }
               }
               accumulate = 1;

@@ -187,10 +187,10 @@ struct opb_ctx {
   uint64_t cache_epoch = 0;        // bumped whenever cached chains / workspaces / weights are freed (invalidates graphs)
   int two_streams = 1;             // OPB_TWO_STREAMS=0: both streaming slots share `stream` and one set of buffers
   int use_graphs = 1;              // OPB_GRAPH=0: streaming mode launches kernel by kernel
-  // Experimental (default off until measured on a B200; bit-exactness is covered by tests/test_emu_postprocess.py):
-  int fused_peaks = 0;             // OPB_FUSED_PEAKS=1: the peak kernel interpolates its tiles from the low-res heat maps;
+  // Post-process variants (A/B on a B200: profiles/r02_lowres_ab.txt; bit-exact against the oracle in every combination):
+  int fused_peaks = 1;             // OPB_FUSED_PEAKS=1: the peak kernel interpolates its tiles from the low-res heat maps;
                                    // =2: materialised maps, but the tile-skip bound comes from the low-res maps (no cell_max pass)
-  int paf_lowres = 0;              // OPB_PAF_LOWRES=1: PAF line integrals sample the low-res PAFs on demand
+  int paf_lowres = 1;              // OPB_PAF_LOWRES=1: PAF line integrals sample the low-res PAFs on demand
   int peaks_v2 = 0;                // OPB_PEAKS_V2=1 (with OPB_FUSED_PEAKS=2): smoothing passes spread over all 256 threads
   int conn_cap = kAssignMaxType;
   bool profile = false;                       // OPB_PROFILE=1: cudaEvent after every launch of a batch

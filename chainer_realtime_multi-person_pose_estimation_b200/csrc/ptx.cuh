@@ -111,6 +111,17 @@ __device__ __forceinline__ void mma_f16_ss_acc(uint32_t tmem_d, uint64_t adesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
 }
+// kind::f8f6f4 (8-bit float operands, K = 32 per instruction, fp32 accumulate): the correction MMAs of the
+// compensated precision accumulate into the SAME TMEM columns as the kind::f16 MMAs
+__device__ __forceinline__ void mma_f8_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -207,6 +218,15 @@ __device__ __forceinline__ void mma_f16_ss_pair_acc(uint32_t tmem_d, uint64_t ad
       "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
 }
+__device__ __forceinline__ void mma_f8_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive (count 1) on the mbarrier at this offset in BOTH CTAs once all prior MMAs completed
 __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
   asm volatile(
@@ -231,6 +251,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
          | (0u << 15) | (0u << 16)                  // a_major = b_major = K
          | (static_cast<uint32_t>(n >> 3) << 17)    // n_dim
          | (static_cast<uint32_t>(m >> 4) << 24);   // m_dim
+}
+
+// kind::f8f6f4 instruction descriptor: 8-bit float A/B (K-major; format 0 = E4M3, 1 = E5M2), fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_f8(int m, int n, int a_fmt, int b_fmt) {
+  return (1u << 4) | (static_cast<uint32_t>(a_fmt) << 7) | (static_cast<uint32_t>(b_fmt) << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 }  // namespace ptx
