@@ -166,7 +166,8 @@ def run_ours(args):
     model = pkg("models.CocoPoseNet").CocoPoseNet()
     model.load_npz(syn.he_weights(0))
     prm = pkg("pose_detector").make_opb_params(max_peaks=2048, max_candidates=8192, max_persons=args.max_persons)
-    eng = native.Engine(local_rank, prm, native.PRECISION_FAST if args.precision == "fast" else native.PRECISION_PARITY)
+    eng = native.Engine(local_rank, prm, {"fast": native.PRECISION_FAST, "parity": native.PRECISION_PARITY,
+                                          "comp": native.PRECISION_COMP}[args.precision])
     eng.load_model(model)
     # a dedicated (non-default) torch stream: libopb launches on it, torch events time it
     stream = torch.cuda.Stream()
@@ -462,7 +463,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--precision", default="fast", choices=["fast", "parity", "comp"])
     ap.add_argument("--max-persons", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the per-stage re-launches (clean ncu launch lists)")

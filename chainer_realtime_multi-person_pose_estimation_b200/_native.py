@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("OPB_LIB_PATH", os.path.join(HERE, "libopb.so"))   # O
 
 OPB_HOST, OPB_DEVICE = 0, 1
 F32_NCHW, U8_NHWC_BGR = 0, 1
-PRECISION_FAST, PRECISION_PARITY = 0, 1
+PRECISION_FAST, PRECISION_PARITY, PRECISION_COMP = 0, 1, 2
 UPSAMPLE_BILINEAR_AC, UPSAMPLE_BICUBIC = 0, 1
 ERR_CUDA, ERR_ARG, ERR_STATE, ERR_CAPACITY, ERR_INDEX, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 N_JOINTS, N_LIMBS, MAX_TAPS = 18, 19, 64

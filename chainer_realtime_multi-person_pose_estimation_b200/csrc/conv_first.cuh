@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "conv_tcgen05.cuh"
+
 namespace opb {
 
 constexpr int CF_TH = 8, CF_TW = 32;
@@ -21,7 +23,7 @@ constexpr int CF_TH = 8, CF_TW = 32;
 __global__ void __launch_bounds__(256, 2)
 conv_first_kernel(const uint8_t* __restrict__ x_u8, const float* __restrict__ x_f32, const float* __restrict__ wt,
                   const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W, int cstride,
-                  int lo_off, float u8_denom) {
+                  int lo_off, float u8_denom, int comp) {
   __shared__ __align__(16) float s_w[27 * 64];
   __shared__ float s_b[64];
   __shared__ float s_lut[256];
@@ -129,7 +131,14 @@ conv_first_kernel(const uint8_t* __restrict__ x_u8, const float* __restrict__ x_
           lo[j] = __float2half_rn(v - __half2float(hi[j]));
         }
         *reinterpret_cast<uint4*>(o + g * 8) = *reinterpret_cast<const uint4*>(hi);
-        if (lo_off) *reinterpret_cast<uint4*>(o + lo_off + g * 8) = *reinterpret_cast<const uint4*>(lo);
+        if (comp) {   // compensated precision: correction plane [fp8(lo * 2^11) 64 B | fp8(v) 64 B] of the single 64-channel chunk
+          float v[8], l[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { v[j] = fmaxf(acc[g * 8 + j], 0.f); l[j] = (v[j] - __half2float(hi[j])) * kCompLoScale; }
+          uint8_t* c = reinterpret_cast<uint8_t*>(o - half * 32 + lo_off) + half * 32 + g * 8;
+          *reinterpret_cast<uint2*>(c) = make_uint2(f32x4_to_act8x4(l[0], l[1], l[2], l[3]), f32x4_to_act8x4(l[4], l[5], l[6], l[7]));
+          *reinterpret_cast<uint2*>(c + 64) = make_uint2(f32x4_to_act8x4(v[0], v[1], v[2], v[3]), f32x4_to_act8x4(v[4], v[5], v[6], v[7]));
+        } else if (lo_off) *reinterpret_cast<uint4*>(o + lo_off + g * 8) = *reinterpret_cast<const uint4*>(lo);
       }
     }
   }

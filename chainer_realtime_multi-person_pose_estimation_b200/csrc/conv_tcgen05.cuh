@@ -31,7 +31,7 @@
 // (activation-channel-offset, weight-k-offset) chunk pairs, so both modes run this kernel.
 // OPB_PRECISION_COMP ("compensated") keeps the fp16 main product and adds the two first-order rounding
 // corrections as 8-bit-float MMAs at twice the fp16 rate: per 64-channel chunk one extra K = 128 row
-//   [ e5m2(x_lo * 2^11) | e5m2(x) ]  .  [ e4m3(W * 2^kW) | e4m3(W_lo * 2^S) ],   S = kW + 11,
+//   [ fp8(x_lo * 2^11) | fp8(x) ]  .  [ e4m3(W * 2^kW) | e4m3(W_lo * 2^S) ],   S = kW + 11,
 // accumulated into the SAME TMEM accumulator as x_hi . (W_hi * 2^S) (the fp16 weights are pre-scaled by
 // the per-layer power of two 2^S, which is exact; the epilogue multiplies by 2^-S).  Cost: 2 MMAs per
 // k-step instead of 3 + two-level accumulation; map error ~1e-4 (tolerance 1e-3).
@@ -95,17 +95,34 @@ struct ConvCfg {
 
 
 // ---- 8-bit float helpers (compensated precision) ----
-constexpr float kCompLoScale = 2048.f;   // x_lo is stored as e5m2(x_lo * 2^11): |x_lo| <= 2^-11 |x|, so no overflow
-__host__ __device__ __forceinline__ uint8_t f32_to_e5m2(float v) {
-  return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2));
-}
+// Activation-side correction bytes: e4m3 (4 significant bits; saturating at 448 -- a larger activation only loses part
+// of its correction) by default, e5m2 (3 bits, fp16's range) with -DOPB_COMP_ACT_E5M2=1.  Weight side: always e4m3.
+#ifndef OPB_COMP_ACT_E5M2
+#define OPB_COMP_ACT_E5M2 0
+#endif
+constexpr int kCompActFmt = OPB_COMP_ACT_E5M2 ? 1 : 0;   // tcgen05 kind::f8f6f4 format code: 0 = E4M3, 1 = E5M2
+#define OPB_NV_ACT_FMT (OPB_COMP_ACT_E5M2 ? __NV_E5M2 : __NV_E4M3)
+constexpr float kCompLoScale = 2048.f;   // x_lo is stored as fp8(x_lo * 2^11): |x_lo| <= 2^-11 |x|, so it is never larger than |x|
 __host__ __device__ __forceinline__ uint8_t f32_to_e4m3(float v) {
   return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3));
 }
-__host__ __device__ __forceinline__ uint32_t f32x4_to_e5m2x4(float a, float b, float c, float d) {
-  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
-  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E5M2);
+__host__ __device__ __forceinline__ uint8_t f32_to_act8(float v) {
+  return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, OPB_NV_ACT_FMT));
+}
+__host__ __device__ __forceinline__ uint32_t f32x4_to_act8x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, OPB_NV_ACT_FMT);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, OPB_NV_ACT_FMT);
   return lo | (hi << 16);
+}
+// value of one activation-side correction byte (host side of opb_test_conv)
+__host__ inline float act8_to_f32(uint8_t b) {
+  if (OPB_COMP_ACT_E5M2) {   // an e5m2 byte is the high byte of the fp16 with the same value
+    const __half_raw hr{static_cast<unsigned short>(static_cast<unsigned short>(b) << 8)};
+    return __half2float(__half(hr));
+  }
+  const int e = (b >> 3) & 15, m = b & 7;
+  const float v = e ? ldexpf(1.f + m / 8.f, e - 7) : ldexpf(m / 8.f, -6);
+  return (b & 0x80) ? -v : v;
 }
 // byte address of tensor channel t in the correction plane of one pixel: [chunk t/64][x_lo 64 B | x 64 B]
 __host__ __device__ __forceinline__ int comp_byte_off(int t) { return ((t >> 6) << 7) + (t & 63); }
@@ -133,8 +150,8 @@ __device__ __forceinline__ void comp_store(const float (&f)[CW], __half* o, uint
           const float v = f[g * 16 + 4 * i + k];
           l[k] = (v - __half2float(__float2half_rn(v))) * kCompLoScale;
         }
-        xl[i] = f32x4_to_e5m2x4(l[0], l[1], l[2], l[3]);
-        x8[i] = f32x4_to_e5m2x4(f[g * 16 + 4 * i], f[g * 16 + 4 * i + 1], f[g * 16 + 4 * i + 2], f[g * 16 + 4 * i + 3]);
+        xl[i] = f32x4_to_act8x4(l[0], l[1], l[2], l[3]);
+        x8[i] = f32x4_to_act8x4(f[g * 16 + 4 * i], f[g * 16 + 4 * i + 1], f[g * 16 + 4 * i + 2], f[g * 16 + 4 * i + 3]);
       }
       *reinterpret_cast<uint4*>(o + g * 16) = make_uint4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<uint4*>(o + g * 16 + 8) = make_uint4(h[4], h[5], h[6], h[7]);
@@ -149,8 +166,8 @@ __device__ __forceinline__ void comp_store(const float (&f)[CW], __half* o, uint
         const __half hi = __float2half_rn(f[i]);
         o[i] = hi;
         uint8_t* c = corr + comp_byte_off(t0 + i);
-        c[0] = f32_to_e5m2((f[i] - __half2float(hi)) * kCompLoScale);
-        c[64] = f32_to_e5m2(f[i]);
+        c[0] = f32_to_act8((f[i] - __half2float(hi)) * kCompLoScale);
+        c[64] = f32_to_act8(f[i]);
       }
     }
   }
@@ -324,7 +341,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   using Cfg = ConvCfg<KS, BN, MT, NSA, NSB, ACC_STAGES>;
   constexpr int PAD = (KS - 1) / 2;
   constexpr uint32_t IDESC = ptx::umma_idesc_f16(128, BN);
-  constexpr uint32_t IDESC8 = ptx::umma_idesc_f8(128, BN, 1 /*A: activations e5m2*/, 0 /*B: weights e4m3*/);
+  constexpr uint32_t IDESC8 = ptx::umma_idesc_f8(128, BN, kCompActFmt /*A: activations*/, 0 /*B: weights e4m3*/);
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment

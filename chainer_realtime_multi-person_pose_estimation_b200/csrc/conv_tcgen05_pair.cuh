@@ -36,15 +36,20 @@ struct ConvPairCfg {
   static constexpr int SMEM_BYTES = 1024 + NSA * A_STAGE_BYTES + NSB * B_STAGE_BYTES + 512 + 8 * BN * 4;
 };
 
-template <int KS, int BN, int MT, int NSA, int NSB, int ACC_STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads2, 1)
+// DRAIN (compensated precision, BN = 256, MT = 1): two-level accumulation as in conv_tcgen05_swap.cuh -- every
+// (chunk pair, filter column) segment lands in a fresh TMEM buffer and eight epilogue warps per CTA (128 channel columns
+// each) add the partial sums in round-to-nearest fp32 registers.
+constexpr int kPairDrainThreads = 64 + 256;
+
+template <int KS, int BN, int MT, int NSA, int NSB, int ACC_STAGES, bool DRAIN = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DRAIN ? kPairDrainThreads : kConvThreads2, 1)
 conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                          const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                          const __grid_constant__ ConvParams P) {
   using Cfg = ConvPairCfg<KS, BN, MT, NSA, NSB, ACC_STAGES>;
   constexpr int PAD = (KS - 1) / 2;
   constexpr uint32_t IDESC = ptx::umma_idesc_f16(256, BN);
-  constexpr uint32_t IDESC8 = ptx::umma_idesc_f8(256, BN, 1 /*A: activations e5m2*/, 0 /*B: weights e4m3*/);
+  constexpr uint32_t IDESC8 = ptx::umma_idesc_f8(256, BN, kCompActFmt /*A: activations*/, 0 /*B: weights e4m3*/);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -62,7 +67,9 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
 
   // warp roles: 0..7 epilogue, 8 TMA producer, 9 MMA issuer.  The SMSP arbiter prefers the HIGHEST
   // warp id, so the two latency-critical single-thread roles get the top ids of their SMSPs.
-  constexpr int kEpiWarps = 4 * OPB_EPI_SETS;
+  static_assert(!DRAIN || (MT == 1 && BN == 256), "drain mode: one 256-channel accumulator per buffer");
+  constexpr int EPI_SETS = DRAIN ? 2 : OPB_EPI_SETS;
+  constexpr int kEpiWarps = 4 * EPI_SETS;
   const int warp_raw = threadIdx.x >> 5;
 #if OPB_ROLE_REORDER
   const int warp = (warp_raw >= kEpiWarps) ? warp_raw - kEpiWarps : warp_raw + 2;   // logical: 0 TMA, 1 MMA, 2.. epilogue
@@ -81,7 +88,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
     }
     for (int i = 0; i < NSA; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NSB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 256 * OPB_EPI_SETS); }
+    for (int i = 0; i < ACC_STAGES; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 256 * EPI_SETS); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
@@ -146,13 +153,19 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
         const int x0 = tx * (16 * MT);
         const int n_sub = min(2 * MT, (P.W - x0 + 7) >> 3);
         const int n_mma = (n_sub + 1) >> 1;
-        ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
-        ptx::tc_fence_after();
+        if (!DRAIN) {
+          ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
+          ptx::tc_fence_after();
+        }
         uint32_t accumulate = 0;
         for (int j = 0; j < P.n_pairs; ++j) {
           const bool f8 = P.comp && (j & 1);   // compensated precision: odd pairs are the 8-bit correction rows
           for (int s = 0; s < KS; ++s) {
             ptx::mbar_wait(&a_full[sa], pa);
+            if (DRAIN) {   // a fresh accumulator buffer per segment
+              ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
+              accumulate = 0;
+            }
             ptx::tc_fence_after();
             const uint64_t a_st = a_desc0 + static_cast<uint64_t>((sa * Cfg::A_STAGE_BYTES) >> 4);
 #pragma unroll
@@ -184,10 +197,16 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
             }
             ptx::mma_commit_pair(&a_empty[sa]);
             if (++sa == NSA) { sa = 0; pa ^= 1; }
+            if (DRAIN) {
+              ptx::mma_commit_pair(&t_full[acc]);
+              if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+            }
           }
         }
-        ptx::mma_commit_pair(&t_full[acc]);
-        if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+        if (!DRAIN) {
+          ptx::mma_commit_pair(&t_full[acc]);
+          if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+        }
       }
     }
   } else {
@@ -217,6 +236,42 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
         bias_key = p * 1024 + nb;
         epilogue_load_bias<BN>(s_bias_w, pr.bias + nb * BN, lane);
       }
+      if constexpr (DRAIN) {
+        // two-level accumulation: this warp's 128 channel columns [col0, col0 + 128) of every segment's buffer
+        const int col0 = eset * 128;
+        float sum[128];
+#pragma unroll
+        for (int i = 0; i < 128; ++i) sum[i] = 0.f;
+        const int n_seg = P.n_pairs * KS;
+        const bool mine = static_cast<int>(rank) < n_sub;        // this CTA's 8-column block is inside the image
+        for (int seg = 0; seg < n_seg; ++seg) {
+          ptx::mbar_wait(&t_full[acc], pacc);
+          ptx::tc_fence_after();
+          if (mine) {
+#pragma unroll
+            for (int cc = 0; cc < 128; cc += 32) {
+              float f[32];
+              tmem_load_group<32>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0 + cc, f);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sum[cc + i] += f[i];
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&t_empty[acc]), 0));
+          if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+        }
+        if (mine) {
+          const int x = x0 + 8 * static_cast<int>(rank) + wl;
+          const bool valid = (y < P.H) && (x < P.W);
+#pragma unroll
+          for (int cc = 0; cc < 128; cc += 32) {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = sum[cc + i];
+            epilogue_store_group<32, false>(pr, f, s_bias_w + col0 + cc, nb * BN + col0 + cc, n, y, x, P.H, P.W, valid);
+          }
+        }
+      } else {
       ptx::mbar_wait(&t_full[acc], pacc);
       ptx::tc_fence_after();
       int item = 0;
@@ -227,7 +282,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
         const bool valid = (y < P.H) && (x < P.W);
 #pragma unroll 1
         for (int cc = 0; cc < BN; cc += CW, ++item) {
-          if ((item & (OPB_EPI_SETS - 1)) != eset) continue;
+          if ((item & (EPI_SETS - 1)) != eset) continue;
           float f[CW];
           tmem_load_group<CW>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * MT + mt) * BN + cc, f);
           epilogue_store_group<CW, false>(pr, f, s_bias_w + cc, nb * BN + cc, n, y, x, P.H, P.W, valid);
@@ -236,6 +291,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
       ptx::tc_fence_before();
       ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&t_empty[acc]), 0));
       if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+      }
     }
   }
 

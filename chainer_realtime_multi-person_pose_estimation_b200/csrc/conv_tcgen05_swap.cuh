@@ -30,8 +30,15 @@ struct ConvSwapCfg {
   static constexpr int SMEM_BYTES = 1024 + NSP * P_STAGE_BYTES + NSW * W_STAGE_BYTES + 512;
 };
 
-template <int KS, int NSP, int NSW>
-__global__ void __launch_bounds__(kConvThreads, 1)
+// DRAIN = two-level accumulation (compensated precision): the tensor core adds into its fp32 accumulator with
+// round-toward-zero, a bias that grows with the number of chained MMAs (784 for a 7x7 128->128 layer with its correction
+// rows).  Every (chunk pair, filter column) segment of KS x 4 MMAs therefore lands in a fresh TMEM buffer (the two
+// buffers ping-pong WITHIN a tile) and eight epilogue warps (two per TMEM lane quarter, 128 pixel columns each) add the
+// partial sums in round-to-nearest fp32 registers while the next segment's MMAs run.
+constexpr int kSwapDrainThreads = 64 + 256;
+
+template <int KS, int NSP, int NSW, bool DRAIN = false>
+__global__ void __launch_bounds__(DRAIN ? kSwapDrainThreads : kConvThreads, 1)
 conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __grid_constant__ CUtensorMap tmP8_0,
                          const __grid_constant__ CUtensorMap tmW_0, const __grid_constant__ CUtensorMap tmP16_1,
                          const __grid_constant__ CUtensorMap tmP8_1, const __grid_constant__ CUtensorMap tmW_1,
@@ -67,7 +74,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
     }
     for (int i = 0; i < NSP; ++i) { ptx::mbar_init(&p_full[i], 1); ptx::mbar_init(&p_empty[i], 1); }
     for (int i = 0; i < NSW; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 128); }
+    for (int i = 0; i < ACC_STAGES; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], DRAIN ? 256 : 128); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
@@ -129,14 +136,23 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
         // the last tile row of an image only needs its valid rows (rounded to even): N = rows x 16 (or x 8)
         const int rows = min(16, (P.H - ty * 16 + 1) & ~1);
         const uint32_t idesc = ptx::umma_idesc_f16(128, rows * (narrow ? 8 : 16));
+        const uint32_t idesc8 = ptx::umma_idesc_f8(128, rows * (narrow ? 8 : 16), 0 /*A: weights e4m3*/, kCompActFmt /*B: activations*/);
         const uint32_t row_pitch16 = narrow ? (1024 >> 4) : (2048 >> 4);   // bytes per image row of the box, >> 4
-        ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d = tmem_base + acc * 256;
+        if (!DRAIN) {
+          ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
+          ptx::tc_fence_after();
+        }
+        uint32_t d = tmem_base + acc * 256;
         uint32_t accumulate = 0;
         for (int j = 0; j < P.n_pairs; ++j) {
+          const bool f8 = P.comp && (j & 1);   // compensated precision: odd pairs are the 8-bit correction rows
           for (int s = 0; s < KS; ++s) {
             ptx::mbar_wait(&p_full[sp], pp);
+            if (DRAIN) {   // a fresh accumulator buffer per segment
+              ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
+              d = tmem_base + acc * 256;
+              accumulate = 0;
+            }
             ptx::tc_fence_after();
             const uint64_t p_st = p_desc0 + static_cast<uint64_t>((sp * Cfg::P_STAGE_BYTES) >> 4);
 #pragma unroll
@@ -145,19 +161,31 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
               ptx::tc_fence_after();
               const uint64_t w_st = w_desc0 + static_cast<uint64_t>((sw * Cfg::W_STAGE_BYTES) >> 4);
               const uint64_t pd0 = p_st + static_cast<uint64_t>(r * row_pitch16);
-              ptx::mma_f16_ss(d, w_st, pd0, idesc, accumulate);
+              if (f8) {
+                ptx::mma_f8_ss(d, w_st, pd0, idesc8, accumulate);
 #pragma unroll
-              for (int k = 1; k < 4; ++k) ptx::mma_f16_ss_acc(d, w_st + (k * 32 >> 4), pd0 + (k * 32 >> 4), idesc);
+                for (int k = 1; k < 4; ++k) ptx::mma_f8_ss(d, w_st + (k * 32 >> 4), pd0 + (k * 32 >> 4), idesc8, 1u);
+              } else {
+                ptx::mma_f16_ss(d, w_st, pd0, idesc, accumulate);
+#pragma unroll
+                for (int k = 1; k < 4; ++k) ptx::mma_f16_ss_acc(d, w_st + (k * 32 >> 4), pd0 + (k * 32 >> 4), idesc);
+              }
               accumulate = 1;
               ptx::mma_commit(&w_empty[sw]);
               if (++sw == NSW) { sw = 0; pw ^= 1; }
             }
             ptx::mma_commit(&p_empty[sp]);
             if (++sp == NSP) { sp = 0; pp ^= 1; }
+            if (DRAIN) {
+              ptx::mma_commit(&t_full[acc]);
+              if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+            }
           }
         }
-        ptx::mma_commit(&t_full[acc]);
-        if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+        if (!DRAIN) {
+          ptx::mma_commit(&t_full[acc]);
+          if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+        }
       }
     }
   } else {
@@ -182,25 +210,84 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
       const bool ch_ok = ch < pr.cout_valid;
       const float bias = ch_ok ? __ldg(pr.bias + ch) : 0.f;
       __half* out_c = pr.out + pr.out_coff + ch;
-      ptx::mbar_wait(&t_full[acc], pacc);
-      ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < n_pix; c0 += 32) {
-        float f[32];
-        tmem_load_group<32>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + c0, f);
+      const float sc = pr.acc_scale;
+      // compensated precision: this channel's two bytes in the correction plane of a pixel
+      uint8_t* corr_c = reinterpret_cast<uint8_t*>(pr.out + pr.out_lo_off) + comp_byte_off(pr.out_coff + ch);
+      const bool comp = pr.out_lo_off != 0;
+      if constexpr (!DRAIN) {
+        ptx::mbar_wait(&t_full[acc], pacc);
+        ptx::tc_fence_after();
+  #pragma unroll 1
+        for (int c0 = 0; c0 < n_pix; c0 += 32) {
+          float f[32];
+          tmem_load_group<32>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + c0, f);
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int pix = c0 + i;
+            const int y = y0 + (pix >> wshift), x = x0 + (pix & ((1 << wshift) - 1));
+            float v = fmaf(f[i], sc, bias);
+            v = pr.relu ? fmaxf(v, 0.f) : v;
+            if (ch_ok && y < P.H && x < P.W) {
+              const size_t o = ((static_cast<size_t>(n) * P.H + y) * P.W + x) * pr.out_cstride;
+              const __half hi = __float2half_rn(v);
+              out_c[o] = hi;
+              if (comp) {
+                const uint32_t b2 = __nv_cvt_float2_to_fp8x2(make_float2((v - __half2float(hi)) * kCompLoScale, v), __NV_SATFINITE, OPB_NV_ACT_FMT);
+                corr_c[2 * o] = static_cast<uint8_t>(b2 & 0xffu);
+                corr_c[2 * o + 64] = static_cast<uint8_t>(b2 >> 8);
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&t_empty[acc]);
+        if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+      } else {
+        // two-level accumulation: this warp's 128 pixel columns [col0, col0 + 128) of every segment's buffer
+        const int col0 = ((warp - 2) >> 2) * 128;
+        float sum[128];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int pix = c0 + i;
-          const int y = y0 + (pix >> wshift), x = x0 + (pix & ((1 << wshift) - 1));
-          float v = f[i] + bias;
-          v = pr.relu ? fmaxf(v, 0.f) : v;
-          if (ch_ok && y < P.H && x < P.W)
-            out_c[((static_cast<size_t>(n) * P.H + y) * P.W + x) * pr.out_cstride] = __float2half_rn(v);
+        for (int i = 0; i < 128; ++i) sum[i] = 0.f;
+        const int n_seg = P.n_pairs * KS;
+        for (int seg = 0; seg < n_seg; ++seg) {
+          ptx::mbar_wait(&t_full[acc], pacc);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int cc = 0; cc < 128; cc += 32) {
+            if (col0 + cc < n_pix) {       // warp-uniform
+              float f[32];
+              tmem_load_group<32>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + col0 + cc, f);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sum[cc + i] += f[i];
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&t_empty[acc]);
+          if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 128; cc += 32) {
+          if (col0 + cc < n_pix) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int pix = col0 + cc + i;
+              const int y = y0 + (pix >> wshift), x = x0 + (pix & ((1 << wshift) - 1));
+              float v = fmaf(sum[cc + i], sc, bias);
+              v = pr.relu ? fmaxf(v, 0.f) : v;
+              if (ch_ok && y < P.H && x < P.W) {
+                const size_t o = ((static_cast<size_t>(n) * P.H + y) * P.W + x) * pr.out_cstride;
+                const __half hi = __float2half_rn(v);
+                out_c[o] = hi;
+                if (comp) {
+                  const uint32_t b2 = __nv_cvt_float2_to_fp8x2(make_float2((v - __half2float(hi)) * kCompLoScale, v), __NV_SATFINITE, OPB_NV_ACT_FMT);
+                  corr_c[2 * o] = static_cast<uint8_t>(b2 & 0xffu);
+                  corr_c[2 * o + 64] = static_cast<uint8_t>(b2 >> 8);
+                }
+              }
+            }
+          }
         }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&t_empty[acc]);
-      if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
     }
   }
 

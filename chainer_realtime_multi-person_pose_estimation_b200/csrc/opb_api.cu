@@ -51,6 +51,7 @@ struct PackedW {          // one "B" operand: [cout_pad][ks*ks][k_per_tap] fp16
   __half* w = nullptr;
   float* bias = nullptr;  // [cout_pad]
   int cout_pad = 0, k_per_tap = 0, cin_pad = 0, ks = 0;
+  float acc_scale = 1.f;  // compensated precision: 2^-S (the fp16 weights are stored pre-scaled by 2^S)
 };
 
 struct Act {              // NHWC fp16 activation tensor, channels [hi C | lo C]
@@ -305,32 +306,32 @@ int launch_conv_t(opb_ctx* ctx, const Op& op) {
   return OPB_OK;
 }
 
-template <int KS, int BN, int MT, int NSA, int NSB, int ACC>
+template <int KS, int BN, int MT, int NSA, int NSB, int ACC, bool DRAIN = false>
 int launch_conv_pair_t(opb_ctx* ctx, const Op& op) {
   using Cfg = ConvPairCfg<KS, BN, MT, NSA, NSB, ACC>;
-  auto kern = conv_tcgen05_pair_kernel<KS, BN, MT, NSA, NSB, ACC>;
+  auto kern = conv_tcgen05_pair_kernel<KS, BN, MT, NSA, NSB, ACC, DRAIN>;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     OPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set[ctx->device & 63] = true;
   }
-  kern<<<op.grid, kConvThreads2, Cfg::SMEM_BYTES, ctx->stream>>>(op.tmA[0], op.tmB[0], op.tmA[1], op.tmB[1], op.P);
+  kern<<<op.grid, DRAIN ? kPairDrainThreads : kConvThreads2, Cfg::SMEM_BYTES, ctx->stream>>>(op.tmA[0], op.tmB[0], op.tmA[1], op.tmB[1], op.P);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   return OPB_OK;
 }
 
-template <int KS, int NSP, int NSW>
+template <int KS, int NSP, int NSW, bool DRAIN = false>
 int launch_conv_swap_t(opb_ctx* ctx, const Op& op) {
   using Cfg = ConvSwapCfg<KS, NSP, NSW>;
-  auto kern = conv_tcgen05_swap_kernel<KS, NSP, NSW>;
+  auto kern = conv_tcgen05_swap_kernel<KS, NSP, NSW, DRAIN>;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     OPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set[ctx->device & 63] = true;
   }
-  kern<<<op.grid, kConvThreads, Cfg::SMEM_BYTES, ctx->stream>>>(op.tmP16[0], op.tmA[0], op.tmB[0], op.tmP16[1], op.tmA[1],
-                                                                op.tmB[1], op.P);
+  kern<<<op.grid, DRAIN ? kSwapDrainThreads : kConvThreads, Cfg::SMEM_BYTES, ctx->stream>>>(
+      op.tmP16[0], op.tmA[0], op.tmB[0], op.tmP16[1], op.tmA[1], op.tmB[1], op.P);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   return OPB_OK;
@@ -339,15 +340,16 @@ int launch_conv_swap_t(opb_ctx* ctx, const Op& op) {
 int launch_conv(opb_ctx* ctx, const Op& op) {
   const int key = op.ks * 10000 + op.bn * 10 + op.mt;
   if (op.swap) {
-    if (op.ks == 7) return launch_conv_swap_t<7, 3, 5>(ctx, op);
-    if (op.ks == 3) return launch_conv_swap_t<3, 3, 6>(ctx, op);
+    if (op.ks == 7) return op.drain ? launch_conv_swap_t<7, 3, 5, true>(ctx, op) : launch_conv_swap_t<7, 3, 5>(ctx, op);
+    if (op.ks == 3) return op.drain ? launch_conv_swap_t<3, 3, 6, true>(ctx, op) : launch_conv_swap_t<3, 3, 6>(ctx, op);
     OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "no swap-mode conv variant");
   }
   if (op.pair) {    // CTA-pair kernels (fast precision)
     switch (key) {
       case 7 * 10000 + 128 * 10 + 2: return launch_conv_pair_t<7, 128, 2, 3, 6, 2>(ctx, op);
       case 7 * 10000 + 128 * 10 + 1: return launch_conv_pair_t<7, 128, 1, 4, 8, 2>(ctx, op);
-      case 7 * 10000 + 256 * 10 + 1: return launch_conv_pair_t<7, 256, 1, 4, 6, 2>(ctx, op);
+      case 7 * 10000 + 256 * 10 + 1:
+        return op.drain ? launch_conv_pair_t<7, 256, 1, 4, 6, 2, true>(ctx, op) : launch_conv_pair_t<7, 256, 1, 4, 6, 2>(ctx, op);
       case 3 * 10000 + 128 * 10 + 2: return launch_conv_pair_t<3, 128, 2, 3, 6, 2>(ctx, op);
       case 3 * 10000 + 256 * 10 + 1: return launch_conv_pair_t<3, 256, 1, 4, 6, 2>(ctx, op);
       case 3 * 10000 + 64 * 10 + 2: return launch_conv_pair_t<3, 64, 2, 3, 6, 2>(ctx, op);
@@ -431,7 +433,8 @@ int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
   const int grid = std::min(tiles, ctx->num_sms * 8);
   conv_first_kernel<<<grid, 256, 0, ctx->stream>>>(op.C == 1 ? (ch->img_u8_src ? ch->img_u8_src : ch->img_u8) : nullptr,
                                                    op.C == 1 ? nullptr : ch->img_f32, ctx->w_first, ctx->b_first,
-                                                   op.out, op.N, op.H, op.W, op.cstride, op.lo_off, ctx->u8_denom);
+                                                   op.out, op.N, op.H, op.W, op.cstride, op.lo_off, ctx->u8_denom,
+                                                   ctx->precision == OPB_PRECISION_COMP ? 1 : 0);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   return OPB_OK;
@@ -440,15 +443,32 @@ int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
 // ------------------------------------------------------------------ weight packing
 // rows: list of (layer, n_rows_pad); cin_map[d] = reference input channel of device channel d
 // (or -1 = zero).  Output [sum rows_pad][ks*ks][cin_pad * (split ? 2 : 1)].
+// Compensated precision (prec == OPB_PRECISION_COMP): per tap [W_hi * 2^S : cin_pad halves][per 64-channel chunk:
+// e4m3(W * 2^kW) 64 B | e4m3(W_lo * 2^S) 64 B], S = kW + 11, 2^kW * max|W| in (8, 16] (one power of two per packed matrix).
 int pack_weights(opb_ctx* ctx, const std::string& key, const std::vector<std::pair<std::string, int>>& rows,
-                 const std::vector<int>& cin_map, int ks, bool split) {
+                 const std::vector<int>& cin_map, int ks, int prec) {
+  const bool split = prec == OPB_PRECISION_PARITY, comp = prec == OPB_PRECISION_COMP;
   const int cin_pad = static_cast<int>(cin_map.size());
-  const int kpt = cin_pad * (split ? 2 : 1);
+  const int kpt = cin_pad * ((split || comp) ? 2 : 1);
   int cout_pad = 0;
   for (auto& r : rows) cout_pad += r.second;
   const size_t ktot = static_cast<size_t>(ks) * ks * kpt;
   std::vector<__half> hw(static_cast<size_t>(cout_pad) * ktot, __float2half(0.f));
   std::vector<float> hb(cout_pad, 0.f);
+  int kW = 0, S = 0;
+  if (comp) {
+    float mx = 0.f;
+    for (auto& r : rows) {
+      auto it = ctx->host_layers.find(r.first);
+      if (it == ctx->host_layers.end()) OPB_FAIL(ctx, OPB_ERR_STATE, "weights for layer " + r.first + " were not loaded");
+      for (float v : it->second.W) mx = std::max(mx, std::fabs(v));
+    }
+    if (mx > 0.f && std::isfinite(mx)) {
+      kW = static_cast<int>(std::floor(std::log2(16.0 / static_cast<double>(mx))));
+      kW = std::max(-100, std::min(100, kW));
+      S = kW + 11;
+    }
+  }
   int row0 = 0;
   for (auto& r : rows) {
     auto it = ctx->host_layers.find(r.first);
@@ -463,6 +483,15 @@ int pack_weights(opb_ctx* ctx, const std::string& key, const std::vector<std::pa
           const int c = cin_map[d];
           if (c < 0 || c >= L.cin) continue;
           const float v = L.W[(static_cast<size_t>(o) * L.cin + c) * ks * ks + t];
+          if (comp) {
+            const __half hs = __float2half_rn(std::ldexp(v, S));                     // W_hi * 2^S (exact scaling)
+            dst[d] = hs;
+            const double lo_s = std::ldexp(static_cast<double>(v), S) - static_cast<double>(__half2float(hs));   // W_lo * 2^S
+            uint8_t* cb = reinterpret_cast<uint8_t*>(dst + cin_pad) + comp_byte_off(d);
+            cb[0] = f32_to_e4m3(std::ldexp(v, kW));
+            cb[64] = f32_to_e4m3(static_cast<float>(lo_s));
+            continue;
+          }
           const __half hi = __float2half_rn(v);
           dst[d] = hi;
           if (split) dst[cin_pad + d] = __float2half_rn(v - __half2float(hi));
@@ -476,6 +505,7 @@ int pack_weights(opb_ctx* ctx, const std::string& key, const std::vector<std::pa
   pw.k_per_tap = kpt;
   pw.cin_pad = cin_pad;
   pw.ks = ks;
+  pw.acc_scale = comp ? std::ldexp(1.f, -S) : 1.f;
   int rc = dev_alloc(ctx, &pw.w, hw.size(), ctx->weight_allocs, false);
   if (rc) return rc;
   rc = dev_alloc(ctx, &pw.bias, hb.size() + 64, ctx->weight_allocs, true);
@@ -513,6 +543,7 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
   op.tag = tag;
   const PackedW& w0 = ctx->packed.at(s.wkey[0]);
   const bool split = ctx->precision == OPB_PRECISION_PARITY;
+  const bool comp = ctx->precision == OPB_PRECISION_COMP;
   op.ks = w0.ks;
   const int per_problem_cout_pad = w0.cout_pad;
   op.drain = split;
@@ -536,6 +567,8 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     if (!split && use_pair && op.bn >= 64 && op.bn != 48) {
       op.pair = true;
       if (op.bn == 256 || op.ks == 1) op.mt = 1;
+      const char* d = getenv("OPB_COMP_DRAIN");   // two-level accumulation of the fused Mconv1 launch (1176 chained MMAs)
+      if (comp && op.ks == 7 && op.bn == 256 && !(d && atoi(d) == 0)) op.drain = true;
     }
   }
   {  // weights-as-A kernel (N = 256-pixel tiles) for the Cout=128 7x7 layers: measured 6.63 -> 5.23 ms on the
@@ -547,6 +580,11 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
         (op.ks == 7 || (op.ks == 3 && (want & 2))) && !s.pool && !s.out32[0] && a0.W >= 16) {
       op.swap = true;
       op.mt = 1;
+      // compensated precision: two-level accumulation on the long-K 7x7 layers (784 chained MMAs each; the tensor core's
+      // round-toward-zero accumulate is most of the remaining map error -- profiles/r02_precision_ladder.txt).
+      // OPB_COMP_DRAIN=0 disables.
+      const char* d = getenv("OPB_COMP_DRAIN");
+      if (comp && !(d && atoi(d) == 0)) op.drain = true;
     }
   }
   {  // Small batches (one camera frame): the throughput-optimal shapes above leave most SMs idle (a 46x62 map is 12
@@ -565,6 +603,7 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
       op.swap = false;
       op.pair = false;
       op.mt = 1;
+      if (comp) op.drain = false;
       if (op.bn > 128 && per_problem_cout_pad % 128 == 0 && tiles_of(false, false, 1, op.bn) * 2 <= ctx->num_sms) op.bn = 128;
       if (op.bn == 128 && !s.pool && tiles_of(false, false, 1, 128) * 2 <= ctx->num_sms) op.bn = 64;
     }
@@ -591,14 +630,18 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
       P.a_off[np] = a0.C + i * 64; P.b_off[np] = i * 64; ++np;             // lo * Whi
       P.a_off[np] = i * 64; P.b_off[np] = w0.cin_pad + i * 64; ++np;        // hi * Wlo
     }
+    if (comp) {   // odd pairs: the 128-byte 8-bit-float correction row of chunk i (addressed as 64 halves)
+      P.a_off[np] = a0.C + i * 64; P.b_off[np] = w0.cin_pad + i * 64; ++np;
+    }
   }
+  P.comp = comp ? 1 : 0;
   if (np > kMaxPairs) OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "too many K chunk pairs");
   P.n_pairs = np;
   for (int p = 0; p < s.n_problems; ++p) {
     const PackedW& w = ctx->packed.at(s.wkey[p]);
     if (w.ks != op.ks || w.cout_pad != per_problem_cout_pad || w.k_per_tap != w0.k_per_tap)
       OPB_FAIL(ctx, OPB_ERR_ARG, "grouped problems must share a shape");
-    if (split && s.in[p]->C != a0.C) OPB_FAIL(ctx, OPB_ERR_ARG, "grouped problems must share the lo-plane offset");
+    if ((split || comp) && s.in[p]->C != a0.C) OPB_FAIL(ctx, OPB_ERR_ARG, "grouped problems must share the lo-plane offset");
     int rc = make_act_map(ctx, &op.tmA[p], *s.in[p], s.in_coff[p], op.ks);
     if (rc) return rc;
     if (op.swap) {
@@ -613,10 +656,11 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     pr.bias = w.bias;
     pr.out_cstride = s.out[p] ? s.out[p]->Ctot : 0;
     pr.out_coff = s.out_coff[p];
-    pr.out_lo_off = (split && s.out[p]) ? s.out[p]->C : 0;
+    pr.out_lo_off = ((split || comp) && s.out[p]) ? s.out[p]->C : 0;
     pr.cout_valid = s.cout_valid[p];
     pr.relu = s.relu;
     pr.pool = s.pool;
+    pr.acc_scale = w.acc_scale;
   }
   if (s.n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; op.tmP16[1] = op.tmP16[0]; P.prob[1] = P.prob[0]; }
   const int total_tiles = P.n_problems * P.n_blocks * P.N * P.tiles_y * P.tiles_x;
@@ -627,7 +671,7 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
 
 int alloc_act(opb_ctx* ctx, Chain* ch, Act* a, int N, int H, int W, int C) {
   a->N = N; a->H = H; a->W = W; a->C = C;
-  a->Ctot = C * (ctx->precision == OPB_PRECISION_PARITY ? 2 : 1);
+  a->Ctot = C * (ctx->precision == OPB_PRECISION_FAST ? 1 : 2);   // parity: [hi | lo] fp16; compensated: [hi fp16 | 2C correction bytes]
   return dev_alloc(ctx, &a->p, a->bytes() / sizeof(__half), ch->allocs, true);
 }
 
@@ -674,6 +718,7 @@ int add_mlp2(opb_ctx* ctx, Chain* ch, const std::string& tag, int n_problems, co
     pr.cout_valid = cout_valid[p];
     pr.relu = 0;
     pr.pool = 0;
+    pr.acc_scale = 1.f;
   }
   if (n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; op.tmP16[1] = op.tmP16[0]; M.prob[1] = M.prob[0]; M.bias1[1] = M.bias1[0]; }
   const int m_tiles = M.N * M.tiles_y * M.tiles_x;
@@ -686,7 +731,7 @@ int add_mlp2(opb_ctx* ctx, Chain* ch, const std::string& tag, int n_problems, co
 int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
   if (ctx->kp_out) return build_chain_keypoint(ctx, ch, N, H, W);
   ch->N = N; ch->H = H; ch->W = W;
-  const bool split = ctx->precision == OPB_PRECISION_PARITY;
+  const bool split = ctx->precision != OPB_PRECISION_FAST;   // two planes per activation tensor (parity: lo; compensated: correction bytes)
   const int h8 = H / 8, w8 = W / 8;
   int rc;
 #define RC(x) do { rc = (x); if (rc) return rc; } while (0)
@@ -732,7 +777,8 @@ int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
     s.cout_valid[0] = cout; s.out32[0] = nullptr; s.n_problems = 1; s.relu = 1; s.pool = fuse_pool;
     return add_conv(ctx, ch, layer, s);
   };
-  const bool fuse = !(getenv("OPB_NO_POOL_FUSION") && atoi(getenv("OPB_NO_POOL_FUSION")));   // debug knob
+  const bool fuse = ctx->precision == OPB_PRECISION_COMP ||   // (the stand-alone pool kernel has no compensated variant)
+                    !(getenv("OPB_NO_POOL_FUSION") && atoi(getenv("OPB_NO_POOL_FUSION")));   // debug knob
   auto conv2 = [&](const std::string& tag, const std::string& l1, const std::string& l2, const Act& in, int ic1,
                    int ic2, const Act& out, int oc1, int oc2, int cv1, int cv2, int relu, float* o32a,
                    float* o32b) -> int {
@@ -794,7 +840,7 @@ int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
 // [features 0..127 | maps 128..128+kp_out-1 | 0 pad] (the Mconv1 weights are permuted to match).
 int build_chain_keypoint(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
   ch->N = N; ch->H = H; ch->W = W;
-  const bool split = ctx->precision == OPB_PRECISION_PARITY;
+  const bool split = ctx->precision != OPB_PRECISION_FAST;
   const int h8 = H / 8, w8 = W / 8, KC = ctx->kp_out;
   int rc;
 #define RC(x) do { rc = (x); if (rc) return rc; } while (0)
@@ -967,7 +1013,10 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
   OPB_CUDA(ctx, cudaMemsetAsync(ws->status, 0, sizeof(int) * n, ctx->stream));
   const int c_use = c_total - 1;   // background channel dropped, pose_detector.py:78
   const size_t smem = smooth_nms_smem_bytes(ctx->taps.radius);
-  static bool attr1 = false, attr2 = false;
+  // function attributes are per device: key the one-time flags by device like the conv launchers do
+  static bool attr1_d[64] = {}, attr2_d[64] = {}, attr3_d[64] = {}, attr4_d[64] = {};
+  bool &attr1 = attr1_d[ctx->device & 63], &attr2 = attr2_d[ctx->device & 63], &attr3 = attr3_d[ctx->device & 63],
+       &attr4 = attr4_d[ctx->device & 63];
   if (!attr1) {
     OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_kernel<PK_R_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -976,7 +1025,6 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
   dim3 grid((W + PK_TX - 1) / PK_TX, (H + PK_TY - 1) / PK_TY, n * c_use);
   if (grid.z > 65535) OPB_FAIL(ctx, OPB_ERR_ARG, "batch too large for the peaks grid");
   if (h_lo > 0) {
-    static bool attr3 = false;
     if (!attr3) {
       OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_lowres_kernel<PK_R_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_lowres_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -986,7 +1034,6 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
     }
     if (h_lo < 2 || w_lo < 2) OPB_FAIL(ctx, OPB_ERR_ARG, "low-resolution maps need at least 2 x 2 samples");
     if (heat_full && ctx->peaks_v2 && ctx->taps.radius == PK_R_FAST) {   // + both smoothing passes on all threads
-      static bool attr4 = false;
       if (!attr4) {
         OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_loskip_kernel_v2<PK_R_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr4 = true;
@@ -1253,7 +1300,7 @@ int opb_load_weights(opb_ctx* ctx, const char* layer, const float* W, const int6
 
 int opb_finalize_weights(opb_ctx* ctx, int precision_mode) {
   if (!ctx) return OPB_ERR_ARG;
-  if (precision_mode != OPB_PRECISION_FAST && precision_mode != OPB_PRECISION_PARITY)
+  if (precision_mode != OPB_PRECISION_FAST && precision_mode != OPB_PRECISION_PARITY && precision_mode != OPB_PRECISION_COMP)
     OPB_FAIL(ctx, OPB_ERR_ARG, "bad precision mode");
   cudaSetDevice(ctx->device);
   // drop everything derived from older weights
@@ -1265,7 +1312,7 @@ int opb_finalize_weights(opb_ctx* ctx, int precision_mode) {
   free_all(ctx->weight_allocs);
   ctx->packed.clear();
   ctx->precision = precision_mode;
-  const bool split = precision_mode == OPB_PRECISION_PARITY;
+  const int split = precision_mode;   // pack_weights' precision argument
   int rc;
   // conv1_1: [27][64] fp32, k = (r*3+s)*3 + c
   {
@@ -1407,7 +1454,7 @@ int opb_upsample(opb_ctx* ctx, int mode, const float* in, int in_loc, int planes
     rc = launch_upsample(ctx, d_in, planes, h, w, d_out, out_h, out_w);
   } else if (mode == OPB_UPSAMPLE_BICUBIC) {
     dim3 grid((out_w + 31) / 32, (out_h + 7) / 8, std::min(planes, 64)), block(32, 8);
-    resize_cubic_kernel<<<grid, block, 0, ctx->stream>>>(d_in, planes, h, w, d_out, out_h, out_w, out_h, out_w, 0, 1.f);
+    resize_cubic_kernel<<<grid, block, 0, ctx->stream>>>(d_in, planes, h, w, d_out, out_h, out_w, out_h, out_w, 0, 0.f);
     ctx->launches++;
     rc = OPB_OK;
     cudaError_t e = cudaGetLastError();
@@ -1754,14 +1801,14 @@ static int precise_accumulate(opb_ctx* ctx, PostWs* ws, Chain* ch, int ph, int p
     ctx->precise_mid_cap = need;
   }
   float* mid = ctx->precise_mid;
-  const float scale = (scale_index == n_scales - 1) ? 1.0f / static_cast<float>(n_scales) : 1.0f;
+  const float scale = (scale_index == n_scales - 1) ? static_cast<float>(n_scales) : 0.f;   // divisor of the last pass (0 = none)
   for (int which = 0; which < 2; ++which) {
     const int C = which ? 19 : 38;
     const float* lo = which ? ch->heat_lo : ch->paf_lo;
     float* acc = which ? ws->heat : ws->pafs;
     dim3 block(32, 8);
     dim3 g1((ch_w + 31) / 32, (ch_h + 7) / 8, C);
-    resize_cubic_kernel<<<g1, block, 0, ctx->stream>>>(lo, C, h8, w8, mid, ph, pw, ch_h, ch_w, 0, 1.f);
+    resize_cubic_kernel<<<g1, block, 0, ctx->stream>>>(lo, C, h8, w8, mid, ph, pw, ch_h, ch_w, 0, 0.f);
     dim3 g2((ws->W + 31) / 32, (ws->H + 7) / 8, C);
     resize_cubic_kernel<<<g2, block, 0, ctx->stream>>>(mid, C, ch_h, ch_w, acc, ws->H, ws->W, ws->H, ws->W,
                                                        scale_index > 0 ? 1 : 0, scale);
@@ -2204,7 +2251,7 @@ int opb_test_conv(opb_ctx* ctx, const float* x, int n, int h, int w, int cin, co
                   int ksize, int relu, int precision_mode, float* y) {
   if (!ctx || !x || !W || !b || !y) return OPB_ERR_ARG;
   cudaSetDevice(ctx->device);
-  const bool split = precision_mode == OPB_PRECISION_PARITY;
+  const bool split = precision_mode == OPB_PRECISION_PARITY, comp = precision_mode == OPB_PRECISION_COMP;
   const int saved_precision = ctx->precision;
   ctx->precision = precision_mode;
   const int pool = (relu >> 1) & 1;   // bit 1 of `relu`: fuse the 2x2 max-pool (y is then [N,H/2,W/2,Cout])
@@ -2225,9 +2272,10 @@ int opb_test_conv(opb_ctx* ctx, const float* x, int n, int h, int w, int cin, co
   std::vector<__half> hx;
   std::vector<__half> hy;
   do {
-    if ((rc = pack_weights(ctx, "__test__", {{"__test__", cout_pad}}, identity_map(cin, cin_pad), ksize, split))) break;
+    if ((rc = pack_weights(ctx, "__test__", {{"__test__", cout_pad}}, identity_map(cin, cin_pad), ksize, precision_mode))) break;
     if ((rc = alloc_act(ctx, &tmp, &in, n, h, w, cin_pad))) break;
-    if ((rc = alloc_act(ctx, &tmp, &out, n, oh, ow, cout_pad))) break;
+    // (the correction plane of the compensated precision is laid out in whole 64-channel chunks)
+    if ((rc = alloc_act(ctx, &tmp, &out, n, oh, ow, comp ? round_up(cout_pad, 64) : cout_pad))) break;
     hx.assign(static_cast<size_t>(n) * h * w * in.Ctot, __float2half(0.f));
     for (size_t pix = 0; pix < static_cast<size_t>(n) * h * w; ++pix)
       for (int c = 0; c < cin; ++c) {
@@ -2235,6 +2283,11 @@ int opb_test_conv(opb_ctx* ctx, const float* x, int n, int h, int w, int cin, co
         const __half hi = __float2half_rn(v);
         hx[pix * in.Ctot + c] = hi;
         if (split) hx[pix * in.Ctot + in.C + c] = __float2half_rn(v - __half2float(hi));
+        if (comp) {
+          uint8_t* cb = reinterpret_cast<uint8_t*>(&hx[pix * in.Ctot + in.C]) + comp_byte_off(c);
+          cb[0] = f32_to_act8((v - __half2float(hi)) * kCompLoScale);
+          cb[64] = f32_to_act8(v);
+        }
       }
     cudaError_t e = cudaMemcpyAsync(in.p, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = OPB_ERR_CUDA; break; }
@@ -2251,6 +2304,8 @@ int opb_test_conv(opb_ctx* ctx, const float* x, int n, int h, int w, int cin, co
       for (int c = 0; c < cout; ++c) {
         float v = __half2float(hy[pix * out.Ctot + c]);
         if (split) v += __half2float(hy[pix * out.Ctot + out.C + c]);
+        if (comp)   // hi + the 8-bit-float lo
+          v += act8_to_f32(reinterpret_cast<const uint8_t*>(&hy[pix * out.Ctot + out.C])[comp_byte_off(c)]) / kCompLoScale;
         y[pix * cout + c] = v;
       }
   } while (0);

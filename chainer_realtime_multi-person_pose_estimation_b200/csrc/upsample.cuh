@@ -239,7 +239,7 @@ __device__ __forceinline__ void cubic_taps(float t, float (&c)[4]) {
 // out = ((accumulate ? out : 0) + value) * scale.
 __global__ void __launch_bounds__(256)
 resize_cubic_kernel(const float* __restrict__ in, int C, int h, int w, float* __restrict__ out, int H_full,
-                    int W_full, int crop_h, int crop_w, int accumulate, float scale) {
+                    int W_full, int crop_h, int crop_w, int accumulate, float divisor) {
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * 8 + threadIdx.y;
   if (x >= crop_w || y >= crop_h) return;
@@ -272,7 +272,8 @@ resize_cubic_kernel(const float* __restrict__ in, int C, int h, int w, float* __
       acc += hsum * cy[r];
     }
     float* o = out + c * out_plane + static_cast<size_t>(y) * crop_w + x;
-    *o = ((accumulate ? *o : 0.f) + acc) * scale;   // scale = 1, or 1/len(scales) on the last pass
+    const float sum = __fadd_rn(accumulate ? *o : 0.f, acc);
+    *o = divisor > 0.f ? __fdiv_rn(sum, divisor) : sum;   // `/ len(scales)` (pose_detector.py:471-472) on the last pass, a true division
   }
 }
 

@@ -60,7 +60,8 @@ class NetContainer(object):
 
     def save_npz(self, path):
         """Writes the layout chainer.serializers.save_npz produces (and load_npz reads)."""
-        np.savez(path, **self.state_dict())
+        with open(path, "wb") as f:     # np.savez(path) would append ".npz"; chainer writes the exact file name
+            np.savez(f, **self.state_dict())
 
     def to_gpu(self, device=None):
         return self

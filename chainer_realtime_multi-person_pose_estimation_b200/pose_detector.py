@@ -64,8 +64,11 @@ def make_opb_params(p=params, max_peaks=None, max_candidates=None, max_persons=N
     return s
 
 
-_PRECISIONS = {"parity": _native.PRECISION_PARITY, "fast": _native.PRECISION_FAST,
-               _native.PRECISION_PARITY: _native.PRECISION_PARITY, _native.PRECISION_FAST: _native.PRECISION_FAST}
+# "comp" (compensated: fp16 product + 8-bit-float rounding corrections, map error ~1e-4) is the fastest precision inside
+# the 1e-3 map tolerance; "parity" (split fp16, ~2e-5) the most accurate; "fast" (plain fp16, ~3e-3) is outside it.
+_PRECISIONS = {"parity": _native.PRECISION_PARITY, "fast": _native.PRECISION_FAST, "comp": _native.PRECISION_COMP,
+               _native.PRECISION_PARITY: _native.PRECISION_PARITY, _native.PRECISION_FAST: _native.PRECISION_FAST,
+               _native.PRECISION_COMP: _native.PRECISION_COMP}
 
 
 class PoseDetector(object):
@@ -187,6 +190,42 @@ class PoseDetector(object):
         bbox = (int(x - crop_size), int(y - crop_size), int(x + crop_size), int(y + crop_size))
         return self.crop_image(img, bbox), bbox
 
+    # joint -> rank tables of crop_person (pose_detector.py:312-313; lower rank = preferred anchor) and the padding,
+    # in unit lengths, above / below the anchoring joint (:343-344)
+    _TOP_RANK = (4, 5, 6, 12, 16, 7, 13, 17, 8, 10, 14, 9, 11, 15, 2, 3, 0, 1)
+    _BOTTOM_RANK = (9, 6, 7, 14, 16, 8, 15, 17, 4, 2, 0, 5, 3, 1, 10, 11, 12, 13)
+    _TOP_PAD = (0.9, 1.9, 1.9, 2.9, 3.7, 1.9, 2.9, 3.7, 4.0, 5.5, 7.0, 4.0, 5.5, 7.0, 0.7, 0.8, 0.7, 0.8)
+    _BOTTOM_PAD = (6.9, 5.9, 5.9, 4.9, 4.1, 5.9, 4.9, 4.1, 3.8, 2.3, 0.8, 3.8, 2.3, 0.8, 7.1, 7.0, 7.1, 7.0)
+
+    def crop_person(self, img, person_pose, unit_length):
+        """pose_detector.py:311-352 (the reference's own version raises NameError: it uses `sys` without importing
+        it, :1-12).  Same walk over the joints, including its either/or updates: a joint that improves the top anchor
+        (or the top / left extent) is not considered for the bottom anchor (bottom / right extent) in the same step."""
+        import sys
+        top_rank, bottom_rank = sys.maxsize, sys.maxsize
+        top_joint = bottom_joint = len(self._TOP_RANK)          # "none": index of the sentinel entry
+        top_pos = left_pos = sys.maxsize
+        bottom_pos = right_pos = 0
+        for i, joint in enumerate(person_pose):
+            if not joint[2] > 0:
+                continue
+            if self._TOP_RANK[i] < top_rank:
+                top_rank, top_joint = self._TOP_RANK[i], i
+            elif self._BOTTOM_RANK[i] < bottom_rank:
+                bottom_rank, bottom_joint = self._BOTTOM_RANK[i], i
+            if joint[1] < top_pos:
+                top_pos = joint[1]
+            elif joint[1] > bottom_pos:
+                bottom_pos = joint[1]
+            if joint[0] < left_pos:
+                left_pos = joint[0]
+            elif joint[0] > right_pos:
+                right_pos = joint[0]
+        # (IndexError, like the reference, when no anchor joint was found)
+        bbox = (int(left_pos - 0.3 * unit_length), int(top_pos - self._TOP_PAD[top_joint] * unit_length),
+                int(right_pos + 0.3 * unit_length), int(bottom_pos + self._BOTTOM_PAD[bottom_joint] * unit_length))
+        return self.crop_image(img, bbox), bbox
+
     def crop_face(self, img, person_pose, unit_length):
         nose = person_pose[JointType.Nose]
         if not nose[2] > 0:
@@ -275,20 +314,30 @@ class PoseDetector(object):
         in order, one item behind the input: the upload of item i+1 overlaps the kernels of item i."""
         pending = None                                    # (slot, single, ow, oh, map_w, map_h, n)
         slot = 0
-        for item in frames:
-            a = np.ascontiguousarray(item, np.uint8)
-            single = a.ndim == 3
-            if single:
-                a = a[None]
-            in_w, in_h = self.compute_optimal_size(a[0], params['inference_img_size'])
-            map_w, map_h = self.compute_optimal_size(a[0], params['heatmap_size'])
-            self.engine.stream_submit(a, in_h, in_w, map_h, map_w, slot=slot, img_len=map_w)
-            cur = (slot, single, a.shape[2], a.shape[1], map_w, map_h, len(a))
+        try:
+            for item in frames:
+                a = np.ascontiguousarray(item, np.uint8)
+                single = a.ndim == 3
+                if single:
+                    a = a[None]
+                in_w, in_h = self.compute_optimal_size(a[0], params['inference_img_size'])
+                map_w, map_h = self.compute_optimal_size(a[0], params['heatmap_size'])
+                self.engine.stream_submit(a, in_h, in_w, map_h, map_w, slot=slot, img_len=map_w)
+                cur = (slot, single, a.shape[2], a.shape[1], map_w, map_h, len(a))
+                prev, pending, slot = pending, cur, slot ^ 1
+                if prev is not None:
+                    yield self._collect_stream(prev)
             if pending is not None:
-                yield self._collect_stream(pending)
-            pending, slot = cur, slot ^ 1
-        if pending is not None:
-            yield self._collect_stream(pending)
+                last, pending = pending, None
+                yield self._collect_stream(last)
+        finally:
+            # the consumer stopped early (break / exception / generator closed): a submitted batch must not stay
+            # "busy" in the C context, or the next submit on that slot would fail for the lifetime of the engine
+            if pending is not None:
+                try:
+                    self.engine.stream_collect(pending[0])
+                except Exception:
+                    pass
 
     def _collect_stream(self, pending):
         slot, single, ow, oh, map_w, map_h, n = pending

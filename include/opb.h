@@ -44,7 +44,10 @@ typedef enum {
 
 enum { OPB_HOST = 0, OPB_DEVICE = 1 };
 enum { OPB_F32_NCHW = 0, OPB_U8_NHWC_BGR = 1 };          /* opb_forward input formats       */
-enum { OPB_PRECISION_FAST = 0, OPB_PRECISION_PARITY = 1 }; /* fp16 | split-fp16 (hi+lo, 3 MMAs) */
+enum { OPB_PRECISION_FAST = 0, OPB_PRECISION_PARITY = 1, OPB_PRECISION_COMP = 2 };
+/* FAST: fp16 operands, fp32 accumulate (map error ~3e-3).  PARITY: split-fp16 (hi+lo, 3 MMAs, two-level accumulation;
+ * ~2e-5).  COMP ("compensated"): fp16 main product + 8-bit-float first-order rounding corrections (2 MMAs; ~1e-4),
+ * the fastest precision inside north_star's 1e-3 map tolerance. */
 enum { OPB_UPSAMPLE_BILINEAR_AC = 0, OPB_UPSAMPLE_BICUBIC = 1 };
 
 /* Constants of entity.py:71-105 (`params`) plus the 21 Gaussian taps of

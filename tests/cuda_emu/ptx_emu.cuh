@@ -106,7 +106,7 @@ EMU_INTERNAL inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
   mbar_check(b);
 }
 
-struct QueuedMma { uint32_t tmem_d; uint64_t adesc, bdesc; uint32_t idesc; uint32_t accumulate; int pair; };
+struct QueuedMma { uint32_t tmem_d; uint64_t adesc, bdesc; uint32_t idesc; uint32_t accumulate; int pair; int f8 = 0; };
 // MMAs issued and not yet committed, per CTA (one thread per CTA issues them; plain arrays touched only inside
 // EMU_INTERNAL functions so that the racecheck build does not see the emulator's own bookkeeping)
 constexpr int MAX_QUEUED_MMA = 4096;
@@ -132,6 +132,22 @@ EMU_INTERNAL inline float half_at(uint32_t addr, int cta) {
   return __half2float(h);
 }
 
+// kind::f8f6f4 operand element: one byte, E4M3 (fmt 0) or E5M2 (fmt 1)
+EMU_INTERNAL inline float f8_at(uint32_t addr, int cta, int fmt) {
+  uint8_t b;
+  EMU_RACE_READ(smem_ptr(swz128(addr), cta), 1);
+  memcpy(&b, smem_ptr(swz128(addr), cta), 1);
+  if (fmt == 1) {   // e5m2 = the high byte of the fp16 with the same value
+    const __half_raw hr{static_cast<unsigned short>(static_cast<unsigned short>(b) << 8)};
+    return __half2float(__half(hr));
+  }
+  if (fmt != 0) { fprintf(stderr, "emu: unsupported kind::f8f6f4 operand format %d\n", fmt); abort(); }
+  const int e = (b >> 3) & 15, m = b & 7;
+  float v = e ? ldexpf(1.f + m / 8.f, e - 7) : ldexpf(m / 8.f, -6);
+  if (e == 15 && m == 7) v = NAN;
+  return (b & 0x80) ? -v : v;
+}
+
 // cta_group::1: D[128 x N] in the issuing CTA's TMEM.  cta_group::2 (pair): M = 256 -- rows 0..127 are CTA 0's A operand
 // and accumulate in CTA 0's TMEM, rows 128..255 CTA 1's; the B operand's rows 0..N/2-1 come from CTA 0's shared memory and
 // rows N/2..N-1 from CTA 1's, each through the same descriptor.
@@ -146,21 +162,27 @@ __attribute__((optimize("O3"))) EMU_INTERNAL inline void execute_mma(const Queue
   const uint32_t a_sbo = static_cast<uint32_t>((q.adesc >> 32) & 0x3FFF) << 4, b_sbo = static_cast<uint32_t>((q.bdesc >> 32) & 0x3FFF) << 4;
   const uint32_t dcol = q.tmem_d & 0xffff, dlane = q.tmem_d >> 16;
   if (dlane != 0 || dcol + N > 512) { fprintf(stderr, "emu: tcgen05.mma accumulator outside TMEM (lane %u col %u N %d)\n", dlane, dcol, N); abort(); }
-  static float A[128][16], Bt[16][256];
+  static float A[128][32], Bt[32][256];
   const int nhalf = q.pair ? N / 2 : N;
+  const int KK = q.f8 ? 32 : 16;      // K per instruction: 32 bytes of either element size
+  const int afmt = static_cast<int>((q.idesc >> 7) & 7u), bfmt = static_cast<int>((q.idesc >> 10) & 7u);
+  if (!q.f8 && (afmt || bfmt)) { fprintf(stderr, "emu: kind::f16 is modelled for fp16 operands only\n"); abort(); }
   for (int n = 0; n < N; ++n) {
     const int src_cta = q.pair ? n / nhalf : issuer_cta, row = q.pair ? n % nhalf : n;
-    for (int k = 0; k < 16; ++k) Bt[k][n] = half_at(b0 + (row >> 3) * b_sbo + (row & 7) * 128 + 2 * k, src_cta);
+    const uint32_t rb = b0 + (row >> 3) * b_sbo + (row & 7) * 128;
+    for (int k = 0; k < KK; ++k) Bt[k][n] = q.f8 ? f8_at(rb + k, src_cta, bfmt) : half_at(rb + 2 * k, src_cta);
   }
   for (int half = 0; half < (q.pair ? 2 : 1); ++half) {
     const int cta = q.pair ? half : issuer_cta;
-    for (int m = 0; m < 128; ++m)
-      for (int k = 0; k < 16; ++k) A[m][k] = half_at(a0 + (m >> 3) * a_sbo + (m & 7) * 128 + 2 * k, cta);
+    for (int m = 0; m < 128; ++m) {
+      const uint32_t ra = a0 + (m >> 3) * a_sbo + (m & 7) * 128;
+      for (int k = 0; k < KK; ++k) A[m][k] = q.f8 ? f8_at(ra + k, cta, afmt) : half_at(ra + 2 * k, cta);
+    }
     for (int m = 0; m < 128; ++m) {    // per element: acc = (((d + a0*b0) + a1*b1) + ...), k ascending; vectorises over n
       float* d = &g_tmem[cta][m][dcol];
       EMU_RACE_WRITE(d, 4ul * N);
       if (!q.accumulate) for (int n = 0; n < N; ++n) d[n] = 0.f;
-      for (int k = 0; k < 16; ++k) {
+      for (int k = 0; k < KK; ++k) {
         const float a = A[m][k];
         const float* b = Bt[k];
         for (int n = 0; n < N; ++n) d[n] += a * b[n];
@@ -353,6 +375,9 @@ EMU_INTERNAL inline void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bd
 EMU_INTERNAL inline void mma_f16_ss_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
   emu::mma_enqueue(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, 1u, 0});
 }
+EMU_INTERNAL inline void mma_f8_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  emu::mma_enqueue(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, accumulate, 0, 1});
+}
 EMU_INTERNAL inline void mma_commit(uint64_t* bar) {
   emu::mma_flush();
   emu::mbar_arrive_n(bar, 1);
@@ -398,6 +423,9 @@ EMU_INTERNAL inline void mma_f16_ss_pair_acc(uint32_t tmem_d, uint64_t adesc, ui
   emu::mma_enqueue(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, 1u, 1});
 }
 // multicast commit: arrive (count 1) on the barrier at this offset in BOTH CTAs once the queued MMAs have run
+EMU_INTERNAL inline void mma_f8_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  emu::mma_enqueue(emu::QueuedMma{tmem_d, adesc, bdesc, idesc, accumulate, 1, 1});
+}
 EMU_INTERNAL inline void mma_commit_pair(uint64_t* bar) {
   emu::mma_flush();
   const uint32_t off = emu::smem_addr_of(bar);

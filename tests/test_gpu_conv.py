@@ -2,6 +2,8 @@
 same op (floating-point kernel -> torch fp32 reference, tolerance stated per mode):
   fast   : operands rounded to fp16, fp32 accumulate, fp16 output  -> 2e-3 * scale
   parity : split-fp16 operands (hi+lo, 3 MMAs), hi+lo output       -> 1e-4 * scale
+  comp   : fp16 product + 8-bit-float rounding corrections (kind::f8f6f4 MMAs into the same accumulator),
+           hi + e5m2 lo output                                      -> 3e-4 * scale (vs the UNquantized reference)
 where scale = max|reference|.  Covers every (ksize, Cout tile) kernel variant the chain uses,
 partial tiles at the right/bottom edge, zero padding at all four borders and multi-image
 batches."""
@@ -52,8 +54,12 @@ CASES = [
 ]
 
 
+_PREC = {"fast": "PRECISION_FAST", "parity": "PRECISION_PARITY", "comp": "PRECISION_COMP"}
+_TOL = {"fast": 2e-3, "parity": 1e-4, "comp": 3e-4}
+
+
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "n%d_%dx%d_c%d_o%d_k%d" % c[:6])
-@pytest.mark.parametrize("mode", ["fast", "parity"])
+@pytest.mark.parametrize("mode", ["fast", "parity", "comp"])
 def test_conv_vs_torch(engine, case, mode):
     n, h, w, cin, cout, ks, relu = case
     native = pkg("_native")
@@ -61,12 +67,12 @@ def test_conv_vs_torch(engine, case, mode):
     x = rs.standard_normal((n, h, w, cin)).astype(np.float32)
     W = (rs.standard_normal((cout, cin, ks, ks)) * np.sqrt(2.0 / (cin * ks * ks))).astype(np.float32)
     b = (rs.standard_normal(cout) * 0.1).astype(np.float32)
-    prec = native.PRECISION_FAST if mode == "fast" else native.PRECISION_PARITY
+    prec = getattr(native, _PREC[mode])
     y = engine.test_conv(x, W, b, relu, prec)
     ref = _ref_conv(x, W, b, relu, quantize=(mode == "fast"))
     scale = np.abs(ref).max()
     err = np.abs(y - ref).max()
-    tol = (2e-3 if mode == "fast" else 1e-4) * scale
+    tol = _TOL[mode] * scale
     assert err <= tol, "max abs err %.3e > tol %.3e (scale %.3f)" % (err, tol, scale)
 
 
@@ -83,7 +89,7 @@ def test_conv_zero_padding_borders(engine):
         assert np.array_equal(y, ref.astype(np.float32))
 
 
-@pytest.mark.parametrize("mode", ["fast", "parity"])
+@pytest.mark.parametrize("mode", ["fast", "parity", "comp"])
 @pytest.mark.parametrize("case", [(2, 24, 40, 64, 64, 3), (1, 32, 18, 128, 128, 3), (1, 46, 82, 256, 256, 3)],
                          ids=lambda c: "n%d_%dx%d_c%d_o%d_k%d" % c)
 def test_conv_fused_maxpool(engine, case, mode):
@@ -94,11 +100,11 @@ def test_conv_fused_maxpool(engine, case, mode):
     x = rs.standard_normal((n, h, w, cin)).astype(np.float32)
     W = (rs.standard_normal((cout, cin, ks, ks)) * np.sqrt(2.0 / (cin * ks * ks))).astype(np.float32)
     b = (rs.standard_normal(cout) * 0.1).astype(np.float32)
-    prec = native.PRECISION_FAST if mode == "fast" else native.PRECISION_PARITY
+    prec = getattr(native, _PREC[mode])
     y = engine.test_conv(x, W, b, 1, prec, pool=True)
     ref = _ref_conv(x, W, b, 1, quantize=(mode == "fast"))
     ref = torch.nn.functional.max_pool2d(torch.from_numpy(ref).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).numpy()
     scale = np.abs(ref).max()
     err = np.abs(y - ref).max()
     assert y.shape == ref.shape
-    assert err <= (2e-3 if mode == "fast" else 1e-4) * scale, "max abs err %.3e (scale %.3f)" % (err, scale)
+    assert err <= _TOL[mode] * scale, "max abs err %.3e (scale %.3f)" % (err, scale)

@@ -1,12 +1,20 @@
 """`-m gpu`: end-to-end parity of the device pipeline against the committed goldens (outputs of
-the reference's own files run verbatim, oracle/make_goldens.py) on identical seeded weights.
+the reference's own files run verbatim, oracle/make_goldens.py) on identical seeded weights, in the two
+precisions that claim parity ("parity": split fp16, ~2e-5; "comp": fp16 + 8-bit-float rounding corrections, ~1e-4).
 
-Float maps: |device - oracle| <= 1e-3 (north_star tolerance; parity mode is expected ~3e-5).
-Keypoints: the peak / person sets must be identical.  Because the conv output differs from
-the fp32 oracle by ~1e-5, a peak whose decision margin in the oracle is itself below that
-noise can legitimately flip; such near-ties are identified FROM THE ORACLE MAPS (margin <
-TIE_EPS) and excluded from the identity check -- the count of excluded peaks is asserted to
-be tiny.  Kernel-level bit-exactness on identical inputs is in test_gpu_postprocess.py."""
+Every end-to-end case asserts, UNCONDITIONALLY:
+  (1) float maps: |device - reference golden| <= 1e-3 (north_star tolerance);
+  (2) bit-exact keypoints given the maps: peaks, connections (ids and float64 scores), subsets, poses and scores
+      returned by the device equal the oracle post-process (oracle/restate.py, pinned to the reference) run on the
+      DEVICE's own maps;
+  (3) against the golden: every peak that differs is a provable near-tie (its decision margin in the reference maps is
+      below TIE_FACTOR x the measured map error) and their number stays inside _max_flips().
+When (3) finds no flipped peak and no flipped connection threshold the "strong" branch additionally asserts poses
+identical to the reference golden (OKS = 1.0); the branch each case took is recorded (gpurun_out/r2_e2e_branches.json
+when that directory exists) and REQUIRED to be the strong one for the cases in STRONG_REQUIRED.
+Kernel-level bit-exactness on identical inputs is in test_gpu_postprocess.py."""
+import json
+import os
 import numpy as np
 import pytest
 
@@ -17,6 +25,26 @@ pytestmark = pytest.mark.gpu
 
 MAP_TOL = 1e-3
 TIE_FACTOR = 4.0      # a peak may flip only if its oracle margin is below TIE_FACTOR x the measured map error
+# (precision, golden) pairs whose poses must be IDENTICAL to the reference golden (measured on a B200, round 2)
+STRONG_REQUIRED = {("parity", "fast_584_he0.npz"), ("parity", "precise_480_he0.npz"), ("parity", "precise_200x300_he0.npz")}
+
+
+def _max_flips(n_ref, map_err):
+    """Sanity bound on top of the per-peak margin check: these goldens are dense noise maps (thousands of peaks at noise
+    level), so the number of peaks whose margin lies inside the error band grows with the map error; measured on a B200:
+    parity (2e-5) 0 / 3 / 2 flips of 1758 / 2190 / 5829 peaks, i.e. a flipped fraction of up to ~60 x map_err."""
+    return max(2, int(np.ceil(80.0 * map_err * n_ref)))
+_BRANCHES = {}
+
+
+def _record_branch(precision, name, info):
+    _BRANCHES["%s/%s" % (precision, name)] = info
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "r2_e2e_branches.json"), "w") as f:
+            json.dump(_BRANCHES, f, indent=1, sort_keys=True)
+    if (precision, name) in STRONG_REQUIRED:
+        assert info["strong"], "%s/%s must reproduce the reference golden exactly: %s" % (precision, name, info)
 
 
 @pytest.fixture(scope="module")
@@ -30,6 +58,19 @@ def weights_model():
 def det_parity(weights_model):
     return pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="parity",
                                              max_candidates=131072, max_persons=4096)
+
+
+@pytest.fixture(scope="module")
+def det_comp(weights_model):
+    return pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="comp",
+                                             max_candidates=131072, max_persons=4096)
+
+
+@pytest.fixture(params=["parity", "comp"])
+def det_any(request, det_parity, det_comp):
+    d = det_parity if request.param == "parity" else det_comp
+    d._test_precision = request.param
+    return d
 
 
 def _oracle_margins(heat):
@@ -51,15 +92,17 @@ def _peak_sets_match(got_peaks, ref_peaks, heat_oracle, tie_eps):
     return len(sym)
 
 
-def test_forward_maps_parity_mode(det_parity):
+def test_forward_maps_parity_mode(det_any):
+    det_parity = det_any
     g = load_golden("fast_584_he0.npz")
     img = pkg("synthetic").procedural_image(584, 584, seed=1)
     import cv2
     x = det_parity.preprocess(cv2.resize(img, (368, 368)))
     paf, heat = det_parity.engine.forward(x)
     e1, e2 = np.abs(paf[0] - g["paf_lo_0"]).max(), np.abs(heat[0] - g["heat_lo_0"]).max()
-    print("parity-mode max abs err: paf %.3e heat %.3e" % (e1, e2))
+    print("%s-precision max abs err: paf %.3e heat %.3e" % (det_any._test_precision, e1, e2))
     assert e1 <= MAP_TOL and e2 <= MAP_TOL
+    assert max(e1, e2) <= (1e-4 if det_any._test_precision == "parity" else 5e-4)   # measured: ~2e-5 / ~1.5e-4
     # uint8 entry (preprocess fused into conv1_1) gives the same maps
     paf_u8, heat_u8 = det_parity.engine.forward(cv2.resize(img, (368, 368))[None])
     assert np.abs(paf_u8 - paf).max() <= 1e-5 and np.abs(heat_u8 - heat).max() <= 1e-5
@@ -107,17 +150,34 @@ def test_fused_1x1_pair_is_bit_identical_to_two_launches(weights_model, monkeypa
 
 
 def test_forward_maps_fast_mode(weights_model):
-    det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="fast")
-    g = load_golden("fast_584_he0.npz")
+    """fp16 operands ("fast"): OUTSIDE the 1e-3 tolerance by design (BASELINE.json configs[1] names fp16 for the roofline
+    measurement); SURVEY 8d(ii) prescribes reporting its max-abs map error and the symmetric difference of the peak sets
+    on the fast goldens instead of claiming parity -- both are bounded here so that a regression shows."""
     import cv2
-    img = pkg("synthetic").procedural_image(584, 584, seed=1)
-    paf, heat = det.engine.forward(cv2.resize(img, (368, 368))[None])
-    e1, e2 = np.abs(paf[0] - g["paf_lo_0"]).max(), np.abs(heat[0] - g["heat_lo_0"]).max()
-    print("fast-mode (fp16) max abs err: paf %.3e heat %.3e" % (e1, e2))
-    assert e1 <= 5e-2 and e2 <= 5e-2   # reported, not a parity claim (~5e-3 expected)
+    det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="fast", max_candidates=131072,
+                                            max_persons=4096)
+    syn = pkg("synthetic")
+    report = {}
+    for name, img in (("fast_584_he0.npz", syn.procedural_image(584, 584, seed=1)),
+                      ("fast_480x640_he0.npz", syn.procedural_image(480, 640, seed=2)),
+                      ("fast_368x656_he0_img0.npz", syn.random_images(2, 368, 656, seed=0)[0])):
+        g = load_golden(name)
+        in_w, in_h = R.compute_optimal_size(img, 368)
+        paf, heat = det.engine.forward(cv2.resize(img, (in_w, in_h))[None])
+        err = max(float(np.abs(paf[0] - g["paf_lo_0"]).max()), float(np.abs(heat[0] - g["heat_lo_0"]).max()))
+        det(img)
+        peaks = det.engine.image_detail(0)[0]
+        key = lambda p: set(map(tuple, p[:, :3].astype(int))) if len(p) else set()
+        sym, n_ref = len(key(peaks) ^ key(g["all_peaks"])), len(g["all_peaks"])
+        report[name] = dict(map_err=err, peak_symdiff=sym, ref_peaks=n_ref)
+        print("fast (fp16) %s: max abs map err %.3e, peak-set symmetric difference %d of %d" % (name, err, sym, n_ref))
+        assert err <= 2e-2                  # ~3e-3 on the O(1) procedural maps, ~1e-2 on the O(10) white-noise frame
+        assert sym <= max(4, n_ref // 4)    # SURVEY probe: ~10 % of the noise peaks flip at fp16
+    _record_branch("fast", "peak_symdiff_report", dict(strong=False, report=report))
 
 
 def _check_call(det, name, img):
+    precision = det._test_precision
     g = load_golden(name)
     poses, scores = det(img)
     if g["all_peaks"].shape[0] == 0:
@@ -126,44 +186,57 @@ def _check_call(det, name, img):
     oh, ow = img.shape[:2]
     in_w, in_h = R.compute_optimal_size(img, 368)
     map_w, map_h = R.compute_optimal_size(img, 320)
-    heat_or = R.resize_bilinear_align_corners(g["heat_lo_0"][None], (map_h, map_w))[0]
     peaks, conns, subsets = det.engine.image_detail(0)
     import cv2
     paf_lo, heat_lo = det.engine.forward(cv2.resize(img, (in_w, in_h))[None])
+    # (1) maps within the tolerance of the reference
     map_err = max(np.abs(paf_lo[0] - g["paf_lo_0"]).max(), np.abs(heat_lo[0] - g["heat_lo_0"]).max())
     assert map_err <= MAP_TOL
+    # (2) given the device's maps, everything downstream is bit-exact: oracle post-process of the device's own maps
+    d_pafs = R.resize_bilinear_align_corners(paf_lo, (map_h, map_w))[0]
+    d_heat = R.resize_bilinear_align_corners(heat_lo, (map_h, map_w))[0]
+    o_poses, o_scores, parts = R.postprocess_fast(d_pafs, d_heat, map_w, ow, oh, map_h, return_parts=True)
+    assert np.array_equal(peaks, parts["all_peaks"])
+    assert len(conns) == len(parts["connections"]) and all(np.array_equal(a, b) for a, b in zip(conns, parts["connections"]))
+    assert np.array_equal(subsets, parts["subsets"])
+    assert poses.shape == o_poses.shape and np.array_equal(poses, o_poses) and np.array_equal(scores, o_scores)
+    # (3) against the reference golden: only provable near-ties may differ
+    heat_or = R.resize_bilinear_align_corners(g["heat_lo_0"][None], (map_h, map_w))[0]
     n_ties = _peak_sets_match(peaks, g["all_peaks"], heat_or, max(TIE_FACTOR * map_err, 1e-4))
-    print(name, "map err %.2e" % map_err, "peaks", len(peaks), "ref", len(g["all_peaks"]), "near-tie flips", n_ties)
-    assert n_ties <= max(2, len(g["all_peaks"]) // 500)
+    assert n_ties <= _max_flips(len(g["all_peaks"]), map_err)
+    ref_conns = split_conns(g["conn_lens"], g["conn_flat"])
+    n_conn_diff = -1
     if n_ties == 0:
         assert np.array_equal(peaks[:, :3], g["all_peaks"][:, :3])
         assert np.abs(peaks[:, 3] - g["all_peaks"][:, 3]).max() <= MAP_TOL
-        ref_conns = split_conns(g["conn_lens"], g["conn_flat"])
-        same_conn = all(a.shape == b.shape and np.array_equal(a[:, :2], b[:, :2]) for a, b in zip(conns, ref_conns))
         # connection acceptance thresholds (ip > 0.05, score > 0) have their own measure-zero ties
-        if same_conn:
-            assert subsets.shape == g["subsets"].shape
-            assert np.array_equal(subsets[:, :18], g["subsets"][:, :18])
-            assert np.abs(subsets[:, 18:] - g["subsets"][:, 18:]).max() <= 1e-2
-            assert poses.shape == g["poses"].shape and np.array_equal(poses, g["poses"])      # OKS = 1.0
-            assert np.abs(scores - g["scores"]).max() <= 1e-2
-        else:
-            n_diff = sum(0 if (a.shape == b.shape and np.array_equal(a[:, :2], b[:, :2])) else 1
-                         for a, b in zip(conns, ref_conns))
-            print("connection lists differ on", n_diff, "limbs (threshold near-ties)")
-            assert n_diff <= 2
+        n_conn_diff = sum(0 if (a.shape == b.shape and np.array_equal(a[:, :2], b[:, :2])) else 1
+                          for a, b in zip(conns, ref_conns))
+        assert n_conn_diff <= 2
+    strong = n_ties == 0 and n_conn_diff == 0
+    if strong:
+        assert subsets.shape == g["subsets"].shape
+        assert np.array_equal(subsets[:, :18], g["subsets"][:, :18])
+        assert np.abs(subsets[:, 18:] - g["subsets"][:, 18:]).max() <= 1e-2
+        assert poses.shape == g["poses"].shape and np.array_equal(poses, g["poses"])      # OKS = 1.0
+        assert np.abs(scores - g["scores"]).max() <= 1e-2
+    info = dict(strong=bool(strong), map_err=float(map_err), peaks=int(len(peaks)), ref_peaks=int(len(g["all_peaks"])),
+                near_tie_peak_flips=int(n_ties), limbs_with_flipped_connections=int(n_conn_diff),
+                persons=int(len(poses)), ref_persons=int(len(g["poses"])))
+    print(precision, name, info)
+    _record_branch(precision, name, info)
 
 
-def test_call_fast_path_584(det_parity):
-    _check_call(det_parity, "fast_584_he0.npz", pkg("synthetic").procedural_image(584, 584, seed=1))
+def test_call_fast_path_584(det_any):
+    _check_call(det_any, "fast_584_he0.npz", pkg("synthetic").procedural_image(584, 584, seed=1))
 
 
-def test_call_fast_path_webcam_shape(det_parity):
-    _check_call(det_parity, "fast_480x640_he0.npz", pkg("synthetic").procedural_image(480, 640, seed=2))
+def test_call_fast_path_webcam_shape(det_any):
+    _check_call(det_any, "fast_480x640_he0.npz", pkg("synthetic").procedural_image(480, 640, seed=2))
 
 
-def test_call_fast_path_dense_noise(det_parity):
-    _check_call(det_parity, "fast_368x656_he0_img0.npz", pkg("synthetic").random_images(2, 368, 656, seed=0)[0])
+def test_call_fast_path_dense_noise(det_any):
+    _check_call(det_any, "fast_368x656_he0_img0.npz", pkg("synthetic").random_images(2, 368, 656, seed=0)[0])
 
 
 def test_call_default_init_returns_empty():
@@ -243,40 +316,41 @@ def test_injected_synthetic_eight_person_maps(det_parity):
         assert np.array_equal(subsets, parts["subsets"])
 
 
-def test_precise_path_480(weights_model):
-    det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precise=True, precision="parity",
+def _check_precise(weights_model, precision, name, img, stride):
+    det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precise=True, precision=precision,
                                             max_candidates=131072, max_persons=4096)
-    g = load_golden("precise_480_he0.npz")
-    img = pkg("synthetic").procedural_image(480, 480, seed=3)
+    g = load_golden(name)
+    oh, ow = img.shape[:2]
     poses, scores = det(img)
-    e1 = np.abs(det.pafs[:, ::7, ::7] - g["pafs_sample"]).max()
-    e2 = np.abs(det.heatmaps[:, ::7, ::7] - g["heatmaps_sample"]).max()
-    print("precise maps max abs err: paf %.3e heat %.3e; peaks %d ref %d" % (e1, e2, len(det.all_peaks),
-                                                                            len(g["all_peaks"])))
+    # (1) maps
+    e1 = np.abs(det.pafs[:, ::stride, ::stride] - g["pafs_sample"]).max()
+    e2 = np.abs(det.heatmaps[:, ::stride, ::stride] - g["heatmaps_sample"]).max()
     assert e1 <= MAP_TOL and e2 <= MAP_TOL
+    # (2) bit-exact post-process of the device's own averaged maps (pose_detector.py:476-482, img_len = original width)
+    o_peaks = R.compute_peaks_from_heatmaps(det.heatmaps)
+    assert np.array_equal(det.all_peaks, o_peaks)
+    o_conns = R.compute_connections(det.pafs, o_peaks, ow)
+    o_subsets = R.grouping_key_points(o_conns, o_peaks)
+    o_poses = R.subsets_to_pose_array(o_subsets, o_peaks)
+    assert poses.shape == o_poses.shape and np.array_equal(poses, o_poses) and np.array_equal(scores, o_subsets[:, -2])
+    # (3) against the reference golden
     G = set(map(tuple, det.all_peaks[:, :3].astype(int)))
     Rf = set(map(tuple, g["all_peaks"][:, :3].astype(int)))
-    print("precise peak-set symmetric difference:", len(G ^ Rf))
-    assert len(G ^ Rf) <= max(2, len(Rf) // 500)
-    if G == Rf and poses.shape == g["poses"].shape:
-        assert np.array_equal(poses, g["poses"])       # OKS = 1.0 vs the reference
+    assert len(G ^ Rf) <= _max_flips(len(Rf), max(e1, e2))
+    strong = (G == Rf) and poses.shape == g["poses"].shape and np.array_equal(poses, g["poses"])   # OKS = 1.0 vs the reference
+    info = dict(strong=bool(strong), map_err=float(max(e1, e2)), peaks=len(G), ref_peaks=len(Rf), peak_symdiff=len(G ^ Rf),
+                persons=int(len(poses)), ref_persons=int(len(g["poses"])))
+    print(precision, name, info)
+    _record_branch(precision, name, info)
 
 
-def test_precise_path_padded_200x300(weights_model):
+@pytest.mark.parametrize("precision", ["parity", "comp"])
+def test_precise_path_480(weights_model, precision):
+    _check_precise(weights_model, precision, "precise_480_he0.npz", pkg("synthetic").procedural_image(480, 480, seed=3), 7)
+
+
+@pytest.mark.parametrize("precision", ["parity", "comp"])
+def test_precise_path_padded_200x300(weights_model, precision):
     """Precise path with padding: the scaled inputs 184x276 and 552x828 are padded to 280 / 832 columns
     (pad_image, :445) and the x8 maps cropped again (:462,:466)."""
-    det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precise=True, precision="parity",
-                                            max_candidates=131072, max_persons=4096)
-    g = load_golden("precise_200x300_he0.npz")
-    img = pkg("synthetic").procedural_image(200, 300, seed=4)
-    poses, scores = det(img)
-    e1 = np.abs(det.pafs[:, ::5, ::5] - g["pafs_sample"]).max()
-    e2 = np.abs(det.heatmaps[:, ::5, ::5] - g["heatmaps_sample"]).max()
-    G = set(map(tuple, det.all_peaks[:, :3].astype(int)))
-    Rf = set(map(tuple, g["all_peaks"][:, :3].astype(int)))
-    print("precise 200x300 max abs err: paf %.3e heat %.3e; peaks %d ref %d symdiff %d" % (
-        e1, e2, len(G), len(Rf), len(G ^ Rf)))
-    assert e1 <= MAP_TOL and e2 <= MAP_TOL
-    assert len(G ^ Rf) <= max(2, len(Rf) // 500)
-    if G == Rf and poses.shape == g["poses"].shape:
-        assert np.array_equal(poses, g["poses"])
+    _check_precise(weights_model, precision, "precise_200x300_he0.npz", pkg("synthetic").procedural_image(200, 300, seed=4), 5)
