@@ -75,6 +75,7 @@ struct ConvParams {
   int b_tap_stride;      // K elements per filter tap in the packed weights
   int pad_edge8;         // swap kernel: the last tile of a row is 8 (not 16) pixels wide
   int comp;              // compensated precision: odd chunk pairs are the 8-bit-float correction rows
+  int drain_seg;         // swap / pair DRAIN kernels: (chunk pair, filter column) steps accumulated per TMEM buffer
   int a_off[kMaxPairs];  // activation channel offset of chunk pair j
   int b_off[kMaxPairs];  // weight k offset (inside one tap) of chunk pair j
   ConvProblem prob[2];
@@ -450,7 +451,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
         uint32_t accumulate = 0;
         for (int j = 0; j < P.n_pairs; ++j) {
-          const bool f8 = !DRAIN && P.comp && (j & 1);   // compensated precision: odd pairs are the 8-bit correction rows
+          const bool f8 = P.comp && (j & 1);   // compensated precision: odd pairs are the 8-bit correction rows
           for (int s = 0; s < KS; ++s) {
             ptx::mbar_wait(&a_full[sa], pa);
             if (DRAIN) {   // two-level accumulation: a fresh TMEM accumulator per A stage
@@ -578,7 +579,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           float f[CW];
 #pragma unroll
           for (int i = 0; i < CW; ++i) f[i] = sum[cc + i];
-          epilogue_store_group<CW, true>(pr, f, s_bias_w + cc, nb * BN + cc, n, y, x, P.H, P.W, valid);
+          if (P.comp) epilogue_store_group<CW, false>(pr, f, s_bias_w + cc, nb * BN + cc, n, y, x, P.H, P.W, valid);
+          else epilogue_store_group<CW, true>(pr, f, s_bias_w + cc, nb * BN + cc, n, y, x, P.H, P.W, valid);
         }
       }
     }

@@ -158,11 +158,13 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
           ptx::tc_fence_after();
         }
         uint32_t accumulate = 0;
+        int step = 0;
+        const int n_steps = P.n_pairs * KS;
         for (int j = 0; j < P.n_pairs; ++j) {
           const bool f8 = P.comp && (j & 1);   // compensated precision: odd pairs are the 8-bit correction rows
           for (int s = 0; s < KS; ++s) {
             ptx::mbar_wait(&a_full[sa], pa);
-            if (DRAIN) {   // a fresh accumulator buffer per segment
+            if (DRAIN && step % P.drain_seg == 0) {   // a fresh accumulator buffer per segment of drain_seg steps
               ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
               accumulate = 0;
             }
@@ -197,7 +199,8 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
             }
             ptx::mma_commit_pair(&a_empty[sa]);
             if (++sa == NSA) { sa = 0; pa ^= 1; }
-            if (DRAIN) {
+            ++step;
+            if (DRAIN && (step % P.drain_seg == 0 || step == n_steps)) {
               ptx::mma_commit_pair(&t_full[acc]);
               if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
             }
@@ -242,7 +245,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
         float sum[128];
 #pragma unroll
         for (int i = 0; i < 128; ++i) sum[i] = 0.f;
-        const int n_seg = P.n_pairs * KS;
+        const int n_seg = (P.n_pairs * KS + P.drain_seg - 1) / P.drain_seg;
         const bool mine = static_cast<int>(rank) < n_sub;        // this CTA's 8-column block is inside the image
         for (int seg = 0; seg < n_seg; ++seg) {
           ptx::mbar_wait(&t_full[acc], pacc);

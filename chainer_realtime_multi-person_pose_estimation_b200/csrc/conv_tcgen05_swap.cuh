@@ -144,11 +144,13 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
         }
         uint32_t d = tmem_base + acc * 256;
         uint32_t accumulate = 0;
+        int step = 0;
+        const int n_steps = P.n_pairs * KS;
         for (int j = 0; j < P.n_pairs; ++j) {
           const bool f8 = P.comp && (j & 1);   // compensated precision: odd pairs are the 8-bit correction rows
           for (int s = 0; s < KS; ++s) {
             ptx::mbar_wait(&p_full[sp], pp);
-            if (DRAIN) {   // a fresh accumulator buffer per segment
+            if (DRAIN && step % P.drain_seg == 0) {   // a fresh accumulator buffer per segment of drain_seg steps
               ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
               d = tmem_base + acc * 256;
               accumulate = 0;
@@ -176,7 +178,8 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
             }
             ptx::mma_commit(&p_empty[sp]);
             if (++sp == NSP) { sp = 0; pp ^= 1; }
-            if (DRAIN) {
+            ++step;
+            if (DRAIN && (step % P.drain_seg == 0 || step == n_steps)) {
               ptx::mma_commit(&t_full[acc]);
               if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
             }
@@ -248,7 +251,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
         float sum[128];
 #pragma unroll
         for (int i = 0; i < 128; ++i) sum[i] = 0.f;
-        const int n_seg = P.n_pairs * KS;
+        const int n_seg = (P.n_pairs * KS + P.drain_seg - 1) / P.drain_seg;
         for (int seg = 0; seg < n_seg; ++seg) {
           ptx::mbar_wait(&t_full[acc], pacc);
           ptx::tc_fence_after();

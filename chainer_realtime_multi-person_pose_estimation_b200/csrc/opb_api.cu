@@ -25,6 +25,7 @@
 #include "conv_tcgen05_swap.cuh"
 #include "paf.cuh"
 #include "peaks.cuh"
+#include "peaks_sep.cuh"
 #include "pool.cuh"
 #include "upsample.cuh"
 
@@ -114,6 +115,9 @@ struct PostWs {           // post-process workspace for (N, map_h, map_w)
   const float* last_paf_lo = nullptr;   // low-res maps the last opb_detect_batch upsampled (network or injected)
   const float* last_heat_lo = nullptr;
   int last_h8 = 0, last_w8 = 0;         // their size
+  float* sep_wy = nullptr;              // smooth_nms_sep_kernel: per-row / per-column operator records ([H][8], [W][8] floats)
+  float* sep_wx = nullptr;
+  int sep_h = 0, sep_w = 0;             // low-resolution size the records were built for (0: none); -1: not representable
   float* lo_stage = nullptr;            // opb_postprocess_batch: device copy of host low-res maps [N][57][h8][w8]
   size_t lo_cap = 0;                    // floats
   double last_img_len = 0;
@@ -189,7 +193,8 @@ struct opb_ctx {
   int two_streams = 1;             // OPB_TWO_STREAMS=0: both streaming slots share `stream` and one set of buffers
   int use_graphs = 1;              // OPB_GRAPH=0: streaming mode launches kernel by kernel
   // Post-process variants (A/B on a B200: profiles/r02_lowres_ab.txt; bit-exact against the oracle in every combination):
-  int fused_peaks = 1;             // OPB_FUSED_PEAKS=1: the peak kernel interpolates its tiles from the low-res heat maps;
+  int fused_peaks = 3;             // OPB_FUSED_PEAKS=1: the peak kernel interpolates its tiles from the low-res heat maps;
+                                   // =3: candidates from the separable (bilinear o Gaussian) operator on the low-res maps (peaks_sep.cuh);
                                    // =2: materialised maps, but the tile-skip bound comes from the low-res maps (no cell_max pass)
   int paf_lowres = 1;              // OPB_PAF_LOWRES=1: PAF line integrals sample the low-res PAFs on demand
   int peaks_v2 = 0;                // OPB_PEAKS_V2=1 (with OPB_FUSED_PEAKS=2): smoothing passes spread over all 256 threads
@@ -603,9 +608,12 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
       op.swap = false;
       op.pair = false;
       op.mt = 1;
-      if (comp) op.drain = false;
       if (op.bn > 128 && per_problem_cout_pad % 128 == 0 && tiles_of(false, false, 1, op.bn) * 2 <= ctx->num_sms) op.bn = 128;
       if (op.bn == 128 && !s.pool && tiles_of(false, false, 1, 128) * 2 <= ctx->num_sms) op.bn = 64;
+      if (comp) {   // the plain kernel's two-level accumulation variants (BN <= 128, MT = 1) serve the long-K layers here
+        const char* d = getenv("OPB_COMP_DRAIN");
+        op.drain = op.bn <= 128 && op.ks == 7 && !(d && atoi(d) == 0);
+      }
     }
   }
   std::memset(&op.P, 0, sizeof(op.P));
@@ -635,6 +643,11 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     }
   }
   P.comp = comp ? 1 : 0;
+  {  // two-level accumulation granularity of the swap / pair DRAIN kernels: steps (chunk pair x filter column) per TMEM
+     // buffer.  Default: one chunk pair (KS steps = KS*KS*4 chained MMAs, 196 for 7x7); OPB_DRAIN_SEG overrides.
+    const char* e = getenv("OPB_DRAIN_SEG");
+    P.drain_seg = std::max(1, e ? atoi(e) : op.ks);
+  }
   if (np > kMaxPairs) OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "too many K chunk pairs");
   P.n_pairs = np;
   for (int p = 0; p < s.n_problems; ++p) {
@@ -1001,6 +1014,63 @@ int launch_upsample(opb_ctx* ctx, const float* in, int planes, int h, int w, flo
   return OPB_OK;
 }
 
+// One axis of the combined (align-corners bilinear upsample, then Gaussian with scipy's 'reflect' border) operator of
+// csrc/peaks_sep.cuh: rec[i] = {w0..w5, first input index (int bits), 0}.  false if some output depends on more than
+// PKS_TAPS inputs or the first indices are not non-decreasing (the kernel's sliding window needs both).
+bool build_sep_axis(int n_in, int n_out, const GaussTaps& taps, std::vector<float>& rec) {
+  if (n_in < PKS_TAPS || n_out < 1) return false;
+  const int R = taps.radius;
+  const double step = (n_out > 1) ? static_cast<double>(n_in - 1) / static_cast<double>(n_out - 1) : 0.0;
+  rec.assign(static_cast<size_t>(n_out) * 8, 0.f);
+  std::vector<double> c(n_in);
+  int prev_base = 0;
+  for (int i = 0; i < n_out; ++i) {
+    std::fill(c.begin(), c.end(), 0.0);
+    for (int j = -R; j <= R; ++j) {
+      int ii = i + j;
+      while (ii < 0 || ii >= n_out) { if (ii < 0) ii = -ii - 1; if (ii >= n_out) ii = 2 * n_out - 1 - ii; }
+      const double u = (n_out == 1) ? 0.0 : (ii == n_out - 1) ? static_cast<double>(n_in - 1) : ii * step;
+      int k = static_cast<int>(std::floor(u));
+      k = std::max(0, std::min(k, n_in - 2));
+      c[k] += taps.w[j + R] * (static_cast<double>(k + 1) - u);
+      c[k + 1] += taps.w[j + R] * (u - static_cast<double>(k));
+    }
+    int lo = 0, hi = n_in - 1;
+    while (lo < n_in - 1 && c[lo] == 0.0) ++lo;
+    while (hi > lo && c[hi] == 0.0) --hi;
+    if (hi - lo + 1 > PKS_TAPS) return false;
+    int base = std::max(0, std::min(lo, n_in - PKS_TAPS));
+    base = std::max(base, prev_base);                    // keep the window monotone (it still has to cover [lo, hi])
+    if (base > lo || base + PKS_TAPS - 1 < hi) return false;
+    prev_base = base;
+    for (int k = 0; k < PKS_TAPS; ++k) rec[static_cast<size_t>(i) * 8 + k] = static_cast<float>(c[base + k]);
+    std::memcpy(&rec[static_cast<size_t>(i) * 8 + 6], &base, sizeof(int));
+  }
+  return true;
+}
+
+// (re)builds the operator records of workspace `ws` for low-resolution size (h_lo, w_lo); *ok = usable
+int ensure_sep_axes(opb_ctx* ctx, PostWs* ws, int h_lo, int w_lo, bool* ok) {
+  if (ws->sep_h == h_lo && ws->sep_w == w_lo) { *ok = true; return OPB_OK; }
+  if (ws->sep_h == -h_lo - 1 && ws->sep_w == -w_lo - 1) { *ok = false; return OPB_OK; }
+  std::vector<float> ry, rx;
+  const bool good = ctx->taps.radius == PK_R_FAST && ws->H <= 4096 && build_sep_axis(h_lo, ws->H, ctx->taps, ry) &&
+                    build_sep_axis(w_lo, ws->W, ctx->taps, rx) &&
+                    smooth_nms_sep_smem_bytes(ws->H, PKS_MAX_WARPS) <= 200 * 1024;
+  if (!good) { ws->sep_h = -h_lo - 1; ws->sep_w = -w_lo - 1; *ok = false; return OPB_OK; }
+  if (!ws->sep_wy) {
+    int rc = dev_alloc(ctx, &ws->sep_wy, static_cast<size_t>(ws->H) * 8, ws->allocs, false);
+    if (rc) return rc;
+    if ((rc = dev_alloc(ctx, &ws->sep_wx, static_cast<size_t>(ws->W) * 8, ws->allocs, false))) return rc;
+  }
+  OPB_CUDA(ctx, cudaMemcpyAsync(ws->sep_wy, ry.data(), ry.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  OPB_CUDA(ctx, cudaMemcpyAsync(ws->sep_wx, rx.data(), rx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors die here
+  ws->sep_h = h_lo; ws->sep_w = w_lo;
+  *ok = true;
+  return OPB_OK;
+}
+
 // heat: [n][c_total][H][W]; fills ws->peaks / idx_list / type_start / peak_counts.
 // h_lo > 0: `heat` is the network-resolution map [n][c_total][h_lo][w_lo] and the peak kernel interpolates its tiles
 // from it (smooth_nms_lowres_kernel): the same peaks as upsampling to (H, W) first, without the full-resolution map.
@@ -1033,7 +1103,29 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
       attr3 = true;
     }
     if (h_lo < 2 || w_lo < 2) OPB_FAIL(ctx, OPB_ERR_ARG, "low-resolution maps need at least 2 x 2 samples");
-    if (heat_full && ctx->peaks_v2 && ctx->taps.radius == PK_R_FAST) {   // + both smoothing passes on all threads
+    bool sep = false;
+    if (!heat_full && ctx->fused_peaks == 3 && H == ws->H && W == ws->W) {   // separable-operator candidate search (peaks_sep.cuh)
+      int rc = ensure_sep_axes(ctx, ws, h_lo, w_lo, &sep);
+      if (rc) return rc;
+    }
+    if (sep) {
+      // warps per block: 30 owned columns each; pick the count that wastes the fewest lanes over the plane width
+      int nw = 4, best = 1 << 30;
+      for (int k = 4; k <= PKS_MAX_WARPS; ++k) {
+        const int waste = ((W + 30 * k - 1) / (30 * k)) * 30 * k - W;
+        if (waste < best || (waste == best && k > nw)) { best = waste; nw = k; }
+      }
+      static bool attr5_d[64] = {};
+      if (!attr5_d[ctx->device & 63]) {
+        OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr5_d[ctx->device & 63] = true;
+      }
+      dim3 gs((W + 30 * nw - 1) / (30 * nw), 1, n * c_use);
+      SepAxes axes{ws->sep_wy, ws->sep_wx};
+      smooth_nms_sep_kernel<<<gs, nw * 32, smooth_nms_sep_smem_bytes(H, nw), ctx->stream>>>(
+          heat, c_total, c_use, h_lo, w_lo, H, W, ctx->taps, static_cast<float>(p.heatmap_peak_thresh), axes, ws->keys,
+          ws->peak_counts, p.max_peaks);
+    } else if (heat_full && ctx->peaks_v2 && ctx->taps.radius == PK_R_FAST) {   // + both smoothing passes on all threads
       if (!attr4) {
         OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_loskip_kernel_v2<PK_R_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr4 = true;
@@ -1652,7 +1744,7 @@ static int run_postprocess(opb_ctx* ctx, PostWs* ws, int n, int h8, int w8, int 
     if ((rc = launch_upsample(ctx, paf_lo, n * 38, h8, w8, ws->pafs, map_h, map_w))) return rc;
     prof_mark(ctx, "upsample_paf");
   }
-  if (ctx->fused_peaks == 1) {
+  if (ctx->fused_peaks == 1 || ctx->fused_peaks == 3) {
     if ((rc = launch_peaks(ctx, ws, heat_lo, n, 19, map_h, map_w, h8, w8))) return rc;
   } else if (ctx->fused_peaks == 2) {
     if ((rc = launch_upsample(ctx, heat_lo, n * 19, h8, w8, ws->heat, map_h, map_w))) return rc;
@@ -2195,7 +2287,7 @@ int opb_time_stage(opb_ctx* ctx, const char* stage, int reps, float* ms) {
       if (s == "upsample_paf") { ++n_launch; return launch_upsample(ctx, plo, n * 38, h8, w8, ws->pafs, ws->H, ws->W); }
       if (s == "upsample_heat") { ++n_launch; return launch_upsample(ctx, hlo, n * 19, h8, w8, ws->heat, ws->H, ws->W); }
       if (s == "peaks") {
-        if (ctx->fused_peaks == 1) { n_launch += 2; return launch_peaks(ctx, ws, hlo, n, 19, ws->H, ws->W, h8, w8); }
+        if (ctx->fused_peaks == 1 || ctx->fused_peaks == 3) { n_launch += 2; return launch_peaks(ctx, ws, hlo, n, 19, ws->H, ws->W, h8, w8); }
         if (ctx->fused_peaks == 2) { n_launch += 2; return launch_peaks(ctx, ws, hlo, n, 19, ws->H, ws->W, h8, w8, ws->heat); }
         n_launch += 3;
         return launch_peaks(ctx, ws, ws->heat, n, 19, ws->H, ws->W);

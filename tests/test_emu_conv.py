@@ -87,6 +87,23 @@ def test_conv_vs_torch(engine, emu_native, case, mode):
     assert err <= tol, "max abs err %.3e > tol %.3e (scale %.3f)" % (err, tol, scale)
 
 
+@pytest.mark.parametrize("case", [(1, 24, 30, 128, 128, 7, 1), (1, 24, 24, 185, 256, 7, 1)], ids=lambda c: "n%d_%dx%d_c%d_o%d_k%d" % c[:6])
+def test_comp_small_batch_two_level_accumulation(emu_native, monkeypatch, case):
+    """compensated precision on a launch that fills less than half a wave (one camera frame): add_conv then picks the plain
+    kernel's two-level accumulation variants (BN <= 128, MT = 1) with the 8-bit correction rows and the three-plane
+    epilogue -- the path PoseDetector.__call__ takes for a single frame."""
+    monkeypatch.setenv("OPB_EMU_SMS", "148")
+    n, h, w, cin, cout, ks, relu = case
+    rs = np.random.RandomState(sum(case) + 1)
+    x = rs.standard_normal((n, h, w, cin)).astype(np.float32)
+    W = (rs.standard_normal((cout, cin, ks, ks)) * np.sqrt(2.0 / (cin * ks * ks))).astype(np.float32)
+    b = (rs.standard_normal(cout) * 0.1).astype(np.float32)
+    eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params())
+    y = eng.test_conv(x, W, b, relu, emu_native.PRECISION_COMP)
+    ref = G._ref_conv(x, W, b, relu, quantize=False)
+    assert np.abs(y - ref).max() <= 3e-4 * np.abs(ref).max()
+
+
 def _emu_stats(lib):
     st = (C.c_longlong * 4)()
     lib.opb_emu_stats(st)

@@ -205,13 +205,13 @@ def test_keypoints_exact_ties_and_threshold(engine):
                 assert (a[0], a[1]) == (b[0], b[1]) and np.float32(a[2]) == np.float32(b[2]), (a, b)
 
 
-@pytest.mark.parametrize("fused_peaks,paf_lowres", [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1), (2, 1)])
+@pytest.mark.parametrize("fused_peaks,paf_lowres", [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1), (2, 1), (3, 1)])
 def test_postprocess_batch_from_network_resolution_maps(emu_native, monkeypatch, request, fused_peaks, paf_lowres):
     """opb_postprocess_batch = pose_detector.py:501-512 for a batch; with OPB_FUSED_PEAKS / OPB_PAF_LOWRES the peak
     kernel / the PAF line integrals interpolate from the low-resolution maps on demand -- every variant must give the
     oracle's peaks, connections, subsets and person records bit for bit (OPB_FUSED_PEAKS=2: materialised maps, tile-skip
     bound from the low-resolution maps)."""
-    if request.node.callspec.params["emu_lib"] == "fma" and (fused_peaks, paf_lowres) not in ((0, 0), (1, 1), (2, 1)):
+    if request.node.callspec.params["emu_lib"] == "fma" and (fused_peaks, paf_lowres) not in ((0, 0), (1, 1), (2, 1), (3, 1)):
         pytest.skip("the contraction build repeats only the corner combinations (suite time)")
     monkeypatch.setenv("OPB_FUSED_PEAKS", str(fused_peaks))
     monkeypatch.setenv("OPB_PAF_LOWRES", str(paf_lowres))

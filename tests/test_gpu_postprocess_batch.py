@@ -30,7 +30,7 @@ def test_postprocess_batch_materialised_maps(monkeypatch):
     run_batch_cases(_engine())
 
 
-@pytest.mark.parametrize("fused_peaks,paf_lowres", [(1, 0), (2, 0), (0, 1), (1, 1), (2, 1)])
+@pytest.mark.parametrize("fused_peaks,paf_lowres", [(1, 0), (2, 0), (0, 1), (1, 1), (2, 1), (3, 0), (3, 1)])
 def test_postprocess_batch_lowres_variants(monkeypatch, fused_peaks, paf_lowres):
     monkeypatch.setenv("OPB_FUSED_PEAKS", str(fused_peaks))
     monkeypatch.setenv("OPB_PAF_LOWRES", str(paf_lowres))
