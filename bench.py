@@ -38,8 +38,32 @@ FLOPS_PER_IMAGE = 484634285056            # SURVEY.md 8d, true channel counts
 METRIC = "frames/sec at 368x656 batch32 (full pipeline: conv + NMS + PAF integral + grouping)"
 
 
+DTYPES = {"fast": "f16 (fp32 accumulate)", "parity": "split-f16 (hi+lo, 3 MMAs, two-level fp32 accumulation)",
+          "comp": "f16 + f8 rounding corrections (2 MMAs, fp32 accumulate, two-level on the 7x7 layers)"}
+MAP_ERR = {"fast": "2.8e-3 (outside north_star's 1e-3: reported for the fp16 roofline config only)",
+           "parity": "1.9e-5", "comp": "1.6e-4 .. 5.3e-4 on the three fast goldens (profiles/r02_precision_ladder.txt)"}
+
+
 def pkg(sub=None):
     return importlib.import_module(PKG + ("." + sub if sub else ""))
+
+
+def traffic_from_profile(precision):
+    """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, read from the committed
+    ncu summary of this precision (profiles/r02_ncu_<precision>_swap7x7_summary.txt); None when there is none."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_%s_swap7x7_summary.txt" % precision)
+    if not os.path.isfile(path):
+        return None, "no committed ncu --set full summary for this precision (%s)" % os.path.basename(path)
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, seen = 0.0, 0
+    for ln in open(path):
+        f = ln.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in mult:
+            tot += float(f[1].replace(",", "")) * mult[f[2]]
+            seen += 1
+    if seen != 2:
+        return None, "dram__bytes_read/write not found in " + os.path.basename(path)
+    return tot, "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/" + os.path.basename(path)
 
 
 def measured_peaks():
@@ -183,10 +207,15 @@ def run_ours(args):
     d_heat = torch.from_numpy(np.repeat(heat_lo[None], B, 0)).cuda()
     hdr_dev = torch.zeros(B * native.HEADER_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
     per_dev = torch.zeros(B * args.max_persons * native.PERSON_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-    rec_local = torch.zeros(hdr_dev.numel() + per_dev.numel(), dtype=torch.uint8, device="cuda")
-    gathered = [None]
-    rec_pinned = torch.zeros(rec_local.numel(), dtype=torch.uint8).pin_memory()
-    rec_np = rec_pinned.numpy()
+    # N > 1: the ONE collective of the path is opb_allgather_results -- an ncclAllGather of the slot's device-resident
+    # record block [B headers | B x max_persons persons] on the slot's stream, straight behind its pipeline (no host hop).
+    # The library's own communicator: rank 0 creates the NCCL id, torch.distributed ships it.
+    rec_bytes = eng.record_block_bytes(B)
+    gathered = [torch.zeros(world * rec_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    if world > 1:
+        uid = torch.from_numpy(eng.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+        dist.broadcast(uid, 0)
+        eng.nccl_comm_init(world, rank, uid.cpu().numpy())
     hdr_host = np.empty(B, native.HEADER_DTYPE)
     per_host = np.empty((B, args.max_persons), native.PERSON_DTYPE)
     import ctypes as C
@@ -204,8 +233,11 @@ def run_ours(args):
     res_state = {"slot": 0, "primed": False, "hdr": None}
 
     def res_submit():
-        eng.stream_submit((imgs_dev2[res_state["slot"]].data_ptr(), B, H, W), H, W, MAP_H, MAP_W, res_state["slot"],
+        sl = res_state["slot"]
+        eng.stream_submit((imgs_dev2[sl].data_ptr(), B, H, W), H, W, MAP_H, MAP_W, sl,
                           img_len=MAP_W, inject_paf=d_paf.data_ptr(), inject_heat=d_heat.data_ptr(), device=True)
+        if world > 1:
+            eng.allgather_results(sl, gathered[sl].data_ptr())     # ONE NCCL all-gather per step, device to device
         res_state["slot"] ^= 1
 
     def step_resident():
@@ -213,13 +245,8 @@ def run_ours(args):
             res_submit()
             res_state["primed"] = True
         res_submit()
-        hdr, per = eng.stream_collect(res_state["slot"])           # the batch submitted one step earlier
+        hdr, per = eng.stream_collect(res_state["slot"])           # the batch submitted one step earlier (and its all-gather)
         res_state["hdr"] = hdr
-        if world > 1:
-            rec_np[:hdr.nbytes] = hdr.view(np.uint8).ravel()
-            rec_np[hdr.nbytes:] = per.view(np.uint8).ravel()
-            rec_local.copy_(rec_pinned, non_blocking=True)
-            gathered[0] = mg.all_gather_records(rec_local, B)      # ONE NCCL all-gather per step
 
     def step_e2e_sync():
         eng._check(eng.lib.opb_detect_batch(eng.ctx, C.c_void_p(imgs_host.data_ptr()), native.OPB_HOST, B, H, W,
@@ -234,8 +261,11 @@ def run_ours(args):
     e2e_state = {"slot": 0, "primed": False, "hdr": None}
 
     def e2e_submit():
-        eng.stream_submit((imgs_host2[e2e_state["slot"]].data_ptr(), B, H, W), H, W, MAP_H, MAP_W, e2e_state["slot"],
+        sl = e2e_state["slot"]
+        eng.stream_submit((imgs_host2[sl].data_ptr(), B, H, W), H, W, MAP_H, MAP_W, sl,
                           img_len=MAP_W, inject_paf=d_paf.data_ptr(), inject_heat=d_heat.data_ptr())
+        if world > 1:
+            eng.allgather_results(sl, gathered[sl].data_ptr())     # the collective is inside the end-to-end step too
         e2e_state["slot"] ^= 1
 
     def step_e2e():
@@ -262,25 +292,32 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        per_rank = [float(ms.item())]
         if world > 1:
+            allms = torch.zeros(world, device="cuda")
+            dist.all_gather_into_tensor(allms, ms)
+            per_rank = [float(v) for v in allms.cpu()]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        timed.per_rank_ms = per_rank
         return float(ms.item()), eng.launch_count() - l0
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
+    per_rank_ms = [m / args.steps for m in timed.per_rank_ms]
     clocks = sampler.stop() if sampler else None
     # correctness of the timed path: 8 persons per frame (last collected batch and the one still in flight)
     hdr_last, _ = eng.stream_collect(res_state["slot"] ^ 1)
     for hdr in (res_state["hdr"], hdr_last):
         assert (hdr["status"] == 0).all() and (hdr["n_persons"] == 8).all(), hdr
     ms_sync, _ = timed(step_resident_sync, args.steps, args.warmup)
-    if world > 1:   # every rank holds every rank's records after the all-gather
-        g = gathered[0].cpu().numpy().reshape(world, -1)
-        for r in range(world):
-            gh = np.frombuffer(g[r, :hdr_dev.numel()].tobytes(), native.HEADER_DTYPE)
-            assert (gh["n_persons"] == 8).all()
+    if world > 1:   # every rank holds every rank's records after the all-gather (both slots' buffers)
+        for gbuf in gathered:
+            g = gbuf.cpu().numpy().reshape(world, -1)
+            for r in range(world):
+                gh = np.frombuffer(g[r, :hdr_dev.numel()].tobytes(), native.HEADER_DTYPE)
+                assert (gh["status"] == 0).all() and (gh["n_persons"] == 8).all(), (r, gh)
     ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
     hdr_last, _ = eng.stream_collect(e2e_state["slot"] ^ 1)         # drain the batch still in flight
     for hh in (e2e_state["hdr"], hdr_last):
@@ -306,16 +343,30 @@ def run_ours(args):
     flops77 = 2 * (2.0 * B * (H // 8) * (W // 8) * 128 * 128 * 49)
     ach = flops77 / (ms77 * 1e-3) / 1e12
     ms_chain = eng.time_stage("conv_chain", reps=3)
+    # PAF HBM figures.  The default pipeline no longer materialises the full-resolution PAFs (the line
+    # integrals sample the network-resolution maps on demand, OPB_PAF_LOWRES=1), so the HBM-bound kernel of the
+    # reference's data flow (F.resize_images, pose_detector.py:501) is timed on its own here, and then together with the
+    # line-integral stage over the materialised maps, each against its own algorithmic bytes.
     ms_up = eng.time_stage("upsample_paf", reps=10)
-    paf_bytes = B * (38 * (H // 8) * (W // 8) * 4 + 38 * MAP_H * MAP_W * 4) + 80 * 151 * B
+    up_bytes = B * (38 * (H // 8) * (W // 8) * 4 + 38 * MAP_H * MAP_W * 4)          # low-res read + full-res write
+    stage_ms = {s_: eng.time_stage(s_, reps=5) for s_ in ("upsample_heat", "peaks", "paf_integral", "group")}
+    n_pairs = 1193                                                                 # candidate pairs per synthetic 8-person frame
+    both_bytes = up_bytes + 80 * n_pairs * B
     extra = {
         "conv_chain_ms": ms_chain,
         "conv_chain_tflops": B * FLOPS_PER_IMAGE / (ms_chain * 1e-3) / 1e12,
         "conv_chain_frac_of_sustained_peak": B * FLOPS_PER_IMAGE / (ms_chain * 1e-3) / 1e12 / (peaks["tflops_sustained"] or peaks["tflops"]),
-        "paf_upsample_integrate": {"bound": "hbm", "achieved": paf_bytes / (ms_up * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                                   "unit": "GB/s", "frac": paf_bytes / (ms_up * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                   "ms": ms_up},
-        "stage_ms": {s: eng.time_stage(s, reps=5) for s in ("upsample_heat", "peaks", "paf_integral", "group")},
+        "paf_upsample_materialise": {"bound": "hbm", "kernel": "upsample_bilinear_ac_v4_kernel (38 PAF planes per image)",
+                                     "bytes": up_bytes, "achieved": up_bytes / (ms_up * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                     "unit": "GB/s", "frac": up_bytes / (ms_up * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": ms_up,
+                                     "note": "the upsample launch alone; not part of the default pipeline any more"},
+        "paf_upsample_plus_line_integral": {"bound": "hbm", "bytes": both_bytes, "ms": ms_up + stage_ms["paf_integral"],
+                                            "achieved": both_bytes / ((ms_up + stage_ms["paf_integral"]) * 1e-3) / 1e9,
+                                            "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                            "frac": both_bytes / ((ms_up + stage_ms["paf_integral"]) * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                            "note": "upsample launch + the paf_integral stage (paf_candidates + limb_assign, as the default "
+                                                    "pipeline runs them) over upsample bytes + 80 B per candidate pair"},
+        "stage_ms": stage_ms,
     }
     # camera-style latency: one 640x480 BGR frame through the public PoseDetector.__call__ (host resize,
     # H2D, conv chain, post-process, D2H), the loop of camera_pose_demo.py:20-31
@@ -395,22 +446,26 @@ def run_ours(args):
                                              "so sector traffic is ~8x the algorithmic bytes (latency-bound, not an HBM roofline)"}
     except Exception as e:
         extra["paf_gather_dense"] = {"error": str(e)[:200]}
-    # The precision that meets north_star's 1e-3 map tolerance (split-fp16 "parity": 1.9e-5 vs the fp32 oracle; the
-    # headline runs fp16 "fast" as BASELINE.json configs[1] names it: 2.8e-3).  Measured in a child process so that
-    # nothing it does can cost the headline line; same workload, synchronous device-resident entry.
-    if args.precision == "fast" and world == 1 and not args.no_parity_extra:
-        try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--precision", "parity", "--steps", "3", "--warmup", "3",
-                                "--no-stage-timing", "--no-cpu-baseline", "--batch", str(B), "--max-persons", str(args.max_persons)],
-                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=150)
-            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            d = json.loads(line[-1]) if line else None
-            extra["parity_precision"] = ({"value": d["value"], "unit": "frames/s", "ms_per_step": d["ms_per_step"],
-                                          "e2e": d["e2e"]["value"], "dtype": "split-f16 (hi+lo), 3 MMAs per K step, fp32 two-level accumulation",
-                                          "note": "meets the 1e-3 map tolerance (1.9e-5); child process, 3 steps"}
-                                         if d else {"error": (r.stderr or "no output")[-200:]})
-        except Exception as e:
-            extra["parity_precision"] = {"error": str(e)[:200]}
+    # The other precisions on the same workload, each in a child process so that nothing they do can cost the headline line:
+    # "fast" = plain fp16, the precision BASELINE.json configs[1] names for the conv roofline (map error 2.8e-3: outside the
+    # 1e-3 tolerance, so it is an extra, not the headline); "parity" = split fp16, the most accurate (1.9e-5).
+    if world == 1 and not args.no_parity_extra:
+        for other in [p for p in ("fast", "parity") if p != args.precision]:
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--precision", other, "--steps", "5", "--warmup", "3",
+                                    "--no-cpu-baseline", "--no-parity-extra", "--batch", str(B), "--max-persons", str(args.max_persons)],
+                                   stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
+                line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                d = json.loads(line[-1]) if line else None
+                extra[other + "_precision"] = ({"value": d["value"], "unit": "frames/s", "ms_per_step": d["ms_per_step"],
+                                                "e2e": d["e2e"]["value"], "dtype": d["dtype"], "map_error_vs_reference": MAP_ERR[other],
+                                                "roofline": {k: d["roofline"][k] for k in ("achieved", "peak", "frac", "ms_per_launch", "kernel")},
+                                                "conv_chain_ms": d["extra"].get("conv_chain_ms"),
+                                                "conv_chain_tflops": d["extra"].get("conv_chain_tflops"),
+                                                "note": "child process, 5 steps after 3 warm-ups"}
+                                               if d else {"error": (r.stderr or "no output")[-200:]})
+            except Exception as e:
+                extra[other + "_precision"] = {"error": str(e)[:200]}
     # CPU baseline: the oracle port on this box's host cores, bounded sample
     cpu = None
     if not args.no_cpu_baseline and world == 1:            # rank 0 at N = 1 only
@@ -422,14 +477,28 @@ def run_ours(args):
                "sample": "1 timed frame after 1 warm-up per thread setting (reference is batch-1), best of the "
                          "settings tried within 30 s; host has %d logical cores; torch-CPU fp32 conv + NumPy/SciPy "
                          "post-process" % os.cpu_count()}
+    traffic, traffic_note = traffic_from_profile(args.precision)
+    mma_per_kstep = {"fast": 1, "parity": 3, "comp": 2}[args.precision]
+    roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                "traffic": traffic, "traffic_note": traffic_note,
+                "kernel": "grouped L1+L2 7x7 128->128 launch (Mconv2..5 of stages 2-6), 20 launches/step: "
+                          + {"fast": "conv_tcgen05_swap_kernel<7,3,5>", "comp": "conv_tcgen05_swap_kernel<7,3,5,DRAIN> (kind::f16 + kind::f8f6f4)",
+                             "parity": "conv_tcgen05_kernel<7,128,1,3,6,2,DRAIN>"}[args.precision],
+                "flops_per_launch": flops77, "ms_per_launch": ms77,
+                "note": "achieved = ALGORITHMIC flops (2*Cin*Cout*49 per pixel, true channels) / CUDA-event time; this precision "
+                        "issues %d MMA(s) per k-step (8-bit-float correction MMAs run at twice the fp16 rate), so the tensor pipe is "
+                        "busy for %.2f of the launch at the measured fp16 peak" % (
+                            mma_per_kstep, (1.0 if args.precision != "comp" else 2.0) * (1 if args.precision != "parity" else 3) * ach / peaks["tflops"])}
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f16" if args.precision == "fast" else "split-f16 (hi+lo)", "data": "synthetic",
+        "vs_baseline": None, "dtype": DTYPES[args.precision], "data": "synthetic",
         "config": {"workload": "BASELINE.json configs[2]: full pipeline, synthetic 8-person maps injected, 368x656, "
                                "batch %d per GPU" % B,
-                   "precision": args.precision, "global_batch": world * B,
-                   "parallelism": "image-sharded x%d, 1 all-gather of person records per step" % world,
+                   "precision": args.precision, "map_error_vs_reference": MAP_ERR[args.precision], "global_batch": world * B,
+                   "per_rank_ms_per_step": per_rank_ms,
+                   "parallelism": "image-sharded x%d, 1 ncclAllGather of the device-resident person records per step "
+                                  "(opb_allgather_results, inside the timed region of value and e2e)" % world,
                    "l2": "no explicit flush: activations written/read per step (~4.5 GB) exceed the 126 MB L2",
                    "peaks": peaks["source"]},
         "gpu_launches": launches,
@@ -442,13 +511,7 @@ def run_ours(args):
                        "batch i+1 overlap batch i)",
                 "sync_api": {"value": world * B * args.steps / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync / args.steps,
                              "api": "opb_detect_batch with host buffers (upload, kernels, download serialised)"}},
-        "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": ach / peaks["tflops"], "traffic": 86.9e6,
-                     "traffic_note": "bytes per launch = ncu dram__bytes_read.sum (65.1 MB) + dram__bytes_write.sum (21.8 MB), "
-                                     "profiles/r01_conv7x7_swap_ncu_full_summary.txt; algorithmic: 65.0 MB read + 61.8 MB write "
-                                     "(the rest of the write is still dirty in the 126 MB L2 when the kernel ends)",
-                     "kernel": "conv_tcgen05_swap_kernel<7,3,5>: grouped L1+L2 7x7 128->128 (Mconv2..5), 20 launches/step",
-                     "flops_per_launch": flops77, "ms_per_launch": ms77},
+        "roofline": roofline,
         "cpu_baseline": cpu, "clocks": clocks, "extra": extra,
     }
     print(json.dumps(out))
@@ -463,11 +526,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--precision", default="fast", choices=["fast", "parity", "comp"])
+    ap.add_argument("--precision", default="comp", choices=["fast", "parity", "comp"],
+                    help="comp (default): the fastest precision inside the 1e-3 map tolerance; fast: fp16 (roofline config); parity: split fp16")
     ap.add_argument("--max-persons", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the per-stage re-launches (clean ncu launch lists)")
-    ap.add_argument("--no-parity-extra", action="store_true", help="skip the parity-precision throughput extra (child process)")
+    ap.add_argument("--no-parity-extra", action="store_true", help="skip the other-precision throughput extras (child processes)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

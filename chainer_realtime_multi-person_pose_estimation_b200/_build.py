@@ -24,7 +24,7 @@ def build_native(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-           "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3", "-o", LIB, SRC] + os.environ.get("OPB_NVCC_FLAGS", "").split()
+           "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3", "-o", LIB, SRC, "-ldl"] + os.environ.get("OPB_NVCC_FLAGS", "").split()
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

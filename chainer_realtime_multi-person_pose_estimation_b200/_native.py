@@ -66,6 +66,11 @@ _SIGNATURES = {
                                     C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "opb_stream_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "opb_stream_join": (C.c_int, [C.c_void_p]),
+    "opb_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "opb_nccl_comm_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),
+    "opb_nccl_comm_destroy": (C.c_int, [C.c_void_p]),
+    "opb_record_block_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "opb_allgather_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "opb_keypoints_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "opb_keypoints_from_heatmaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -335,6 +340,31 @@ class Engine(object):
                                                map_h, map_w,
                                                float(map_w if img_len is None else img_len),
                                                C.c_void_p(inject_paf or 0), C.c_void_p(inject_heat or 0), slot))
+
+    # ---- multi-GPU: the ONE collective of the path (include/opb.h: opb_allgather_results)
+    def nccl_unique_id(self):
+        """128-byte NCCL id (rank 0 creates it and ships it to the other ranks, e.g. torch.distributed.broadcast)."""
+        buf = np.zeros(128, np.uint8)
+        rc = self.lib.opb_nccl_unique_id(C.c_void_p(buf.ctypes.data))
+        if rc:
+            raise OpbError("opb_nccl_unique_id failed (%d): %s" % (rc, (self.lib.opb_last_error(None) or b"").decode()))
+        return buf
+
+    def nccl_comm_init(self, world, rank, unique_id):
+        comm = C.c_void_p()
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        self._check(self.lib.opb_nccl_comm_init(self.ctx, C.byref(comm), int(world), int(rank), C.c_void_p(uid.ctypes.data)))
+        self._nccl_comm = comm
+        return comm
+
+    def record_block_bytes(self, n):
+        return int(self.lib.opb_record_block_bytes(self.ctx, int(n)))
+
+    def allgather_results(self, slot, gathered_dev_ptr, comm=None):
+        """ncclAllGather of streaming slot `slot`'s device-resident record block into the device buffer at
+        gathered_dev_ptr (world x record_block_bytes(n) bytes), on the slot's stream behind its pipeline."""
+        self._check(self.lib.opb_allgather_results(self.ctx, comm if comm is not None else self._nccl_comm, int(slot),
+                                                   C.c_void_p(int(gathered_dev_ptr))))
 
     def stream_join(self):
         """Make the context's stream wait for every submitted, uncollected batch (opb_stream_join)."""

@@ -284,4 +284,154 @@ conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict_
   if (warp == 0) ptx::tmem_dealloc<64>(tmem);
 }
 
+// ------------------------------------------------------------------------------------------------
+// EXACT tensor-core conv1_1 for the precisions that must stay inside the 1e-3 map tolerance (compensated, parity).
+// preprocess (pose_detector.py:426-431) is affine in the uint8 pixel, x = u/255 - 0.5, and zero padding sets x (not u)
+// to zero, so
+//     conv(x, W)[o] = sum_{taps in the image} ( sum_c u_c * W[o,c,tap]/255  -  0.5 * sum_c W[o,c,tap] ).
+// The im2col row of a pixel therefore holds the 27 raw uint8 values (exact in fp16; 0 where padded) followed by 9
+// in-image indicators (1 / 0), K = 36 -> 48, and the weight matrix holds W/255 and -0.5*sum_c W per tap, each as
+// hi + lo fp16 (pre-scaled by the exact power of two 2^S; the epilogue multiplies by 2^-S).  Every product is exact
+// (8 x 11 significant bits) and the result agrees with the fp32 reference to ~1e-7 relative: 6 MMAs of N = 64 per
+// 16 x 8 tile instead of 1728 fp32 FMAs per pixel.
+// wth: [2][64][64] fp16 = {hi, lo} x (row = output channel, k as above, k >= 36 zero); out_mode 0: fp16 only,
+// 1: parity (hi | lo planes), 2: compensated (hi | correction bytes).
+__global__ void __launch_bounds__(128)
+conv_first_tcx_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict__ wth, const float* __restrict__ bias,
+                      __half* __restrict__ out, int N, int H, int W, int cstride, int lo_off, int out_mode, float acc_scale) {
+  __shared__ __align__(1024) uint8_t sA[128 * 128];
+  __shared__ __align__(1024) uint8_t sB[2 * 64 * 128];
+  __shared__ __align__(4) __half s_val[18 * 10 * 3 + 4];   // raw pixel values of the halo tile as fp16, [row][col][c]
+  __shared__ float s_bias[64];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid < 64) s_bias[tid] = bias[tid];
+  {  // weight rows: 2 x 64 rows of 64 halfs (128 B), 16-byte chunk j of row r stored at chunk j ^ (r & 7)
+    const int r = tid & 63, part = tid >> 6;
+    const uint4* src = reinterpret_cast<const uint4*>(wth + (part * 64 + r) * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(sB + part * 8192 + r * 128 + ((j ^ (r & 7)) * 16)) = src[j];
+  }
+  {  // chunks 6, 7 of A (k = 48..63) are never read; keep them finite
+#pragma unroll
+    for (int j = 6; j < 8; ++j) *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) * 16)) = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) { ptx::mbar_init(&s_bar, 1); ptx::fence_barrier_init(); }
+  if (warp == 0) ptx::tmem_alloc<64>(&s_tmem);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(sA), 1024);
+  const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(sB), 1024);
+  constexpr uint32_t IDESC = ptx::umma_idesc_f16(128, 64);
+
+  const int tiles_x = (W + 7) >> 3, tiles_y = (H + 15) >> 4;
+  const int total = N * tiles_y * tiles_x;
+  const int hl = tid >> 3, wl = tid & 7;
+  uint32_t parity = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int n = tile / (tiles_y * tiles_x);
+    const int rem = tile - n * (tiles_y * tiles_x);
+    const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
+    for (int i = tid; i < 18 * 10 * 3; i += 128) {
+      const int c = i % 3, q = i / 3;
+      const int xx = x0 - 1 + q % 10, yy = y0 - 1 + q / 10;
+      int v = 0;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x_u8[((static_cast<size_t>(n) * H + yy) * W + xx) * 3 + c];
+      s_val[i] = __ushort2half_rn(static_cast<unsigned short>(v));
+    }
+    __syncthreads();
+    {
+      uint32_t seg[3][5];               // seg[r][j] = halfs (2j, 2j+1) of row r's 9-half segment (half 9 is junk)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int o = ((hl + r) * 10 + wl) * 3;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_val) + (o >> 1);
+        const uint32_t sh = (o & 1) * 16;
+        uint32_t w[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) w[j] = wp[j];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) seg[r][j] = __funnelshift_r(w[j], w[j + 1], sh);
+      }
+      const uint32_t LO_LO = 0x5410, HI_LO = 0x5432;   // __byte_perm selectors: (a.lo, b.lo), (a.hi, b.lo)
+      // in-image indicators of the 9 taps (row r: y0+hl+r-1, column s: x0+wl+s-1), fp16 1.0 = 0x3C00
+      const int y = y0 + hl, x = x0 + wl;
+      uint32_t ind[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int sx = 0; sx < 3; ++sx)
+          ind[r * 3 + sx] = (y + r - 1 >= 0 && y + r - 1 < H && x + sx - 1 >= 0 && x + sx - 1 < W) ? 0x3C00u : 0u;
+      uint32_t pk[24];
+      pk[0] = seg[0][0]; pk[1] = seg[0][1]; pk[2] = seg[0][2]; pk[3] = seg[0][3];
+      pk[4] = __byte_perm(seg[0][4], seg[1][0], LO_LO);            // (a8, b0)
+      pk[5] = __byte_perm(seg[1][0], seg[1][1], HI_LO);            // (b1, b2)
+      pk[6] = __byte_perm(seg[1][1], seg[1][2], HI_LO);
+      pk[7] = __byte_perm(seg[1][2], seg[1][3], HI_LO);
+      pk[8] = __byte_perm(seg[1][3], seg[1][4], HI_LO);            // (b7, b8)
+      pk[9] = seg[2][0]; pk[10] = seg[2][1]; pk[11] = seg[2][2]; pk[12] = seg[2][3];
+      pk[13] = (seg[2][4] & 0xffffu) | (ind[0] << 16);             // (c8, i0)            k = 26, 27
+      pk[14] = ind[1] | (ind[2] << 16);                            // k = 28, 29
+      pk[15] = ind[3] | (ind[4] << 16);
+      pk[16] = ind[5] | (ind[6] << 16);
+      pk[17] = ind[7] | (ind[8] << 16);                            // k = 34, 35
+#pragma unroll
+      for (int j = 18; j < 24; ++j) pk[j] = 0u;
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) * 16)) =
+            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      ptx::mma_f16_ss(tmem, a_desc, b_desc, IDESC, 0u);                          // hi weights, k-steps 0..2
+      ptx::mma_f16_ss_acc(tmem, a_desc + 2, b_desc + 2, IDESC);
+      ptx::mma_f16_ss_acc(tmem, a_desc + 4, b_desc + 4, IDESC);
+      ptx::mma_f16_ss_acc(tmem, a_desc, b_desc + (8192 >> 4), IDESC);            // lo weights
+      ptx::mma_f16_ss_acc(tmem, a_desc + 2, b_desc + (8192 >> 4) + 2, IDESC);
+      ptx::mma_f16_ss_acc(tmem, a_desc + 4, b_desc + (8192 >> 4) + 4, IDESC);
+      ptx::mma_commit(&s_bar);
+    }
+    ptx::mbar_wait(&s_bar, parity);
+    parity ^= 1;
+    ptx::tc_fence_after();
+    const int y = y0 + hl, x = x0 + wl;
+    const bool valid = (y < H) && (x < W);
+    __half* px = out + ((static_cast<size_t>(n) * H + y) * W + x) * cstride;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      float f[32];
+      tmem_load_group<32>(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, f);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(f[i], acc_scale, s_bias[c0 + i]), 0.f);
+      if (valid) {
+        if (out_mode == 2) {
+          comp_store<32>(f, px + c0, reinterpret_cast<uint8_t*>(px + lo_off), c0, 32);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            __align__(16) __half hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              hi[j] = __float2half_rn(f[g * 8 + j]);
+              lo[j] = __float2half_rn(f[g * 8 + j] - __half2float(hi[j]));
+            }
+            *reinterpret_cast<uint4*>(px + c0 + g * 8) = *reinterpret_cast<const uint4*>(hi);
+            if (out_mode == 1) *reinterpret_cast<uint4*>(px + lo_off + c0 + g * 8) = *reinterpret_cast<const uint4*>(lo);
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) ptx::tmem_dealloc<64>(tmem);
+}
+
 }  // namespace opb

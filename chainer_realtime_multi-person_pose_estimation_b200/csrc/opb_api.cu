@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -36,6 +37,8 @@ static_assert(sizeof(opb_person) == 240, "opb_person size");
 static_assert(sizeof(opb_image_header) == sizeof(ImageHeader), "opb_image_header layout");
 
 namespace {
+
+struct OpbNcclId { char internal[128]; };   // == ncclUniqueId (passed BY VALUE to ncclCommInitRank)
 
 thread_local std::string g_create_error;
 
@@ -154,6 +157,8 @@ struct opb_ctx {
   std::map<std::string, PackedW> packed;
   float* w_first = nullptr;  // conv1_1 [27][64] fp32
   __half* w_first_h = nullptr;  // conv1_1 [64][32] fp16 (tensor-core variant)
+  __half* w_first_x = nullptr;  // conv1_1 [2][64][64] fp16: exact tensor-core variant (hi / lo of W/255 and of the -0.5*sum_c W indicator taps, x 2^S)
+  float first_x_scale = 1.f;    // 2^-S
   float* b_first = nullptr;
   std::vector<void*> weight_allocs;
   std::map<long long, Chain*> chains;
@@ -171,6 +176,7 @@ struct opb_ctx {
     uint8_t* h_result = nullptr; size_t r_bytes = 0;     // pinned [headers | persons] of the slot
     cudaEvent_t h2d_done = nullptr, done = nullptr;
     int n = 0; bool busy = false;
+    const void* post = nullptr;                          // PostWs of the submitted batch (record block of opb_allgather_results)
     // CUDA-graph replay of the slot's pipeline: the launch sequence of one (shape, buffers) combination is captured
     // the second time it is submitted and replayed afterwards
     struct Key {
@@ -430,6 +436,17 @@ int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
     const int grid = std::min(tiles, ctx->num_sms * 8);
     conv_first_tc_kernel<<<grid, 128, 0, ctx->stream>>>(ch->img_u8_src ? ch->img_u8_src : ch->img_u8, ctx->w_first_h,
                                                         ctx->b_first, op.out, op.N, op.H, op.W, op.cstride, ctx->u8_denom);
+    ctx->launches++;
+    OPB_CUDA(ctx, cudaGetLastError());
+    return OPB_OK;
+  }
+  if (op.C == 1 && ctx->precision != OPB_PRECISION_FAST && !(getenv("OPB_NO_TC_FIRST") && atoi(getenv("OPB_NO_TC_FIRST")))) {
+    // uint8 frames in a precision inside the map tolerance: exact tensor-core conv1_1 (raw pixel values + in-image indicators)
+    const int tiles = op.N * ((op.H + 15) / 16) * ((op.W + 7) / 8);
+    const int grid = std::min(tiles, ctx->num_sms * 8);
+    conv_first_tcx_kernel<<<grid, 128, 0, ctx->stream>>>(ch->img_u8_src ? ch->img_u8_src : ch->img_u8, ctx->w_first_x, ctx->b_first,
+                                                         op.out, op.N, op.H, op.W, op.cstride, op.lo_off,
+                                                         ctx->precision == OPB_PRECISION_COMP ? 2 : 1, ctx->first_x_scale);
     ctx->launches++;
     OPB_CUDA(ctx, cudaGetLastError());
     return OPB_OK;
@@ -992,8 +1009,13 @@ int get_post(opb_ctx* ctx, int n, int H, int W, PostWs** out) {
   RC(dev_alloc(ctx, &ws->conns, static_cast<size_t>(n) * 19 * ctx->conn_cap, ws->allocs, false));
   RC(dev_alloc(ctx, &ws->conn_counts, static_cast<size_t>(n) * 19, ws->allocs));
   RC(dev_alloc(ctx, &ws->subsets_out, static_cast<size_t>(n) * p.max_persons * 20, ws->allocs, false));
-  RC(dev_alloc(ctx, &ws->headers, n, ws->allocs));
-  RC(dev_alloc(ctx, &ws->persons, static_cast<size_t>(n) * p.max_persons, ws->allocs));
+  {  // ONE contiguous record block [n headers | n x max_persons persons]: the payload of opb_allgather_results
+    static_assert(sizeof(ImageHeader) % 16 == 0, "persons must stay 16-byte aligned behind the headers");
+    uint8_t* rec = nullptr;
+    RC(dev_alloc(ctx, &rec, static_cast<size_t>(n) * (sizeof(ImageHeader) + sizeof(PersonOut) * p.max_persons), ws->allocs));
+    ws->headers = reinterpret_cast<ImageHeader*>(rec);
+    ws->persons = reinterpret_cast<PersonOut*>(rec + static_cast<size_t>(n) * sizeof(ImageHeader));
+  }
 #undef RC
   ctx->posts[key] = ws;
   ctx->last_post = ws;
@@ -1422,6 +1444,35 @@ int opb_finalize_weights(opb_ctx* ctx, int precision_mode) {
         for (int t = 0; t < 9; ++t) wh[o * 32 + t * 3 + c] = __float2half_rn(L.W[(static_cast<size_t>(o) * 3 + c) * 9 + t]);
     if ((rc = dev_alloc(ctx, &ctx->w_first_h, wh.size(), ctx->weight_allocs, false))) return rc;
     OPB_CUDA(ctx, cudaMemcpyAsync(ctx->w_first_h, wh.data(), wh.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+    {  // exact tensor-core conv1_1 (csrc/conv_first.cuh: conv_first_tcx_kernel): k < 27: W/255, k = 27 + tap: -0.5 * sum_c W
+      std::vector<double> wx(64 * 36);
+      const double denom = ctx->host_layers.count("conv6_2_CPM") ? 256.0 : 255.0;   // face / hand nets: /256 (face_detector.py:32)
+      double mx = 0.0;
+      for (int o = 0; o < 64; ++o)
+        for (int t = 0; t < 9; ++t) {
+          double sum = 0.0;
+          for (int c = 0; c < 3; ++c) {
+            const double w = L.W[(static_cast<size_t>(o) * 3 + c) * 9 + t];
+            wx[o * 36 + t * 3 + c] = w / denom;
+            sum += w;
+          }
+          wx[o * 36 + 27 + t] = -0.5 * sum;
+        }
+      for (double v : wx) mx = std::max(mx, std::fabs(v));
+      int S = 0;
+      if (mx > 0.0 && std::isfinite(mx)) S = std::max(-60, std::min(60, static_cast<int>(std::floor(std::log2(16384.0 / mx)))));
+      std::vector<__half> whx(2 * 64 * 64, __float2half(0.f));
+      for (int o = 0; o < 64; ++o)
+        for (int k = 0; k < 36; ++k) {
+          const double v = std::ldexp(wx[o * 36 + k], S);
+          const __half hi = __float2half_rn(static_cast<float>(v));
+          whx[o * 64 + k] = hi;
+          whx[64 * 64 + o * 64 + k] = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(hi))));
+        }
+      ctx->first_x_scale = std::ldexp(1.f, -S);
+      if ((rc = dev_alloc(ctx, &ctx->w_first_x, whx.size(), ctx->weight_allocs, false))) return rc;
+      OPB_CUDA(ctx, cudaMemcpyAsync(ctx->w_first_x, whx.data(), whx.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+    }
     OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if ((rc = dev_alloc(ctx, &ctx->w_first, wt.size(), ctx->weight_allocs, false))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->b_first, 64, ctx->weight_allocs, false))) return rc;
@@ -2145,7 +2196,97 @@ int opb_stream_submit(opb_ctx* ctx, const uint8_t* frames, int frames_loc, int n
   sl.key_seen++;
   OPB_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream));
   sl.n = n;
+  sl.post = ws;
   sl.busy = true;
+  return OPB_OK;
+}
+
+// ---- the one collective of the path: all-gather of the fixed-size result records --------------------
+// NCCL is resolved at run time from the library the process already carries (torch loads libnccl.so.2; a stand-alone
+// C program links or preloads it): no link-time dependency, and a box without NCCL can still use everything else.
+namespace {
+struct NcclApi {
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, OpbNcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* h = nullptr;
+  const char* names[] = {getenv("OPB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n || !*n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) { api.why = "libnccl.so.2 not found (set OPB_NCCL_LIB)"; return api; }
+  api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<int (*)(void**, int, OpbNcclId, int)>(dlsym(h, "ncclCommInitRank"));
+  api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+  api.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(h, "ncclAllGather"));
+  api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather;
+  if (!api.ok) api.why = "libnccl lacks ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy / ncclAllGather";
+  return api;
+}
+}  // namespace
+
+int opb_nccl_unique_id(uint8_t id_out[128]) {
+  if (!id_out) return OPB_ERR_ARG;
+  NcclApi& a = nccl_api();
+  if (!a.ok) { g_create_error = a.why; return OPB_ERR_UNSUPPORTED; }
+  OpbNcclId id;
+  const int r = a.GetUniqueId(&id);
+  if (r) { g_create_error = std::string("ncclGetUniqueId: ") + (a.GetErrorString ? a.GetErrorString(r) : "error"); return OPB_ERR_CUDA; }
+  std::memcpy(id_out, id.internal, 128);
+  return OPB_OK;
+}
+
+int opb_nccl_comm_init(opb_ctx* ctx, void** comm_out, int world, int rank, const uint8_t id[128]) {
+  if (!ctx || !comm_out || !id || world < 1 || rank < 0 || rank >= world) return OPB_ERR_ARG;
+  NcclApi& a = nccl_api();
+  if (!a.ok) OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, a.why);
+  cudaSetDevice(ctx->device);
+  OpbNcclId uid;
+  std::memcpy(uid.internal, id, 128);
+  void* comm = nullptr;
+  const int r = a.CommInitRank(&comm, world, uid, rank);
+  if (r) OPB_FAIL(ctx, OPB_ERR_CUDA, std::string("ncclCommInitRank: ") + (a.GetErrorString ? a.GetErrorString(r) : "error"));
+  *comm_out = comm;
+  return OPB_OK;
+}
+
+int opb_nccl_comm_destroy(void* comm) {
+  NcclApi& a = nccl_api();
+  if (!a.ok || !comm) return OPB_ERR_ARG;
+  return a.CommDestroy(comm) ? OPB_ERR_CUDA : OPB_OK;
+}
+
+size_t opb_record_block_bytes(const opb_ctx* ctx, int n) {
+  return ctx ? static_cast<size_t>(n) * (sizeof(ImageHeader) + sizeof(PersonOut) * static_cast<size_t>(ctx->prm.max_persons)) : 0;
+}
+
+int opb_allgather_results(opb_ctx* ctx, void* nccl_comm, int slot, void* gathered_dev) {
+  if (!ctx || !nccl_comm || !gathered_dev || slot < 0 || slot > 1) return OPB_ERR_ARG;
+  NcclApi& a = nccl_api();
+  if (!a.ok) OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, a.why);
+  cudaSetDevice(ctx->device);
+  auto& sl = ctx->slots[slot];
+  if (!sl.busy || !sl.post) OPB_FAIL(ctx, OPB_ERR_STATE, "opb_allgather_results: nothing submitted on this slot");
+  cudaStream_t st = (slot == 1 && ctx->two_streams && ctx->stream_b) ? ctx->stream_b : ctx->stream;
+  const PostWs* ws = static_cast<const PostWs*>(sl.post);
+  // device-resident [headers | persons] of the slot's batch -> every rank's block, in rank order; no host hop
+  const int r = a.AllGather(ws->headers, gathered_dev, opb_record_block_bytes(ctx, sl.n), 1 /* ncclUint8 */, nccl_comm, st);
+  if (r) OPB_FAIL(ctx, OPB_ERR_CUDA, std::string("ncclAllGather: ") + (a.GetErrorString ? a.GetErrorString(r) : "error"));
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaEventRecord(sl.done, st));       // opb_stream_collect / opb_stream_join now also cover the collective
   return OPB_OK;
 }
 

@@ -21,6 +21,7 @@
 #ifndef OPB_H_
 #define OPB_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -200,6 +201,22 @@ int opb_stream_collect(opb_ctx* ctx, int slot, opb_image_header* headers_out, op
  * context's stream (opb_set_stream) wait for every submitted, uncollected batch -- for callers that time or
  * order other work on that stream.                                                              */
 int opb_stream_join(opb_ctx* ctx);
+
+/* -- multi-GPU (images shard by rank; the reference has no multi-device path) ------------
+ * The ONE collective of the path: an ncclAllGather of the fixed-size result records of a streaming slot's batch,
+ * [n opb_image_header | n x max_persons opb_person] = opb_record_block_bytes(ctx, n) bytes per rank, straight from
+ * the device-resident record block (no host hop), enqueued on the slot's stream behind its pipeline; gathered_dev
+ * (device, world x that many bytes) then holds every rank's block in rank order.  opb_stream_collect / opb_stream_join
+ * of that slot afterwards also wait for the collective.  NCCL is resolved at run time (dlopen libnccl.so.2, or
+ * $OPB_NCCL_LIB) -- the process that calls this already carries it (torch.distributed, or a program linked to NCCL).
+ * opb_nccl_unique_id / opb_nccl_comm_init / opb_nccl_comm_destroy wrap ncclGetUniqueId / ncclCommInitRank /
+ * ncclCommDestroy for callers without their own NCCL binding (rank 0 creates the 128-byte id and ships it to the
+ * other ranks through whatever channel it has; one communicator per process = per GPU).                        */
+int opb_nccl_unique_id(uint8_t id_out[128]);
+int opb_nccl_comm_init(opb_ctx* ctx, void** nccl_comm_out, int world, int rank, const uint8_t id[128]);
+int opb_nccl_comm_destroy(void* nccl_comm);
+size_t opb_record_block_bytes(const opb_ctx* ctx, int n);
+int opb_allgather_results(opb_ctx* ctx, void* nccl_comm /* ncclComm_t */, int slot, void* gathered_dev);
 
 /* -- face / hand nets.  A context whose loaded layers contain "conv6_2_CPM" is a FaceNet /
  *    HandNet context (models/FaceNet.py:10-76, models/HandNet.py; 52 layers, final 1x1 with 71 / 22 channels):

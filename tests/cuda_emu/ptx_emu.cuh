@@ -284,6 +284,13 @@ EMU_INTERNAL inline void tma_load(void* smem_dst, const CUtensorMap* m, uint64_t
   t.bar = bar; t.dst = smem_dst; t.rec = tmap_rec(m); t.rank = rank; t.cta = g_cur_cta;
   for (int d = 0; d < 5; ++d) t.c[d] = d < rank ? c[d] : 0;
 }
+// multicast: one pending copy per destination CTA (same offsets of destination and barrier in each)
+EMU_INTERNAL inline void tma_load_to(int cta, void* smem_dst, const CUtensorMap* m, uint64_t* bar, const int* c, int rank) {
+  if (g_n_tma_pending == MAX_PENDING_TMA) { fprintf(stderr, "emu: %d TMA loads in flight whose mbarriers nobody polls\n", MAX_PENDING_TMA); abort(); }
+  PendingTma& t = g_tma_pending[g_n_tma_pending++];
+  t.bar = bar; t.dst = smem_dst; t.rec = tmap_rec(m); t.rank = rank; t.cta = cta;
+  for (int d = 0; d < 5; ++d) t.c[d] = d < rank ? c[d] : 0;
+}
 EMU_INTERNAL inline void tma_flush(uint64_t* bar) {   // bar == nullptr: everything
   if (g_n_tma_pending == 0) return;
   unsigned char* const saved_dyn = g_dyn_smem;
@@ -396,6 +403,23 @@ EMU_INTERNAL inline void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
 EMU_INTERNAL inline void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_cols<32>(taddr, r); }
 EMU_INTERNAL inline void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_cols<16>(taddr, r); }
 inline void tmem_ld_wait() {}
+
+// ---------------------------------------------------------------- cluster multicast (cta_group::1 kernels)
+EMU_INTERNAL inline void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  emu::need_cluster();
+  const int c[2] = {c0, c1};
+  const uint32_t off_d = emu::smem_addr_of(smem_dst), off_b = emu::smem_addr_of(bar);
+  for (int k = 0; k < emu::g_ncta; ++k)
+    if ((cta_mask >> k) & 1)
+      emu::tma_load_to(k, emu::smem_ptr(off_d, k), m, reinterpret_cast<uint64_t*>(emu::smem_ptr(off_b, k)), c, 2);
+}
+EMU_INTERNAL inline void mma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  emu::need_cluster();
+  emu::mma_flush();
+  const uint32_t off = emu::smem_addr_of(bar);
+  for (int k = 0; k < emu::g_ncta; ++k)
+    if ((cta_mask >> k) & 1) emu::mbar_arrive_n(reinterpret_cast<uint64_t*>(emu::smem_ptr(off, k)), 1);
+}
 
 // ---------------------------------------------------------------- CTA pairs (cta_group::2): both CTAs resident
 EMU_INTERNAL inline uint32_t cluster_ctarank() { emu::need_cluster(); return static_cast<uint32_t>(emu::g_cur_cta); }
