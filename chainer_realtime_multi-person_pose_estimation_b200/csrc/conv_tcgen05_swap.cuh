@@ -37,8 +37,13 @@ struct ConvSwapCfg {
 // partial sums in round-to-nearest fp32 registers while the next segment's MMAs run.
 constexpr int kSwapDrainThreads = 64 + 256;
 
-template <int KS, int NSP, int NSW, bool DRAIN = false>
-__global__ void __launch_bounds__(DRAIN ? kSwapDrainThreads : kConvThreads, 1)
+// CL = 2: thread-block clusters of two CTAs that work on two pixel tiles of the same (problem, channel block) in
+// lockstep and SHARE every weight tile: each CTA fetches half of it (64 of the 128 output-channel rows) with a
+// multicast TMA load that lands in both CTAs' shared memory, so the L2 -> SM weight traffic (72 % of this kernel's
+// operand bytes, at ~75 % of the measured L2 throughput cap) halves.  A weight stage is recycled when BOTH CTAs'
+// MMAs have read it (multicast tcgen05.commit onto both w_empty barriers, count 2).
+template <int KS, int NSP, int NSW, bool DRAIN = false, int CL = 1>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DRAIN ? kSwapDrainThreads : kConvThreads, 1)
 conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __grid_constant__ CUtensorMap tmP8_0,
                          const __grid_constant__ CUtensorMap tmW_0, const __grid_constant__ CUtensorMap tmP16_1,
                          const __grid_constant__ CUtensorMap tmP8_1, const __grid_constant__ CUtensorMap tmW_1,
@@ -73,13 +78,14 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
       ptx::prefetch_tensormap(&tmW_1);
     }
     for (int i = 0; i < NSP; ++i) { ptx::mbar_init(&p_full[i], 1); ptx::mbar_init(&p_empty[i], 1); }
-    for (int i = 0; i < NSW; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < NSW; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], CL); }
     for (int i = 0; i < ACC_STAGES; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], DRAIN ? 256 : 128); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync_all();   // the peer's barriers are initialised before anything lands on them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -87,19 +93,42 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
   const int m_tiles = P.N * P.tiles_y * P.tiles_x;
   const int tiles_per_problem = P.n_blocks * m_tiles;
   const int total_tiles = P.n_problems * tiles_per_problem;
+  // Tile order inside one (problem, channel block): all full-width tiles first, then the narrow edge tiles, so that the
+  // two CTAs of a cluster (consecutive tile numbers) do the same amount of work per weight tile.
+  const int tx_full = P.tiles_x - (P.pad_edge8 ? 1 : 0);
+  const int n_full = P.N * P.tiles_y * tx_full;
+  uint32_t crank = 0;
+  if constexpr (CL > 1) crank = ptx::cluster_ctarank();
+  const int tile_first = (static_cast<int>(blockIdx.x) / CL) * CL + static_cast<int>(crank);
+  const int tile_step = static_cast<int>(gridDim.x);     // a multiple of CL; total_tiles % CL == 0 (host)
+  struct TileId { int p, nb, n, ty, tx; };
+  auto decode = [&](int tile) {
+    TileId t;
+    t.p = tile / tiles_per_problem;
+    int rem = tile - t.p * tiles_per_problem;
+    t.nb = rem / m_tiles;
+    rem -= t.nb * m_tiles;
+    if (rem < n_full) {
+      t.n = rem / (P.tiles_y * tx_full);
+      rem -= t.n * (P.tiles_y * tx_full);
+      t.ty = rem / tx_full;
+      t.tx = rem - t.ty * tx_full;
+    } else {
+      rem -= n_full;
+      t.n = rem / P.tiles_y;
+      t.ty = rem - t.n * P.tiles_y;
+      t.tx = P.tiles_x - 1;
+    }
+    return t;
+  };
 
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0) {
       uint32_t sp = 0, pp = 0, sw = 0, pw = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int p = tile / tiles_per_problem;
-        int rem = tile - p * tiles_per_problem;
-        const int nb = rem / m_tiles;
-        rem -= nb * m_tiles;
-        const int n = rem / (P.tiles_y * P.tiles_x);
-        rem -= n * (P.tiles_y * P.tiles_x);
-        const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        const TileId tid_ = decode(tile);
+        const int p = tid_.p, nb = tid_.nb, n = tid_.n, ty = tid_.ty, tx = tid_.tx;
         const int y0 = ty * 16, x0 = tx * 16;
         const bool narrow = P.pad_edge8 && (tx == P.tiles_x - 1);
         const CUtensorMap* tmP = narrow ? (p ? &tmP8_1 : &tmP8_0) : (p ? &tmP16_1 : &tmP16_0);
@@ -115,8 +144,12 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
             for (int r = 0; r < KS; ++r) {
               ptx::mbar_wait(&w_empty[sw], pw ^ 1);
               ptx::mbar_expect_tx(&w_full[sw], Cfg::W_STAGE_BYTES);
-              ptx::tma_load_2d(smemW + sw * Cfg::W_STAGE_BYTES, tmW, &w_full[sw], (r * KS + s) * P.b_tap_stride + bk,
-                               nb * 128);
+              if constexpr (CL > 1)   // this CTA's 64 rows of the tile, delivered to both CTAs (tmW box = {64, 64})
+                ptx::tma_load_2d_mc(smemW + sw * Cfg::W_STAGE_BYTES + crank * (Cfg::W_STAGE_BYTES / 2), tmW, &w_full[sw],
+                                    (r * KS + s) * P.b_tap_stride + bk, nb * 128 + static_cast<int>(crank) * 64, 3);
+              else
+                ptx::tma_load_2d(smemW + sw * Cfg::W_STAGE_BYTES, tmW, &w_full[sw], (r * KS + s) * P.b_tap_stride + bk,
+                                 nb * 128);
               if (++sw == NSW) { sw = 0; pw ^= 1; }
             }
           }
@@ -129,9 +162,9 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
       uint32_t sp = 0, pp = 0, sw = 0, pw = 0, acc = 0, pacc = 0;
       const uint64_t p_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemP), 1024);
       const uint64_t w_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemW), 1024);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int rem_t = (tile % m_tiles) % (P.tiles_y * P.tiles_x);
-        const int ty = rem_t / P.tiles_x, tx = rem_t - ty * P.tiles_x;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        const TileId tid_ = decode(tile);
+        const int ty = tid_.ty, tx = tid_.tx;
         const bool narrow = P.pad_edge8 && (tx == P.tiles_x - 1);
         // the last tile row of an image only needs its valid rows (rounded to even): N = rows x 16 (or x 8)
         const int rows = min(16, (P.H - ty * 16 + 1) & ~1);
@@ -173,7 +206,8 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
                 for (int k = 1; k < 4; ++k) ptx::mma_f16_ss_acc(d, w_st + (k * 32 >> 4), pd0 + (k * 32 >> 4), idesc);
               }
               accumulate = 1;
-              ptx::mma_commit(&w_empty[sw]);
+              if constexpr (CL > 1) ptx::mma_commit_mc(&w_empty[sw], 3);
+              else ptx::mma_commit(&w_empty[sw]);
               if (++sw == NSW) { sw = 0; pw ^= 1; }
             }
             ptx::mma_commit(&p_empty[sp]);
@@ -195,14 +229,9 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
     // ================================================================ epilogue: thread = output channel
     const int q = warp & 3;
     uint32_t acc = 0, pacc = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int p = tile / tiles_per_problem;
-      int rem = tile - p * tiles_per_problem;
-      const int nb = rem / m_tiles;
-      rem -= nb * m_tiles;
-      const int n = rem / (P.tiles_y * P.tiles_x);
-      rem -= n * (P.tiles_y * P.tiles_x);
-      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      const TileId tid_ = decode(tile);
+      const int p = tid_.p, nb = tid_.nb, n = tid_.n, ty = tid_.ty, tx = tid_.tx;
       const int y0 = ty * 16, x0 = tx * 16;
       const bool narrow = P.pad_edge8 && (tx == P.tiles_x - 1);
       const int wshift = narrow ? 3 : 4;                 // pixels per tile row = 8 or 16
@@ -295,7 +324,8 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync_all();   // nothing may still land in a CTA that has exited
+  else __syncthreads();
   if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
 }
 

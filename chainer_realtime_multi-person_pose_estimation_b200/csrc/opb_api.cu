@@ -74,6 +74,7 @@ struct Op {
   bool drain = false;
   bool pair = false;   // cta_group::2 kernel (cluster of 2 CTAs)
   bool swap = false;   // weights-as-A kernel (16x16 pixel tiles as the N=256 operand)
+  int cluster = 1;     // swap kernel: CTAs per cluster sharing every weight tile through multicast TMA (1 or 2)
   CUtensorMap tmP16[2];
   CUtensorMap tmA[2], tmB[2];
   ConvParams P;
@@ -332,10 +333,10 @@ int launch_conv_pair_t(opb_ctx* ctx, const Op& op) {
   return OPB_OK;
 }
 
-template <int KS, int NSP, int NSW, bool DRAIN = false>
+template <int KS, int NSP, int NSW, bool DRAIN = false, int CL = 1>
 int launch_conv_swap_t(opb_ctx* ctx, const Op& op) {
   using Cfg = ConvSwapCfg<KS, NSP, NSW>;
-  auto kern = conv_tcgen05_swap_kernel<KS, NSP, NSW, DRAIN>;
+  auto kern = conv_tcgen05_swap_kernel<KS, NSP, NSW, DRAIN, CL>;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     OPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -351,6 +352,8 @@ int launch_conv_swap_t(opb_ctx* ctx, const Op& op) {
 int launch_conv(opb_ctx* ctx, const Op& op) {
   const int key = op.ks * 10000 + op.bn * 10 + op.mt;
   if (op.swap) {
+    if (op.ks == 7 && op.cluster == 2)
+      return op.drain ? launch_conv_swap_t<7, 3, 5, true, 2>(ctx, op) : launch_conv_swap_t<7, 3, 5, false, 2>(ctx, op);
     if (op.ks == 7) return op.drain ? launch_conv_swap_t<7, 3, 5, true>(ctx, op) : launch_conv_swap_t<7, 3, 5>(ctx, op);
     if (op.ks == 3) return op.drain ? launch_conv_swap_t<3, 3, 6, true>(ctx, op) : launch_conv_swap_t<3, 3, 6>(ctx, op);
     OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "no swap-mode conv variant");
@@ -647,6 +650,14 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
   P.n_blocks = per_problem_cout_pad / op.bn;
   P.n_problems = s.n_problems;
   P.b_tap_stride = w0.k_per_tap;
+  if (op.swap && op.ks == 7) {
+    // clusters of two CTAs sharing every weight tile (multicast TMA): both CTAs of a cluster must be on the same
+    // (problem, channel block), i.e. an even number of pixel tiles per block.  OPB_SWAP_CLUSTER=0 disables.
+    const char* e = getenv("OPB_SWAP_CLUSTER");
+    const int want = e ? atoi(e) : 2;
+    const int m_tiles = P.N * P.tiles_y * P.tiles_x;
+    if (want == 2 && m_tiles % 2 == 0 && m_tiles * P.n_blocks * P.n_problems >= 2 && ctx->num_sms >= 2) op.cluster = 2;
+  }
   const int chunks = w0.cin_pad / 64;
   int np = 0;
   for (int i = 0; i < chunks; ++i) {
@@ -661,9 +672,10 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
   }
   P.comp = comp ? 1 : 0;
   {  // two-level accumulation granularity of the swap / pair DRAIN kernels: steps (chunk pair x filter column) per TMEM
-     // buffer.  Default: one chunk pair (KS steps = KS*KS*4 chained MMAs, 196 for 7x7); OPB_DRAIN_SEG overrides.
+     // buffer.  Default 4 (112 chained MMAs for 7x7): measured the best speed / accuracy trade (profiles/r02_precision_ladder.txt);
+     // OPB_DRAIN_SEG overrides.
     const char* e = getenv("OPB_DRAIN_SEG");
-    P.drain_seg = std::max(1, e ? atoi(e) : op.ks);
+    P.drain_seg = std::max(1, e ? atoi(e) : 4);
   }
   if (np > kMaxPairs) OPB_FAIL(ctx, OPB_ERR_UNSUPPORTED, "too many K chunk pairs");
   P.n_pairs = np;
@@ -678,7 +690,7 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
       rc = make_act_map(ctx, &op.tmP16[p], *s.in[p], s.in_coff[p], op.ks, 16);
       if (rc) return rc;
     }
-    rc = make_w_map(ctx, &op.tmB[p], w, op.pair ? op.bn / 2 : op.bn);
+    rc = make_w_map(ctx, &op.tmB[p], w, (op.pair || op.cluster == 2) ? op.bn / 2 : op.bn);
     if (rc) return rc;
     ConvProblem& pr = P.prob[p];
     pr.out = s.out[p] ? s.out[p]->p : nullptr;
@@ -695,6 +707,7 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
   if (s.n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; op.tmP16[1] = op.tmP16[0]; P.prob[1] = P.prob[0]; }
   const int total_tiles = P.n_problems * P.n_blocks * P.N * P.tiles_y * P.tiles_x;
   op.grid = op.pair ? 2 * std::min(total_tiles, ctx->num_sms / 2) : std::min(total_tiles, ctx->num_sms);
+  if (op.cluster == 2) op.grid = 2 * std::min(total_tiles / 2, ctx->num_sms / 2);
   ch->ops.push_back(op);
   return OPB_OK;
 }
