@@ -651,10 +651,13 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
   P.n_problems = s.n_problems;
   P.b_tap_stride = w0.k_per_tap;
   if (op.swap && op.ks == 7) {
-    // clusters of two CTAs sharing every weight tile (multicast TMA): both CTAs of a cluster must be on the same
-    // (problem, channel block), i.e. an even number of pixel tiles per block.  OPB_SWAP_CLUSTER=0 disables.
+    // OPB_SWAP_CLUSTER=2: clusters of two CTAs sharing every weight tile (multicast TMA); both CTAs of a cluster must be
+    // on the same (problem, channel block), i.e. an even number of pixel tiles per block.  OFF by default: measured on a
+    // B200 (profiles/r02_swap_cluster_ab.txt) it is 5 % slower in fp16 and within noise in compensated precision -- the
+    // L2 already serves the 148 CTAs' identical weight requests at ~75 % of its throughput cap, and the lockstep costs more
+    // than the halved request count saves.  Kept as a measured variant (bit-identical results; emulation-tested).
     const char* e = getenv("OPB_SWAP_CLUSTER");
-    const int want = e ? atoi(e) : 2;
+    const int want = e ? atoi(e) : 0;
     const int m_tiles = P.N * P.tiles_y * P.tiles_x;
     if (want == 2 && m_tiles % 2 == 0 && m_tiles * P.n_blocks * P.n_problems >= 2 && ctx->num_sms >= 2) op.cluster = 2;
   }

@@ -103,9 +103,13 @@ def test_forward_maps_parity_mode(det_any):
     print("%s-precision max abs err: paf %.3e heat %.3e" % (det_any._test_precision, e1, e2))
     assert e1 <= MAP_TOL and e2 <= MAP_TOL
     assert max(e1, e2) <= (1e-4 if det_any._test_precision == "parity" else 5e-4)   # measured: ~2e-5 / ~1.5e-4
-    # uint8 entry (preprocess fused into conv1_1) gives the same maps
+    # uint8 entry (preprocess fused into the exact tensor-core conv1_1) vs the float32 entry (fp32 CUDA-core conv1_1): the
+    # two first layers agree to ~1e-7; compensated precision amplifies that through its 8-bit correction bytes
     paf_u8, heat_u8 = det_parity.engine.forward(cv2.resize(img, (368, 368))[None])
-    assert np.abs(paf_u8 - paf).max() <= 1e-5 and np.abs(heat_u8 - heat).max() <= 1e-5
+    tol_entry = 1e-5 if det_any._test_precision == "parity" else 2e-4
+    assert np.abs(paf_u8 - paf).max() <= tol_entry and np.abs(heat_u8 - heat).max() <= tol_entry
+    e3 = max(np.abs(paf_u8[0] - g["paf_lo_0"]).max(), np.abs(heat_u8[0] - g["heat_lo_0"]).max())
+    assert e3 <= (1e-4 if det_any._test_precision == "parity" else 5e-4)
 
 
 def test_fast_mode_uint8_entry_matches_float_entry(weights_model):
