@@ -126,7 +126,7 @@ class OpbError(RuntimeError):
 class Engine(object):
     """One device context (opb_ctx) + the weights of one CocoPoseNet."""
 
-    def __init__(self, device, params, precision=PRECISION_PARITY):
+    def __init__(self, device, params, precision=PRECISION_COMP):
         self.lib = load_library()
         self.ctx = C.c_void_p()
         self.params = params

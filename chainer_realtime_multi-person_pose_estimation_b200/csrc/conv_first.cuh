@@ -158,11 +158,15 @@ conv_first_kernel(const uint8_t* __restrict__ x_u8, const float* __restrict__ x_
 namespace opb {
 
 // wth: [64][32] fp16 (row = output channel, k = (r*3+s)*3 + c, k >= 27 zero); bias [64] fp32
+// Output: the 128 pixels x 128 B of a tile are staged in shared memory in the SWIZZLE_128B box layout (row = pixel
+// hl * 8 + wl) and leave through ONE TMA store per plane (box {64 ch, 8 px, 16 rows}; clipped at the image edge by the
+// tensor map) -- full 128-byte lines instead of 32 scattered 16-byte stores per warp instruction.
 __global__ void __launch_bounds__(128)
 conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict__ wth, const float* __restrict__ bias,
-                     __half* __restrict__ out, int N, int H, int W, int cstride, float u8_denom) {
+                     const __grid_constant__ CUtensorMap tmOut, int N, int H, int W, float u8_denom) {
   __shared__ __align__(1024) uint8_t sA[128 * 128];
   __shared__ __align__(1024) uint8_t sB[64 * 128];
+  __shared__ __align__(1024) uint8_t sOut[128 * 128];
   __shared__ __half s_lut[260];
   __shared__ __align__(4) __half s_val[18 * 10 * 3 + 4];   // normalised halo tile, [row][col][c]
   __shared__ float s_bias[64];
@@ -257,10 +261,9 @@ conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict_
     ptx::mbar_wait(&s_bar, parity);
     parity ^= 1;
     ptx::tc_fence_after();
-    // (4) epilogue: bias + ReLU + fp16, 128 contiguous bytes per pixel
-    const int y = y0 + hl, x = x0 + wl;
-    const bool valid = (y < H) && (x < W);
-    __half* o = out + ((static_cast<size_t>(n) * H + y) * W + x) * cstride;
+    // (4) epilogue: bias + ReLU + fp16 -> swizzled staging tile -> one TMA store
+    if (tid == 0) ptx::tma_store_wait_read();      // the previous tile's store has finished reading sOut
+    __syncthreads();
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
       float f[32];
@@ -272,15 +275,20 @@ conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict_
                                             fmaxf(f[2 * i + 1] + s_bias[c0 + 2 * i + 1], 0.f));
         h[i] = *reinterpret_cast<const uint32_t*>(&t);
       }
-      if (valid) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          *reinterpret_cast<uint4*>(o + c0 + g * 8) = make_uint4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
-      }
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(sOut + tid * 128 + (((c0 >> 3) + g) ^ (tid & 7)) * 16) =
+            make_uint4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
     }
+    ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
-    __syncthreads();                   // s_val / sA / TMEM are free for the next tile
+    __syncthreads();                   // s_val / sA / TMEM are free for the next tile; sOut is complete
+    if (tid == 0) {
+      ptx::tma_store_4d(&tmOut, sOut, 0, x0, y0, n);
+      ptx::tma_store_commit();
+    }
   }
+  if (tid == 0) ptx::tma_store_wait_all();
   if (warp == 0) ptx::tmem_dealloc<64>(tmem);
 }
 
@@ -296,11 +304,14 @@ conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict_
 // 16 x 8 tile instead of 1728 fp32 FMAs per pixel.
 // wth: [2][64][64] fp16 = {hi, lo} x (row = output channel, k as above, k >= 36 zero); out_mode 0: fp16 only,
 // 1: parity (hi | lo planes), 2: compensated (hi | correction bytes).
+constexpr int kFirstTcxSmem = 1024 + 128 * 128 + 2 * 64 * 128 + 2 * 128 * 128;
 __global__ void __launch_bounds__(128)
 conv_first_tcx_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict__ wth, const float* __restrict__ bias,
-                      __half* __restrict__ out, int N, int H, int W, int cstride, int lo_off, int out_mode, float acc_scale) {
-  __shared__ __align__(1024) uint8_t sA[128 * 128];
-  __shared__ __align__(1024) uint8_t sB[2 * 64 * 128];
+                      const __grid_constant__ CUtensorMap tmOut, int N, int H, int W, int out_mode, float acc_scale) {
+  extern __shared__ uint8_t smem_raw[];   // kFirstTcxSmem bytes: sA 16 KB | sB 16 KB | sOut 32 KB, 1024-byte aligned
+  uint8_t* sA = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = sA + 128 * 128;
+  uint8_t* sOut = sB + 2 * 64 * 128;      // [hi plane | lo / correction plane], SWIZZLE_128B box layout
   __shared__ __align__(4) __half s_val[18 * 10 * 3 + 4];   // raw pixel values of the halo tile as fp16, [row][col][c]
   __shared__ float s_bias[64];
   __shared__ __align__(8) uint64_t s_bar;
@@ -401,36 +412,62 @@ conv_first_tcx_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict
     ptx::mbar_wait(&s_bar, parity);
     parity ^= 1;
     ptx::tc_fence_after();
-    const int y = y0 + hl, x = x0 + wl;
-    const bool valid = (y < H) && (x < W);
-    __half* px = out + ((static_cast<size_t>(n) * H + y) * W + x) * cstride;
+    if (tid == 0) ptx::tma_store_wait_read();      // the previous tile's stores have finished reading sOut
+    __syncthreads();
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
       float f[32];
       tmem_load_group<32>(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, f);
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(f[i], acc_scale, s_bias[c0 + i]), 0.f);
-      if (valid) {
-        if (out_mode == 2) {
-          comp_store<32>(f, px + c0, reinterpret_cast<uint8_t*>(px + lo_off), c0, 32);
-        } else {
+      uint32_t h[16], l[16];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            __align__(16) __half hi[8], lo[8];
+      for (int i = 0; i < 16; ++i) {
+        const __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        h[i] = *reinterpret_cast<const uint32_t*>(&t);
+        const float2 back = __half22float2(t);
+        const __half2 tl = __floats2half2_rn(f[2 * i] - back.x, f[2 * i + 1] - back.y);
+        l[i] = *reinterpret_cast<const uint32_t*>(&tl);
+      }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              hi[j] = __float2half_rn(f[g * 8 + j]);
-              lo[j] = __float2half_rn(f[g * 8 + j] - __half2float(hi[j]));
-            }
-            *reinterpret_cast<uint4*>(px + c0 + g * 8) = *reinterpret_cast<const uint4*>(hi);
-            if (out_mode == 1) *reinterpret_cast<uint4*>(px + lo_off + c0 + g * 8) = *reinterpret_cast<const uint4*>(lo);
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(sOut + tid * 128 + (((c0 >> 3) + g) ^ (tid & 7)) * 16) =
+            make_uint4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
+      uint8_t* row2 = sOut + 128 * 128 + tid * 128;
+      if (out_mode == 1) {            // parity: the lo plane
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(row2 + (((c0 >> 3) + g) ^ (tid & 7)) * 16) = make_uint4(l[4 * g], l[4 * g + 1], l[4 * g + 2], l[4 * g + 3]);
+      } else if (out_mode == 2) {     // compensated: [fp8(lo * 2^11) 64 B | fp8(v) 64 B]
+        uint32_t xl[8], x8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float lo4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float v = f[4 * i + k];
+            lo4[k] = (v - __half2float(__float2half_rn(v))) * kCompLoScale;
           }
+          xl[i] = f32x4_to_act8x4(lo4[0], lo4[1], lo4[2], lo4[3]);
+          x8[i] = f32x4_to_act8x4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          *reinterpret_cast<uint4*>(row2 + (((c0 >> 4) + g) ^ (tid & 7)) * 16) = make_uint4(xl[4 * g], xl[4 * g + 1], xl[4 * g + 2], xl[4 * g + 3]);
+          *reinterpret_cast<uint4*>(row2 + ((4 + (c0 >> 4) + g) ^ (tid & 7)) * 16) = make_uint4(x8[4 * g], x8[4 * g + 1], x8[4 * g + 2], x8[4 * g + 3]);
         }
       }
     }
+    ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
     __syncthreads();
+    if (tid == 0) {
+      ptx::tma_store_4d(&tmOut, sOut, 0, x0, y0, n);
+      if (out_mode != 0) ptx::tma_store_4d(&tmOut, sOut + 128 * 128, 64, x0, y0, n);   // second plane: channels 64..127 (halves)
+      ptx::tma_store_commit();
+    }
   }
+  if (tid == 0) ptx::tma_store_wait_all();
   if (warp == 0) ptx::tmem_dealloc<64>(tmem);
 }
 

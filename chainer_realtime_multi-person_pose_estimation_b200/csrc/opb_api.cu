@@ -438,7 +438,7 @@ int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
     const int tiles = op.N * ((op.H + 15) / 16) * ((op.W + 7) / 8);
     const int grid = std::min(tiles, ctx->num_sms * 8);
     conv_first_tc_kernel<<<grid, 128, 0, ctx->stream>>>(ch->img_u8_src ? ch->img_u8_src : ch->img_u8, ctx->w_first_h,
-                                                        ctx->b_first, op.out, op.N, op.H, op.W, op.cstride, ctx->u8_denom);
+                                                        ctx->b_first, op.tmA[0], op.N, op.H, op.W, ctx->u8_denom);
     ctx->launches++;
     OPB_CUDA(ctx, cudaGetLastError());
     return OPB_OK;
@@ -446,9 +446,14 @@ int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
   if (op.C == 1 && ctx->precision != OPB_PRECISION_FAST && !(getenv("OPB_NO_TC_FIRST") && atoi(getenv("OPB_NO_TC_FIRST")))) {
     // uint8 frames in a precision inside the map tolerance: exact tensor-core conv1_1 (raw pixel values + in-image indicators)
     const int tiles = op.N * ((op.H + 15) / 16) * ((op.W + 7) / 8);
-    const int grid = std::min(tiles, ctx->num_sms * 8);
-    conv_first_tcx_kernel<<<grid, 128, 0, ctx->stream>>>(ch->img_u8_src ? ch->img_u8_src : ch->img_u8, ctx->w_first_x, ctx->b_first,
-                                                         op.out, op.N, op.H, op.W, op.cstride, op.lo_off,
+    const int grid = std::min(tiles, ctx->num_sms * 3);   // 3 CTAs of 66 KB per SM
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+      OPB_CUDA(ctx, cudaFuncSetAttribute(conv_first_tcx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFirstTcxSmem));
+      attr_set[ctx->device & 63] = true;
+    }
+    conv_first_tcx_kernel<<<grid, 128, kFirstTcxSmem, ctx->stream>>>(ch->img_u8_src ? ch->img_u8_src : ch->img_u8, ctx->w_first_x, ctx->b_first,
+                                                         op.tmA[0], op.N, op.H, op.W,
                                                          ctx->precision == OPB_PRECISION_COMP ? 2 : 1, ctx->first_x_scale);
     ctx->launches++;
     OPB_CUDA(ctx, cudaGetLastError());
@@ -578,6 +583,8 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     const char* e = getenv("OPB_MT");
     const int want = e ? atoi(e) : 2;   // measured: 7x7 128->128 grouped launch 10.1 -> 7.9 ms with MT=2
     if (want == 2 && !split && (op.bn == 128 || op.bn == 64) && (op.ks == 7 || op.ks == 3)) op.mt = 2;
+    // (conv1_2 in compensated precision with its 144 KB of main + correction weights resident in shared memory and one
+    //  sub-tile per CTA was measured SLOWER than this shape, 2.45 vs 2.07 ms per batch of 32, and removed.)
   }
   const Act& a0 = *s.in[0];
   if (a0.H < 16 + op.ks - 1 || a0.W < 8)
@@ -805,9 +812,12 @@ int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
   RC(alloc_act(ctx, ch, &SB, N, h8, w8, 256));
   RC(alloc_act(ctx, ch, &S512, N, h8, w8, 1024));
 
+  int first_rc = OPB_OK;
   auto first = [&]() {
     Op op; op.kind = OP_FIRST; op.tag = "conv1_1"; op.out = B0.p; op.N = N; op.H = H; op.W = W; op.C = 1;
-    op.cstride = B0.Ctot; op.lo_off = split ? B0.C : 0; ch->ops.push_back(op);
+    op.cstride = B0.Ctot; op.lo_off = split ? B0.C : 0;
+    first_rc = make_act_map(ctx, &op.tmA[0], B0, 0, 1);   // output tensor map of the tensor-core conv1_1 kernels (TMA store)
+    ch->ops.push_back(op);
   };
   auto pool = [&](const char* tag, const Act& in, const Act& out) {
     Op op; op.kind = OP_POOL; op.tag = tag; op.in = in.p; op.out = out.p; op.N = N; op.H = in.H; op.W = in.W;
@@ -836,6 +846,7 @@ int build_chain(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
   };
 
   first();
+  if (first_rc) return first_rc;
   // F.max_pooling_2d(2,2) (models/CocoPoseNet.py:138,141,146) is fused into the producing conv's epilogue
   if (fuse) { RC(conv1("conv1_2", B0, P1, 0, 64, 1)); } else { RC(conv1("conv1_2", B0, B1, 0, 64)); pool("pool1", B1, P1); }
   RC(conv1("conv2_1", P1, B2, 0, 128));
@@ -910,7 +921,9 @@ int build_chain_keypoint(opb_ctx* ctx, Chain* ch, int N, int H, int W) {
   RC(alloc_act(ctx, ch, &S512, N, h8, w8, 512));
   {
     Op op; op.kind = OP_FIRST; op.tag = "conv1_1"; op.out = B0.p; op.N = N; op.H = H; op.W = W; op.C = 1;
-    op.cstride = B0.Ctot; op.lo_off = split ? B0.C : 0; ch->ops.push_back(op);
+    op.cstride = B0.Ctot; op.lo_off = split ? B0.C : 0;
+    RC(make_act_map(ctx, &op.tmA[0], B0, 0, 1));
+    ch->ops.push_back(op);
   }
   auto conv = [&](const std::string& layer, const Act& in, const Act& out, int out_coff, int cout, int relu = 1,
                   int fuse_pool = 0, float* o32 = nullptr) -> int {

@@ -84,7 +84,7 @@ class PoseDetector(object):
             if weights_file:
                 self.model.load_npz(weights_file)
         self.device = device
-        precision = precision if precision is not None else os.environ.get("OPB_PRECISION", "parity")
+        precision = precision if precision is not None else os.environ.get("OPB_PRECISION", "comp")
         self.engine = _native.Engine(max(int(device), 0), make_opb_params(params, max_peaks, max_candidates,
                                                                            max_persons), _PRECISIONS[precision])
         self.engine.load_model(self.model)

@@ -284,6 +284,40 @@ EMU_INTERNAL inline void tma_load(void* smem_dst, const CUtensorMap* m, uint64_t
   t.bar = bar; t.dst = smem_dst; t.rec = tmap_rec(m); t.rank = rank; t.cta = g_cur_cta;
   for (int d = 0; d < 5; ++d) t.c[d] = d < rank ? c[d] : 0;
 }
+// TMA store (executed at once: the kernels make their shared-memory writes visible and synchronise before issuing it):
+// de-swizzle the box and write the in-bounds part to global memory
+EMU_INTERNAL inline void tma_store(const CUtensorMap* m, const void* smem_src, const int* c, int rank) {
+  const TensorMapRec* r = tmap_rec(m);
+  if (static_cast<int>(r->rank) != rank || r->swizzle != 3 || r->box[0] * r->elem_bytes != 128) {
+    fprintf(stderr, "emu: unsupported TMA store (rank %u, swizzle %u, inner %u B)\n", r->rank, r->swizzle, r->box[0] * r->elem_bytes); abort();
+  }
+  const uint32_t src = smem_addr_of(smem_src);
+  uint32_t rows = 1;
+  for (int d = 1; d < rank; ++d) rows *= r->box[d];
+  const uint32_t eb = r->elem_bytes;
+  for (uint32_t row = 0; row < rows; ++row) {
+    uint32_t rem = row;
+    long long off = 0;
+    bool oob_row = false;
+    for (int d = 1; d < rank; ++d) {
+      const uint32_t bi = rem % r->box[d];
+      rem /= r->box[d];
+      const long long g = static_cast<long long>(c[d]) + static_cast<long long>(bi) * r->estr[d];
+      if (g < 0 || g >= static_cast<long long>(r->dims[d])) oob_row = true;
+      off += g * static_cast<long long>(r->strides[d]);
+    }
+    if (oob_row) continue;
+    for (uint32_t e = 0; e < r->box[0]; ++e) {
+      const long long g0 = static_cast<long long>(c[0]) + static_cast<long long>(e) * r->estr[0];
+      if (g0 < 0 || g0 >= static_cast<long long>(r->dims[0])) continue;
+      const unsigned char* s8 = smem_ptr(swz128(src + row * 128 + e * eb));
+      EMU_RACE_READ(s8, eb);
+      memcpy(static_cast<unsigned char*>(const_cast<void*>(r->base)) + off + g0 * static_cast<long long>(eb), s8, eb);
+    }
+  }
+  ++g_tma_count;
+}
+
 // multicast: one pending copy per destination CTA (same offsets of destination and barrier in each)
 EMU_INTERNAL inline void tma_load_to(int cta, void* smem_dst, const CUtensorMap* m, uint64_t* bar, const int* c, int rank) {
   if (g_n_tma_pending == MAX_PENDING_TMA) { fprintf(stderr, "emu: %d TMA loads in flight whose mbarriers nobody polls\n", MAX_PENDING_TMA); abort(); }
@@ -351,6 +385,13 @@ EMU_INTERNAL inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint6
   const int c[2] = {c0, c1};
   emu::tma_load(smem_dst, m, bar, c, 2);
 }
+EMU_INTERNAL inline void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  const int c[4] = {c0, c1, c2, c3};
+  emu::tma_store(m, smem_src, c, 4);
+}
+inline void tma_store_commit() {}
+inline void tma_store_wait_read() {}
+inline void tma_store_wait_all() {}
 EMU_INTERNAL inline void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
   const int c[4] = {c0, c1, c2, c3};
   emu::tma_load(smem_dst, m, bar, c, 4);
