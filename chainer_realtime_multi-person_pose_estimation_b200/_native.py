@@ -60,6 +60,10 @@ _SIGNATURES = {
                                         C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "opb_resize_linear_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                        C.c_int, C.c_int]),
+    "opb_resize_cubic_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                      C.c_int, C.c_int]),
+    "opb_precise_add_scale_orig": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_int, C.c_int]),
     "opb_detect_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "opb_stream_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -308,6 +312,18 @@ class Engine(object):
         self._check(self.lib.opb_resize_linear_u8(self.ctx, _ptr(a), OPB_HOST, n, h0, w0, _ptr(out), OPB_HOST, out_h, out_w))
         return out[0] if single else out
 
+    def resize_cubic_u8(self, imgs, out_h, out_w):
+        """cv2.resize(img, (out_w, out_h), interpolation=cv2.INTER_CUBIC) (uint8, OpenCV's own non-IPP path) on the
+        device; imgs [N,H,W,3] or [H,W,3]."""
+        a = np.ascontiguousarray(imgs, np.uint8)
+        single = a.ndim == 3
+        if single:
+            a = a[None]
+        n, h0, w0, _ = a.shape
+        out = np.empty((n, out_h, out_w, 3), np.uint8)
+        self._check(self.lib.opb_resize_cubic_u8(self.ctx, _ptr(a), OPB_HOST, n, h0, w0, _ptr(out), OPB_HOST, out_h, out_w))
+        return out[0] if single else out
+
     def detect_image(self, img, in_h, in_w, map_h, map_w, img_len=None):
         """One BGR frame of any size: upload, device resize, full pipeline (opb_detect_image)."""
         img = np.ascontiguousarray(img, np.uint8)
@@ -447,6 +463,14 @@ class Engine(object):
         pv = (C.c_uint8 * 3)(*[int(v) for v in pad_value])
         self._check(self.lib.opb_precise_add_scale_unpadded(self.ctx, _ptr(img), OPB_HOST, h, w, int(stride), pv,
                                                             scale_index, n_scales))
+
+    def precise_add_scale_orig(self, orig_img, h, w, stride, pad_value, scale_index, n_scales):
+        """Original uint8 frame; the cubic resize to (h, w) of pose_detector.py:443 and pad_image run on the device."""
+        img = np.ascontiguousarray(orig_img, np.uint8)
+        oh, ow, _ = img.shape
+        pv = (C.c_uint8 * 3)(*[int(v) for v in pad_value])
+        self._check(self.lib.opb_precise_add_scale_orig(self.ctx, _ptr(img), OPB_HOST, oh, ow, int(h), int(w), int(stride),
+                                                        pv, scale_index, n_scales))
 
     def precise_add_scale(self, padded_img, pad, scale_index, n_scales):
         img = np.ascontiguousarray(padded_img, np.uint8)

@@ -1957,6 +1957,8 @@ int opb_precise_begin(opb_ctx* ctx, int orig_h, int orig_w) {
 }
 
 static int ensure_ingest(opb_ctx* ctx, size_t bytes);
+static int launch_resize_u8(opb_ctx* ctx, const uint8_t* d_src, int n, int h0, int w0, uint8_t* d_dst, int h, int w,
+                            bool cubic = false);
 
 // forward + both cubic resizes + accumulate for the padded frame already in ch->img_u8 (:447-467)
 static int precise_accumulate(opb_ctx* ctx, PostWs* ws, Chain* ch, int ph, int pw, int pad_h, int pad_w, int scale_index,
@@ -2029,6 +2031,26 @@ int opb_precise_add_scale_unpadded(opb_ctx* ctx, const uint8_t* img, int img_loc
   return precise_accumulate(ctx, ws, ch, ph, pw, pad_h, pad_w, scale_index, n_scales);
 }
 
+int opb_precise_add_scale_orig(opb_ctx* ctx, const uint8_t* orig, int img_loc, int orig_h, int orig_w, int h, int w,
+                               int stride, const uint8_t pad_value[3], int scale_index, int n_scales) {
+  if (!ctx || !orig || !pad_value || orig_h <= 0 || orig_w <= 0 || h <= 0 || w <= 0 || stride <= 0) return OPB_ERR_ARG;
+  PostWs* ws = ctx->last_post;
+  if (!ws || ws->N != 1) OPB_FAIL(ctx, OPB_ERR_STATE, "opb_precise_begin was not called");
+  cudaSetDevice(ctx->device);
+  const size_t in_b = static_cast<size_t>(orig_h) * orig_w * 3, mid_b = static_cast<size_t>(h) * w * 3;
+  const size_t mid_off = (in_b + 255) & ~size_t(255);
+  int rc = ensure_ingest(ctx, mid_off + mid_b + 512);
+  if (rc) return rc;
+  const uint8_t* d_src = orig;
+  if (img_loc == OPB_HOST) {
+    if ((rc = copy_in(ctx, ctx->ingest_buf, orig, in_b, OPB_HOST))) return rc;
+    d_src = ctx->ingest_buf;
+  }
+  uint8_t* d_mid = ctx->ingest_buf + mid_off;
+  if ((rc = launch_resize_u8(ctx, d_src, 1, orig_h, orig_w, d_mid, h, w, true))) return rc;   // :443
+  return opb_precise_add_scale_unpadded(ctx, d_mid, OPB_DEVICE, h, w, stride, pad_value, scale_index, n_scales);
+}
+
 int opb_precise_finish(opb_ctx* ctx, double img_len, opb_image_header* header_out, opb_person* persons_out,
                        int out_loc) {
   if (!ctx || !header_out || !persons_out) return OPB_ERR_ARG;
@@ -2058,14 +2080,16 @@ int opb_download_maps(opb_ctx* ctx, float* pafs_out, float* heat_out, int out_lo
   return OPB_OK;
 }
 
-static int launch_resize_u8(opb_ctx* ctx, const uint8_t* d_src, int n, int h0, int w0, uint8_t* d_dst, int h, int w) {
+static int launch_resize_u8(opb_ctx* ctx, const uint8_t* d_src, int n, int h0, int w0, uint8_t* d_dst, int h, int w,
+                            bool cubic) {
   if (h0 == h && w0 == w) {
     OPB_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, static_cast<size_t>(n) * h * w * 3, cudaMemcpyDeviceToDevice, ctx->stream));
     return OPB_OK;
   }
   const double sx = 1.0 / (static_cast<double>(w) / w0), sy = 1.0 / (static_cast<double>(h) / h0);
   dim3 grid((w + 31) / 32, (h + 7) / 8, n), block(32, 8);
-  resize_linear_u8_kernel<<<grid, block, 0, ctx->stream>>>(d_src, h0, w0, d_dst, h, w, sx, sy);
+  if (cubic) resize_cubic_u8_kernel<<<grid, block, 0, ctx->stream>>>(d_src, h0, w0, d_dst, h, w, sx, sy);
+  else resize_linear_u8_kernel<<<grid, block, 0, ctx->stream>>>(d_src, h0, w0, d_dst, h, w, sx, sy);
   ctx->launches++;
   OPB_CUDA(ctx, cudaGetLastError());
   return OPB_OK;
@@ -2079,8 +2103,21 @@ static int ensure_ingest(opb_ctx* ctx, size_t bytes) {
   return OPB_OK;
 }
 
+static int resize_u8_entry(opb_ctx* ctx, const uint8_t* src, int src_loc, int n, int h0, int w0, uint8_t* dst,
+                           int dst_loc, int h, int w, bool cubic);
+
 int opb_resize_linear_u8(opb_ctx* ctx, const uint8_t* src, int src_loc, int n, int h0, int w0, uint8_t* dst,
                          int dst_loc, int h, int w) {
+  return resize_u8_entry(ctx, src, src_loc, n, h0, w0, dst, dst_loc, h, w, false);
+}
+
+int opb_resize_cubic_u8(opb_ctx* ctx, const uint8_t* src, int src_loc, int n, int h0, int w0, uint8_t* dst,
+                        int dst_loc, int h, int w) {
+  return resize_u8_entry(ctx, src, src_loc, n, h0, w0, dst, dst_loc, h, w, true);
+}
+
+static int resize_u8_entry(opb_ctx* ctx, const uint8_t* src, int src_loc, int n, int h0, int w0, uint8_t* dst,
+                           int dst_loc, int h, int w, bool cubic) {
   if (!ctx || !src || !dst || n <= 0 || h0 <= 0 || w0 <= 0 || h <= 0 || w <= 0) return OPB_ERR_ARG;
   cudaSetDevice(ctx->device);
   const size_t in_b = static_cast<size_t>(n) * h0 * w0 * 3, out_b = static_cast<size_t>(n) * h * w * 3;
@@ -2092,7 +2129,7 @@ int opb_resize_linear_u8(opb_ctx* ctx, const uint8_t* src, int src_loc, int n, i
     d_src = ctx->ingest_buf;
   }
   uint8_t* d_dst = (dst_loc == OPB_HOST) ? ctx->ingest_buf + ((in_b + 255) & ~size_t(255)) : dst;
-  if ((rc = launch_resize_u8(ctx, d_src, n, h0, w0, d_dst, h, w))) return rc;
+  if ((rc = launch_resize_u8(ctx, d_src, n, h0, w0, d_dst, h, w, cubic))) return rc;
   if (dst_loc == OPB_HOST && (rc = copy_out(ctx, dst, d_dst, out_b, OPB_HOST))) return rc;
   OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return OPB_OK;

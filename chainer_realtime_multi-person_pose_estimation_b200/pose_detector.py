@@ -73,9 +73,12 @@ _PRECISIONS = {"parity": _native.PRECISION_PARITY, "fast": _native.PRECISION_FAS
 
 class PoseDetector(object):
     def __init__(self, arch=None, weights_file=None, model=None, device=-1, precise=False, precision=None,
-                 max_peaks=None, max_candidates=None, max_persons=None):
+                 max_peaks=None, max_candidates=None, max_persons=None, device_cubic=None):
         self.arch = arch
         self.precise = precise
+        # precise path: run the per-scale uint8 INTER_CUBIC resize (:443) on the device as well.  Off by default: the host
+        # cv2 call is what the reference executes (IPP builds differ from OpenCV's own path by 1 LSB on 4-8 % of the pixels)
+        self.device_cubic = bool(int(os.environ.get("OPB_DEVICE_CUBIC", "0"))) if device_cubic is None else bool(device_cubic)
         if model is not None:
             self.model = model
         else:
@@ -267,15 +270,21 @@ class PoseDetector(object):
 
     def detect_precise(self, orig_img):
         """Multi-scale path (pose_detector.py:433-482): per scale the uint8 image is resized on the host with
-        cv2 INTER_CUBIC exactly as the reference does (OpenCV dispatches 8-bit cubic to IPP, whose arithmetic cannot be
-        restated bit-exactly); padding, forward, both cubic map resizes, averaging and the whole
-        post-process run on the device."""
+        cv2 INTER_CUBIC exactly as the reference does (this OpenCV build dispatches 8-bit cubic to IPP, whose arithmetic
+        is unpublished) -- or, with device_cubic=True / OPB_DEVICE_CUBIC=1, on the device with OpenCV's own
+        8-bit cubic arithmetic (bit-exact with cv2 when IPP is off); padding, forward, both cubic map resizes, averaging
+        and the whole post-process run on the device."""
         oh, ow = orig_img.shape[:2]
         scales = params['inference_scales']
         self.engine.precise_begin(oh, ow)
         for k, scale in enumerate(scales):
             m = scale * params['inference_img_size'] / min(orig_img.shape[:2])
-            img = cv2.resize(orig_img, (math.ceil(ow * m), math.ceil(oh * m)), interpolation=cv2.INTER_CUBIC)
+            rw, rh = math.ceil(ow * m), math.ceil(oh * m)
+            if self.device_cubic:
+                # the uint8 INTER_CUBIC resize of :443 on the device too (OpenCV's own 8-bit path, csrc/ingest.cuh)
+                self.engine.precise_add_scale_orig(orig_img, rh, rw, params['downscale'], (104, 117, 123), k, len(scales))
+                continue
+            img = cv2.resize(orig_img, (rw, rh), interpolation=cv2.INTER_CUBIC)
             # pad_image(img, 8, (104, 117, 123)) of :445 runs on the device (csrc/ingest.cuh)
             self.engine.precise_add_scale_unpadded(img, params['downscale'], (104, 117, 123), k, len(scales))
         header, persons = self.engine.precise_finish(ow)

@@ -179,6 +179,12 @@ int opb_postprocess_batch(opb_ctx* ctx, const float* paf_lo, const float* heat_l
  *    src [n,h0,w0,3] -> dst [n,h,w,3] uint8.                                                     */
 int opb_resize_linear_u8(opb_ctx* ctx, const uint8_t* src, int src_loc, int n, int h0, int w0,
                          uint8_t* dst, int dst_loc, int h, int w);
+/* cv2.resize(orig_img, ..., interpolation=cv2.INTER_CUBIC) on uint8 BGR (detect_precise, pose_detector.py:443):
+ * OpenCV's own 8-bit cubic path (int16 Keys taps x 2048, int32 horizontal pass, float32 vertical pass with the
+ * fixed-point scalar tail), bit-exact with cv2 when OpenCV does not dispatch to IPP (cv2.ipp.setUseIPP(False), or a
+ * build without IPP); IPP's ippiResizeCubic differs from it by 1 LSB in 4-8 % of the pixels.                 */
+int opb_resize_cubic_u8(opb_ctx* ctx, const uint8_t* src, int src_loc, int n, int h0, int w0,
+                        uint8_t* dst, int dst_loc, int h, int w);
 /* PoseDetector.__call__ for ONE frame of arbitrary size (pose_detector.py:484-517): uploads the
  * original frame, resizes it on the device to (in_h, in_w), then runs the same pipeline as
  * opb_detect_batch with n = 1.                                                                  */
@@ -261,6 +267,11 @@ int opb_precise_add_scale(opb_ctx* ctx, const uint8_t* img, int img_loc, int ph,
  * the bottom / right margin up to the next multiple of `stride` is filled with pad_value (B,G,R).  */
 int opb_precise_add_scale_unpadded(opb_ctx* ctx, const uint8_t* img, int img_loc, int h, int w, int stride,
                                    const uint8_t pad_value[3], int scale_index, int n_scales);
+/* same, starting from the ORIGINAL frame [orig_h,orig_w,3]: the per-scale cv2.resize(..., INTER_CUBIC) to (h, w) of
+ * :443 also runs on the device (opb_resize_cubic_u8's kernel), so one scale costs one upload of the original frame and
+ * no host arithmetic.                                                                                           */
+int opb_precise_add_scale_orig(opb_ctx* ctx, const uint8_t* orig, int img_loc, int orig_h, int orig_w, int h, int w,
+                               int stride, const uint8_t pad_value[3], int scale_index, int n_scales);
 int opb_precise_finish(opb_ctx* ctx, double img_len, opb_image_header* header_out,
                        opb_person* persons_out, int out_loc);
 /* copies the full-resolution maps of image 0 of the current post-process workspace

@@ -216,6 +216,53 @@ def cv2_resize_linear_u8(img, dsize):
     return out.astype(np.uint8).reshape((H, W) + img.shape[2:])
 
 
+def cv2_resize_cubic_u8(img, dsize):
+    """cv2.resize(img, dsize, interpolation=cv2.INTER_CUBIC) for uint8 HxWxC (pose_detector.py:443) as OpenCV's OWN
+    8-bit path computes it (imgproc/resize.cpp, OpenCV 4.13; what runs with cv2.ipp.setUseIPP(False) or without IPP):
+    per axis f = float((d+0.5)*scale - 0.5), s = floor(f), f -= s; Keys taps (A = -0.75) in float32 -> int16
+    rint(tap*2048); horizontal pass int32 with replicated borders; vertical pass in float32 for the 8-lane SIMD body
+    ((D3*b3 + D2*b2) + D1*b1) + D0*b0 with b = beta/2^22, unfused, rint, saturate -- and FixedPtCast<int,uchar,22> for
+    the last (W*C) % 8 elements of each row.  Pinned bit-exact against cv2 (IPP off) in tests/test_oracle.py."""
+    dw, dh = dsize
+    sh, sw = img.shape[:2]
+    f32 = np.float32
+
+    def axis(dn, sn):
+        scale = 1.0 / (dn / sn)
+        f = ((np.arange(dn, dtype=np.float64) + 0.5) * scale - 0.5).astype(f32)
+        s = np.floor(f)
+        x = (f - s.astype(f32)).astype(f32)
+        A = f32(-0.75)
+        t, u = x + f32(1), f32(1) - x
+        c0 = ((A * t - f32(5) * A) * t + f32(8) * A) * t - f32(4) * A
+        c1 = ((A + f32(2)) * x - (A + f32(3))) * x * x + f32(1)
+        c2 = ((A + f32(2)) * u - (A + f32(3))) * u * u + f32(1)
+        c3 = f32(1) - c0 - c1 - c2
+        co = np.rint(np.stack([c0, c1, c2, c3], 1) * f32(2048)).astype(np.int64)
+        return s.astype(np.int64), co
+
+    xo, xa = axis(dw, sw)
+    yo, yb = axis(dh, sh)
+    if (dh, dw) == (sh, sw):
+        return img.copy()
+    S = img.astype(np.int64)
+    idx = np.clip(xo[:, None] + np.arange(-1, 3)[None, :], 0, sw - 1)
+    D = (S[:, idx, :] * xa[None, :, :, None]).sum(2)                       # [sh, dw, C] int32-range
+    idy = np.clip(yo[:, None] + np.arange(-1, 3)[None, :], 0, sh - 1)
+    R = D[idy]                                                             # [dh, 4, dw, C]
+    fixed = ((R * yb[:, :, None, None]).sum(1) + (1 << 21)) >> 22
+    b = yb.astype(f32) * f32(1.0 / 4194304.0)
+    Rf = R.astype(f32)
+    acc = Rf[:, 3] * b[:, 3, None, None]
+    for k in (2, 1, 0):
+        acc = Rf[:, k] * b[:, k, None, None] + acc
+    flt = np.rint(acc).astype(np.int64)
+    C = img.shape[2]
+    simd_end = (dw * C) & ~7
+    out = np.where((np.arange(dw * C) < simd_end).reshape(1, dw, C), flt, fixed)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
 def resize_bilinear_align_corners(x, out_hw):
     """Chainer resize_images [3p] (pose_detector.py:501-502).  x: [B,C,H,W] f32."""
     B, C, H, W = x.shape

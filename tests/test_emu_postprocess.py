@@ -57,7 +57,8 @@ def emu_lib(request):
 
 # the FMA-contracting build repeats the arithmetic-heavy cases only (suite time); everything else runs once
 _FMA_CASES = ("test_upsample_bilinear_bit_exact", "test_full_postprocess_synth8", "test_postprocess_batch_from_network_resolution_maps",
-              "test_device_resize_linear_u8_bit_exact_vs_cv2", "test_keypoints_exact_ties_and_threshold",
+              "test_device_resize_linear_u8_bit_exact_vs_cv2", "test_device_resize_cubic_u8_bit_exact_vs_cv2",
+              "test_keypoints_exact_ties_and_threshold",
               "test_upsample_bicubic_vs_cv2", "test_candidate_connections_single_limb", "test_emulated_library_is_not_the_product")
 
 
@@ -180,6 +181,30 @@ def test_device_resize_linear_u8_bit_exact_vs_cv2(engine):
     got = engine.resize_linear_u8(batch, 48, 64)
     for i in range(3):
         assert np.array_equal(got[i], cv2.resize(batch[i], (64, 48)))
+
+
+def test_device_resize_cubic_u8_bit_exact_vs_cv2(engine):
+    """cv2.resize(..., INTER_CUBIC) on uint8 (pose_detector.py:443): OpenCV's own 8-bit path = cv2 with IPP dispatch off."""
+    import cv2
+    rs = np.random.RandomState(1)
+    shapes = [((120, 120), (46, 46)), ((120, 120), (184, 184)), ((50, 75), (69, 46)), ((300, 18), (9, 150)), ((64, 10), (5, 32)),
+              ((83, 129), (144, 92))]
+    for _ in range(4):
+        shapes.append(((rs.randint(10, 150), rs.randint(10, 150)), (rs.randint(5, 160), rs.randint(5, 160))))
+    was = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        for (h0, w0), (W, H) in shapes:
+            img = rs.randint(0, 256, (h0, w0, 3)).astype(np.uint8)
+            got = engine.resize_cubic_u8(img, H, W)
+            assert np.array_equal(got, cv2.resize(img, (W, H), interpolation=cv2.INTER_CUBIC)), ((h0, w0), (W, H))
+            assert np.array_equal(got, R.cv2_resize_cubic_u8(img, (W, H)))
+        batch = rs.randint(0, 256, (3, 60, 80, 3)).astype(np.uint8)
+        got = engine.resize_cubic_u8(batch, 91, 123)
+        for i in range(3):
+            assert np.array_equal(got[i], cv2.resize(batch[i], (123, 91), interpolation=cv2.INTER_CUBIC))
+    finally:
+        cv2.ipp.setUseIPP(was)
 
 
 def test_keypoints_exact_ties_and_threshold(engine):

@@ -320,9 +320,9 @@ def test_injected_synthetic_eight_person_maps(det_parity):
         assert np.array_equal(subsets, parts["subsets"])
 
 
-def _check_precise(weights_model, precision, name, img, stride):
+def _check_precise(weights_model, precision, name, img, stride, device_cubic=False):
     det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precise=True, precision=precision,
-                                            max_candidates=131072, max_persons=4096)
+                                            max_candidates=131072, max_persons=4096, device_cubic=device_cubic)
     g = load_golden(name)
     oh, ow = img.shape[:2]
     poses, scores = det(img)
@@ -345,7 +345,17 @@ def _check_precise(weights_model, precision, name, img, stride):
     info = dict(strong=bool(strong), map_err=float(max(e1, e2)), peaks=len(G), ref_peaks=len(Rf), peak_symdiff=len(G ^ Rf),
                 persons=int(len(poses)), ref_persons=int(len(g["poses"])))
     print(precision, name, info)
-    _record_branch(precision, name, info)
+    _record_branch(precision + ("+device_cubic" if device_cubic else ""), name, info)
+
+
+def test_precise_path_device_cubic_ingest(weights_model):
+    """detect_precise with the per-scale uint8 INTER_CUBIC resize (:443) on the device as well (OpenCV's own 8-bit cubic
+    arithmetic; the golden was produced with this image's IPP-dispatching cv2, 1 LSB apart on a few per cent of the input
+    pixels): maps inside the tolerance, post-process bit-exact on the device's maps, peak flips only at near-ties."""
+    _check_precise(weights_model, "parity", "precise_480_he0.npz", pkg("synthetic").procedural_image(480, 480, seed=3), 7,
+                   device_cubic=True)
+    _check_precise(weights_model, "comp", "precise_200x300_he0.npz", pkg("synthetic").procedural_image(200, 300, seed=4), 5,
+                   device_cubic=True)
 
 
 @pytest.mark.parametrize("precision", ["parity", "comp"])

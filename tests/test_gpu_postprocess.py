@@ -256,3 +256,30 @@ def test_device_resize_linear_u8_bit_exact_vs_cv2(engine):
     got = engine.resize_linear_u8(batch, 96, 128)
     for i in range(3):
         assert np.array_equal(got[i], cv2.resize(batch[i], (128, 96)))
+
+
+def test_device_resize_cubic_u8_bit_exact_vs_cv2(engine):
+    """cv2.resize(..., INTER_CUBIC) on uint8 (detect_precise, pose_detector.py:443) on the device: OpenCV's own 8-bit
+    cubic path, bit-exact with cv2 when IPP dispatch is off (and with the oracle restatement); the sizes are the
+    per-scale sizes detect_precise produces for 480x480 and 200x300 frames plus ragged ones (scalar-tail columns)."""
+    import cv2
+    rs = np.random.RandomState(1)
+    shapes = [((480, 480), (184, 184)), ((480, 480), (368, 368)), ((480, 480), (552, 552)), ((480, 480), (736, 736)),
+              ((200, 300), (276, 184)), ((200, 300), (1104, 736)), ((3000, 54), (27, 1500)), ((2000, 10), (5, 1000)),
+              ((360, 640), (321, 181)), ((97, 131), (131, 97))]
+    for _ in range(8):
+        shapes.append(((rs.randint(20, 400), rs.randint(20, 400)), (rs.randint(5, 500), rs.randint(5, 500))))
+    was = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        for (h0, w0), (W, H) in shapes:
+            img = rs.randint(0, 256, (h0, w0, 3)).astype(np.uint8)
+            got = engine.resize_cubic_u8(img, H, W)
+            assert np.array_equal(got, R.cv2_resize_cubic_u8(img, (W, H))), ((h0, w0), (W, H))
+            assert np.array_equal(got, cv2.resize(img, (W, H), interpolation=cv2.INTER_CUBIC)), ((h0, w0), (W, H))
+        batch = rs.randint(0, 256, (3, 120, 160, 3)).astype(np.uint8)
+        got = engine.resize_cubic_u8(batch, 171, 233)
+        for i in range(3):
+            assert np.array_equal(got[i], cv2.resize(batch[i], (233, 171), interpolation=cv2.INTER_CUBIC))
+    finally:
+        cv2.ipp.setUseIPP(was)

@@ -122,6 +122,30 @@ def test_cv2_linear_u8_restatement_bit_exact():
         assert np.array_equal(R.cv2_resize_linear_u8(img, (W, H)), cv2.resize(img, (W, H))), ((h0, w0), (W, H))
 
 
+def test_cv2_cubic_u8_restatement_bit_exact():
+    """OpenCV's own 8-bit INTER_CUBIC path (pose_detector.py:443), i.e. cv2 with IPP dispatch off; with IPP on (this
+    image's default) ippiResizeCubic differs by 1 LSB on a few per cent of the pixels -- bounded here, not matched."""
+    import cv2
+    rs = np.random.RandomState(0)
+    shapes = [((480, 480), (184, 184)), ((480, 480), (368, 368)), ((480, 480), (552, 552)), ((480, 480), (736, 736)),
+              ((200, 300), (276, 184)), ((200, 300), (1104, 736)), ((3000, 54), (27, 1500)), ((2000, 10), (5, 1000)),
+              ((360, 640), (321, 181)), ((97, 131), (131, 97))]
+    for _ in range(8):
+        shapes.append(((rs.randint(20, 400), rs.randint(20, 400)), (rs.randint(5, 500), rs.randint(5, 500))))
+    was = cv2.ipp.useIPP()
+    try:
+        for (h0, w0), (W, H) in shapes:
+            img = rs.randint(0, 256, (h0, w0, 3)).astype(np.uint8)
+            got = R.cv2_resize_cubic_u8(img, (W, H))
+            cv2.ipp.setUseIPP(False)
+            assert np.array_equal(got, cv2.resize(img, (W, H), interpolation=cv2.INTER_CUBIC)), ((h0, w0), (W, H))
+            cv2.ipp.setUseIPP(True)
+            d = np.abs(got.astype(int) - cv2.resize(img, (W, H), interpolation=cv2.INTER_CUBIC).astype(int))
+            assert d.max() <= 1 and (d != 0).mean() < 0.15, ((h0, w0), (W, H), d.max(), (d != 0).mean())
+    finally:
+        cv2.ipp.setUseIPP(was)
+
+
 def test_optimal_size_rule():
     z = np.zeros
     assert R.compute_optimal_size(z((368, 656, 3)), 368) == (656, 368)

@@ -20,6 +20,10 @@ for K in "${KERNELS[@]}"; do
       python bench.py --precision $PREC --steps 1 --warmup 1 --no-cpu-baseline --no-parity-extra --no-stage-timing ${BENCH_EXTRA:-} > $OUT.log 2>&1
   if [ -f $OUT.ncu-rep ]; then
     ncu -i $OUT.ncu-rep --page raw --csv > $OUT.csv 2>/dev/null
+    ncu -i $OUT.ncu-rep --page details --csv > ${OUT}_details.csv 2>/dev/null
+    if [ "${KEEP_SOURCE:-0}" = "1" ]; then ncu -i $OUT.ncu-rep --page source --csv > ${OUT}_source.csv 2>/dev/null; fi
+    # gpurun merges at most 64 MiB back: the report itself stays on the box unless asked for
+    if [ "${KEEP_REP:-0}" != "1" ]; then rm -f $OUT.ncu-rep; fi
     python - "$OUT.csv" "$K" <<'PY' > ${OUT}_summary.txt
 import csv, sys, re
 rows = list(csv.reader(open(sys.argv[1])))
