@@ -66,6 +66,10 @@ _SIGNATURES = {
                                              C.c_void_p, C.c_int, C.c_int]),
     "opb_detect_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
+    "opb_draw_person_pose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                       C.c_int]),
+    "opb_draw_last_result": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                       C.c_void_p, C.c_int]),
     "opb_stream_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "opb_stream_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -323,6 +327,25 @@ class Engine(object):
         out = np.empty((n, out_h, out_w, 3), np.uint8)
         self._check(self.lib.opb_resize_cubic_u8(self.ctx, _ptr(a), OPB_HOST, n, h0, w0, _ptr(out), OPB_HOST, out_h, out_w))
         return out[0] if single else out
+
+    def draw_person_pose(self, img, poses):
+        """draw_person_pose(orig_img, poses) (pose_detector.py:520-553) on the device; poses float [P,18,3]."""
+        a = np.ascontiguousarray(img, np.uint8)
+        h, w, _ = a.shape
+        ip = np.ascontiguousarray(np.asarray(poses).round().astype('i').reshape(-1, 18, 3), np.int32)
+        out = np.empty_like(a)
+        self._check(self.lib.opb_draw_person_pose(self.ctx, _ptr(a), OPB_HOST, h, w, _ptr(ip) if len(ip) else None, len(ip),
+                                                  _ptr(out), OPB_HOST))
+        return out
+
+    def draw_last_result(self, img, sx, sy, image_index=0):
+        """Overlay of the persons of the last detect call, taken from the device-resident records."""
+        a = np.ascontiguousarray(img, np.uint8)
+        h, w, _ = a.shape
+        out = np.empty_like(a)
+        self._check(self.lib.opb_draw_last_result(self.ctx, int(image_index), _ptr(a), OPB_HOST, h, w, float(sx), float(sy),
+                                                  _ptr(out), OPB_HOST))
+        return out
 
     def detect_image(self, img, in_h, in_w, map_h, map_w, img_len=None):
         """One BGR frame of any size: upload, device resize, full pipeline (opb_detect_image)."""

@@ -252,7 +252,7 @@ conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict_
     ptx::tc_fence_before();
     __syncthreads();
     // (3) two MMAs, one elected thread
-    if (tid == 0) {
+    if (warp == 0 && ptx::elect_one()) {
       ptx::tc_fence_after();
       ptx::mma_f16_ss(tmem, a_desc, b_desc, IDESC, 0u);
       ptx::mma_f16_ss_acc(tmem, a_desc + 2, b_desc + 2, IDESC);
@@ -399,7 +399,7 @@ conv_first_tcx_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && ptx::elect_one()) {
       ptx::tc_fence_after();
       ptx::mma_f16_ss(tmem, a_desc, b_desc, IDESC, 0u);                          // hi weights, k-steps 0..2
       ptx::mma_f16_ss_acc(tmem, a_desc + 2, b_desc + 2, IDESC);

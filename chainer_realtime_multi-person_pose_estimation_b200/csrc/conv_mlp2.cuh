@@ -100,7 +100,7 @@ conv_mlp2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int rem = tile - n * (P.tiles_y * P.tiles_x);
     const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
     const int y0 = ty * 16, x0 = tx * 8;
-    if (tid == 0) {
+    if (warp == 0 && ptx::elect_one()) {
       if (!weights_ready) ptx::mbar_wait(&bars[0], 0);
       ptx::mbar_wait(&bars[1], par_a);
       ptx::tc_fence_after();
@@ -143,7 +143,7 @@ conv_mlp2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     ptx::fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core
     ptx::tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && ptx::elect_one()) {
       ptx::tc_fence_after();
       // GEMM 2: h x W7^T -> TMEM columns 128..175
 #pragma unroll

@@ -395,7 +395,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int p = tile / tiles_per_problem;
@@ -435,7 +435,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
       const uint64_t a_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemA), 1024);
       const uint64_t b_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemB), 1024);

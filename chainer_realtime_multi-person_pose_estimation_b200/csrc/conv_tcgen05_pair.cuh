@@ -104,7 +104,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
 
   if (warp == 0) {
     // ================================================================ TMA producer (both CTAs)
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       for (int tile = pair_id; tile < total_tiles; tile += n_pairs) {
         const int p = tile / tiles_per_problem;
@@ -142,7 +142,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && ptx::elect_one()) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
       const uint64_t a_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemA), 1024);
       const uint64_t b_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemB), 1024);

@@ -124,7 +124,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
 
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t sp = 0, pp = 0, sw = 0, pw = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const TileId tid_ = decode(tile);
@@ -158,7 +158,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __gr
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t sp = 0, pp = 0, sw = 0, pw = 0, acc = 0, pacc = 0;
       const uint64_t p_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemP), 1024);
       const uint64_t w_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemW), 1024);

@@ -20,10 +20,12 @@
 #include "conv_first.cuh"
 #include "conv_mlp2.cuh"
 #include "ingest.cuh"
+#include "overlay.cuh"
 #include "keypoints.cuh"
 #include "conv_tcgen05.cuh"
 #include "conv_tcgen05_pair.cuh"
 #include "conv_tcgen05_swap.cuh"
+#include "conv_tcgen05_swap7.cuh"
 #include "paf.cuh"
 #include "peaks.cuh"
 #include "peaks_sep.cuh"
@@ -75,6 +77,7 @@ struct Op {
   bool pair = false;   // cta_group::2 kernel (cluster of 2 CTAs)
   bool swap = false;   // weights-as-A kernel (16x16 pixel tiles as the N=256 operand)
   int cluster = 1;     // swap kernel: CTAs per cluster sharing every weight tile through multicast TMA (1 or 2)
+  bool swap7 = false;  // 7x7 swap launches use the lean-issue kernel (conv_tcgen05_swap7.cuh)
   CUtensorMap tmP16[2];
   CUtensorMap tmA[2], tmB[2];
   ConvParams P;
@@ -168,6 +171,8 @@ struct opb_ctx {
   PostWs* last_post = nullptr;
   uint8_t* ingest_buf = nullptr;   // staging for the original frame(s) of opb_detect_image
   float* precise_mid = nullptr;    // x8 cubic intermediate of the precise path
+  uint8_t* ov_buf = nullptr;       // overlay scratch: [frame in | frame out | priority plane | int poses | flag]
+  size_t ov_bytes = 0;
   size_t precise_mid_cap = 0;
   size_t ingest_bytes = 0;
   // streaming mode (opb_stream_submit / opb_stream_collect): two slots, pinned staging, a copy stream
@@ -349,9 +354,29 @@ int launch_conv_swap_t(opb_ctx* ctx, const Op& op) {
   return OPB_OK;
 }
 
+template <bool COMP, bool DRAIN>
+int launch_conv_swap7_t(opb_ctx* ctx, const Op& op) {
+  using Cfg = ConvSwap7Cfg;
+  auto kern = conv_tcgen05_swap7_kernel<COMP, DRAIN>;
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    OPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[ctx->device & 63] = true;
+  }
+  kern<<<op.grid, DRAIN ? kSwapDrainThreads : kConvThreads, Cfg::SMEM_BYTES, ctx->stream>>>(
+      op.tmP16[0], op.tmA[0], op.tmB[0], op.tmP16[1], op.tmA[1], op.tmB[1], op.P);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  return OPB_OK;
+}
+
 int launch_conv(opb_ctx* ctx, const Op& op) {
   const int key = op.ks * 10000 + op.bn * 10 + op.mt;
   if (op.swap) {
+    if (op.ks == 7 && op.cluster != 2 && op.swap7) {   // lean-issue variant (conv_tcgen05_swap7.cuh); OPB_SWAP7=0 disables
+      if (op.P.comp) return op.drain ? launch_conv_swap7_t<true, true>(ctx, op) : launch_conv_swap7_t<true, false>(ctx, op);
+      return op.drain ? launch_conv_swap7_t<false, true>(ctx, op) : launch_conv_swap7_t<false, false>(ctx, op);
+    }
     if (op.ks == 7 && op.cluster == 2)
       return op.drain ? launch_conv_swap_t<7, 3, 5, true, 2>(ctx, op) : launch_conv_swap_t<7, 3, 5, false, 2>(ctx, op);
     if (op.ks == 7) return op.drain ? launch_conv_swap_t<7, 3, 5, true>(ctx, op) : launch_conv_swap_t<7, 3, 5>(ctx, op);
@@ -667,6 +692,8 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     const int want = e ? atoi(e) : 0;
     const int m_tiles = P.N * P.tiles_y * P.tiles_x;
     if (want == 2 && m_tiles % 2 == 0 && m_tiles * P.n_blocks * P.n_problems >= 2 && ctx->num_sms >= 2) op.cluster = 2;
+    const char* e7 = getenv("OPB_SWAP7");
+    op.swap7 = !(e7 && atoi(e7) == 0);
   }
   const int chunks = w0.cin_pad / 64;
   int np = 0;
@@ -1393,6 +1420,7 @@ void opb_destroy(opb_ctx* ctx) {
   free_all(ctx->weight_allocs);
   if (ctx->ingest_buf) cudaFree(ctx->ingest_buf);
   if (ctx->precise_mid) cudaFree(ctx->precise_mid);
+  if (ctx->ov_buf) cudaFree(ctx->ov_buf);
   if (ctx->kp_ws) {
     cudaFree(ctx->kp_ws->up); cudaFree(ctx->kp_ws->tmp); cudaFree(ctx->kp_ws->res); cudaFreeHost(ctx->kp_ws->h_res);
     delete ctx->kp_ws;
@@ -2078,6 +2106,100 @@ int opb_download_maps(opb_ctx* ctx, float* pafs_out, float* heat_out, int out_lo
   if (heat_out && (rc = copy_out(ctx, heat_out, ws->heat, plane * 19, out_loc))) return rc;
   OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return OPB_OK;
+}
+
+// ---- draw_person_pose on the device (pose_detector.py:520-553; csrc/overlay.cuh) -------------------------------
+static OverlayTables overlay_tables(const opb_ctx* ctx) {
+  // limb_colors / joint_colors of pose_detector.py:523-535, written into channels 0,1,2 as given
+  static const uint8_t kLimb[OV_LIMBS][3] = {
+      {0, 255, 0}, {0, 255, 85}, {0, 255, 170}, {0, 255, 255}, {0, 170, 255}, {0, 85, 255}, {255, 0, 0},
+      {255, 85, 0}, {255, 170, 0}, {255, 255, 0}, {255, 0, 85}, {170, 255, 0}, {85, 255, 0}, {170, 0, 255},
+      {0, 0, 255}, {0, 0, 255}, {255, 0, 255}, {170, 0, 255}, {255, 0, 170}};
+  static const uint8_t kJoint[OV_JOINTS][3] = {
+      {255, 0, 0}, {255, 85, 0}, {255, 170, 0}, {255, 255, 0}, {170, 255, 0}, {85, 255, 0}, {0, 255, 0},
+      {0, 255, 85}, {0, 255, 170}, {0, 255, 255}, {0, 170, 255}, {0, 85, 255}, {0, 0, 255}, {85, 0, 255},
+      {170, 0, 255}, {255, 0, 255}, {255, 0, 170}, {255, 0, 85}};
+  OverlayTables tb;
+  for (int l = 0; l < OV_LIMBS; ++l) {
+    tb.limb_a[l] = ctx->prm.limbs[l][0];
+    tb.limb_b[l] = ctx->prm.limbs[l][1];
+    for (int c = 0; c < 3; ++c) tb.limb_color[l][c] = kLimb[l][c];
+  }
+  for (int j = 0; j < OV_JOINTS; ++j)
+    for (int c = 0; c < 3; ++c) tb.joint_color[j][c] = kJoint[j][c];
+  return tb;
+}
+
+// poses: device int [n_poses][18][3] when from_records == nullptr; otherwise the records of one image are converted first
+static int overlay_run(opb_ctx* ctx, const uint8_t* img, int img_loc, int h, int w, const int32_t* host_poses, int n_poses,
+                       const PersonOut* d_records, double sx, double sy, uint8_t* out, int out_loc) {
+  cudaSetDevice(ctx->device);
+  const size_t px = static_cast<size_t>(h) * w, img_b = (px * 3 + 255) & ~size_t(255);
+  const size_t prio_b = (px * 4 + 255) & ~size_t(255), poses_b = (static_cast<size_t>(n_poses > 0 ? n_poses : 1) * OV_JOINTS * 3 * 4 + 255) & ~size_t(255);
+  const size_t need = 2 * img_b + prio_b + poses_b + 256;
+  if (ctx->ov_bytes < need) {
+    if (ctx->ov_buf) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->ov_buf); ctx->ov_buf = nullptr; ctx->ov_bytes = 0; }
+    OPB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->ov_buf), need));
+    ctx->ov_bytes = need;
+  }
+  uint8_t* d_in = ctx->ov_buf;
+  uint8_t* d_out = ctx->ov_buf + img_b;
+  unsigned int* d_prio = reinterpret_cast<unsigned int*>(ctx->ov_buf + 2 * img_b);
+  int* d_poses = reinterpret_cast<int*>(ctx->ov_buf + 2 * img_b + prio_b);
+  int* d_bad = reinterpret_cast<int*>(ctx->ov_buf + 2 * img_b + prio_b + poses_b);
+  int rc;
+  const uint8_t* d_src = img;
+  if (img_loc == OPB_HOST) {
+    if ((rc = copy_in(ctx, d_in, img, px * 3, OPB_HOST))) return rc;
+    d_src = d_in;
+  }
+  uint8_t* d_dst = (out_loc == OPB_HOST) ? d_out : out;
+  OPB_CUDA(ctx, cudaMemsetAsync(d_prio, 0, px * 4, ctx->stream));
+  OPB_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+  const OverlayTables tb = overlay_tables(ctx);
+  if (n_poses > 0) {
+    if (d_records) {
+      const int* base = reinterpret_cast<const int*>(d_records);
+      const int stride = static_cast<int>(sizeof(PersonOut) / 4), off_id = 4, off_x = 4 + OPB_N_JOINTS, off_y = 4 + 2 * OPB_N_JOINTS;
+      overlay_poses_from_records_kernel<<<(n_poses * OV_JOINTS + 127) / 128, 128, 0, ctx->stream>>>(
+          base + off_x, base + off_y, base + off_id, stride, n_poses, sx, sy, d_poses);
+      ctx->launches++;
+    } else {
+      if ((rc = copy_in(ctx, d_poses, host_poses, static_cast<size_t>(n_poses) * OV_JOINTS * 3 * 4, OPB_HOST))) return rc;
+    }
+    const int n_prim = n_poses * (OV_LIMBS + OV_JOINTS);
+    overlay_raster_kernel<<<(n_prim + 63) / 64, 64, 0, ctx->stream>>>(d_poses, n_poses, tb, d_prio, h, w, d_bad);
+    ctx->launches++;
+  }
+  overlay_paint_kernel<<<static_cast<unsigned>((px + 255) / 256), 256, 0, ctx->stream>>>(d_src, d_prio, static_cast<int>(px), n_poses, tb, d_dst);
+  ctx->launches++;
+  OPB_CUDA(ctx, cudaGetLastError());
+  int bad = 0;
+  OPB_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_loc == OPB_HOST && (rc = copy_out(ctx, out, d_dst, px * 3, OPB_HOST))) return rc;
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (bad) OPB_FAIL(ctx, OPB_ERR_ARG, "draw_person_pose: a joint lies outside the image");
+  return OPB_OK;
+}
+
+int opb_draw_person_pose(opb_ctx* ctx, const uint8_t* img, int img_loc, int h, int w, const int32_t* poses, int n_poses,
+                         uint8_t* out, int out_loc) {
+  if (!ctx || !img || !out || h <= 0 || w <= 0 || n_poses < 0 || (n_poses > 0 && !poses)) return OPB_ERR_ARG;
+  return overlay_run(ctx, img, img_loc, h, w, poses, n_poses, nullptr, 1.0, 1.0, out, out_loc);
+}
+
+int opb_draw_last_result(opb_ctx* ctx, int image_index, const uint8_t* img, int img_loc, int h, int w, double sx, double sy,
+                         uint8_t* out, int out_loc) {
+  if (!ctx || !img || !out || h <= 0 || w <= 0) return OPB_ERR_ARG;
+  PostWs* ws = ctx->last_post;
+  if (!ws || image_index < 0 || image_index >= ws->N) OPB_FAIL(ctx, OPB_ERR_STATE, "no result for that image");
+  cudaSetDevice(ctx->device);
+  ImageHeader hd;
+  OPB_CUDA(ctx, cudaMemcpyAsync(&hd, ws->headers + image_index, sizeof(hd), cudaMemcpyDeviceToHost, ctx->stream));
+  OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (hd.status != 0) OPB_FAIL(ctx, hd.status, "the image's result carries an error status");
+  return overlay_run(ctx, img, img_loc, h, w, nullptr, hd.n_persons,
+                     ws->persons + static_cast<size_t>(image_index) * ctx->prm.max_persons, sx, sy, out, out_loc);
 }
 
 static int launch_resize_u8(opb_ctx* ctx, const uint8_t* d_src, int n, int h0, int w0, uint8_t* d_dst, int h, int w,

@@ -40,6 +40,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// One lane of a CONVERGED warp (all 32 lanes must execute this).  ptxas recognises a region guarded by elect.sync as
+// single-threaded and emits the tcgen05.mma / TMA / commit instructions inside it bare; guarded by `lane == 0` each of
+// them is wrapped in a "for every active lane" loop (ELECT / R2UR.BROADCAST / PLOP3 / BRA.U.ANY, +5 instructions per
+// MMA) -- measured on the role-swapped 7x7 kernel: ~70 -> ~27 issued instructions per four MMAs, and the issuing thread
+// was the bottleneck (profiles/r02_ncu_comp_swap7x7_summary.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // Bounded wait: a protocol bug must trap, never hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

@@ -291,6 +291,7 @@ class PoseDetector(object):
         self.pafs, self.heatmaps = self.engine.download_maps(oh, ow)
         self.engine.raise_for_status(int(header[0]["status"]))
         self.all_peaks = self.engine.image_detail(0)[0] if header[0]["n_peaks"] else np.array([])
+        self._last_scale = (1.0, 1.0)
         return self._poses_from_records(header[0], persons[0], 1.0, 1.0)
 
     def __call__(self, orig_img):
@@ -303,7 +304,14 @@ class PoseDetector(object):
         # cv2.resize(orig_img, (input_w, input_h)) of the reference (:493) runs on the device, bit-exact with
         # OpenCV's 8-bit INTER_LINEAR (csrc/ingest.cuh); the frame is uploaded once at its original size
         headers, persons = self.engine.detect_image(orig_img, in_h, in_w, map_h, map_w, img_len=map_w)
+        self._last_scale = (ow / map_w, oh / map_h)
         return self._poses_from_records(headers[0], persons[0], ow / map_w, oh / map_h)
+
+    def draw_last_result(self, orig_img):
+        """draw_person_pose(orig_img, poses) for the frame just passed to __call__, with the poses taken from the
+        device-resident result records (the per-frame drawing of camera_pose_demo.py:27 without the host round trip)."""
+        sx, sy = self._last_scale
+        return self.engine.draw_last_result(orig_img, sx, sy)
 
     def detect_batch(self, imgs, orig_sizes=None):
         """Batched fast path for equally sized BGR frames [N,H,W,3] (no reference analogue: the
@@ -365,11 +373,14 @@ _JOINT_COLORS = [
     [170, 0, 255], [255, 0, 255], [255, 0, 170], [255, 0, 85]]
 
 
-def draw_person_pose(orig_img, poses):
+def draw_person_pose(orig_img, poses, engine=None):
     """Skeleton overlay (pose_detector.py:520-553): limbs first (ear-shoulder limbs 9 and 13 are
-    not drawn), then joints."""
+    not drawn), then joints.  With `engine` (a detector's .engine) the overlay is rasterised on the device
+    (opb_draw_person_pose: OpenCV's thick-line / filled-circle arithmetic restated, pixel-identical; csrc/overlay.cuh)."""
     if len(poses) == 0:
         return orig_img
+    if engine is not None:
+        return engine.draw_person_pose(orig_img, poses)
     canvas = orig_img.copy()
     int_poses = poses.round().astype('i')
     for pose in int_poses:

@@ -192,6 +192,20 @@ int opb_detect_image(opb_ctx* ctx, const uint8_t* img, int img_loc, int orig_h, 
                      int in_w, int map_h, int map_w, double img_len, opb_image_header* header_out,
                      opb_person* persons_out, int out_loc);
 
+/* -- skeleton overlay: replaces draw_person_pose(orig_img, poses), pose_detector.py:520-553 (the camera loop's
+ *    per-frame drawing, camera_pose_demo.py:27).  img [h,w,3] uint8 BGR -> out [h,w,3] = img.copy() with, per person,
+ *    the 17 drawn limbs (cv2.line thickness 2; limbs 9 and 13 skipped) and then the joints (cv2.circle radius 3,
+ *    filled) in the reference's order and colours, rasterised exactly as OpenCV 4.x does (csrc/overlay.cuh).
+ *    poses: host int32 [n_poses,18,3] = poses.round().astype('i') (x, y, visible != 0).  Every drawn joint must lie
+ *    inside the image (true for any pose the detector returns); otherwise OPB_ERR_ARG.                           */
+int opb_draw_person_pose(opb_ctx* ctx, const uint8_t* img, int img_loc, int h, int w, const int32_t* poses,
+                         int n_poses, uint8_t* out, int out_loc);
+/* same, taking the persons of image `image_index` of the last detect call straight from the device-resident records
+ * (no host round trip of the poses): joint = rint(peak * (sx, sy)) in float64 as :513-514 and :539 compute it
+ * (sx = orig_w / map_w, sy = orig_h / map_h; 1, 1 after the precise path).                                        */
+int opb_draw_last_result(opb_ctx* ctx, int image_index, const uint8_t* img, int img_loc, int h, int w, double sx,
+                         double sy, uint8_t* out, int out_loc);
+
 /* -- streaming mode: the camera loop of camera_pose_demo.py:20-31, pipelined.  Two slots; submit()
  *    enqueues [pinned staging ->] H2D on a copy stream, the device resize (if orig != in), the whole
  *    pipeline and the D2H of the records, and returns without waiting; collect() blocks until that

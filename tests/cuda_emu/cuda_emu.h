@@ -461,6 +461,7 @@ inline float __fdiv_rn(float a, float b) { float r = a / b; EMU_FENCE(r); return
 inline float __fmaf_rn(float a, float b, float c) { float r = std::fmaf(a, b, c); EMU_FENCE(r); return r; }
 inline float __double2float_rn(double a) { float r = static_cast<float>(a); EMU_FENCE(r); return r; }
 inline int __double2int_rn(double a) { return static_cast<int>(std::nearbyint(a)); }
+inline long long __double2ll_rn(double a) { return static_cast<long long>(std::nearbyint(a)); }
 inline int __float2int_rn(float a) { return static_cast<int>(std::nearbyintf(a)); }
 inline int __float2int_rd(float a) { return static_cast<int>(std::floor(a)); }
 inline int __double2int_rd(double a) { return static_cast<int>(std::floor(a)); }

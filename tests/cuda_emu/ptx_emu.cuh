@@ -463,6 +463,8 @@ EMU_INTERNAL inline void mma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
 }
 
 // ---------------------------------------------------------------- CTA pairs (cta_group::2): both CTAs resident
+// elect.sync: one lane of the (converged) warp -- the emulator elects lane 0
+EMU_INTERNAL inline bool elect_one() { return (threadIdx.x & 31u) == 0u; }
 EMU_INTERNAL inline uint32_t cluster_ctarank() { emu::need_cluster(); return static_cast<uint32_t>(emu::g_cur_cta); }
 EMU_INTERNAL inline void cluster_sync_all() { emu::need_cluster(); emu::yield_wait(emu::WAIT_CLUSTER); }
 EMU_INTERNAL inline uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) { emu::need_cluster(); return emu::cluster_addr(local_addr, rank); }

@@ -104,6 +104,26 @@ def test_comp_small_batch_two_level_accumulation(emu_native, monkeypatch, case):
     assert np.abs(y - ref).max() <= 3e-4 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("mode", ["fast", "comp"])
+def test_lean_issue_swap7_kernel_bit_identical_to_swap_kernel(emu_native, monkeypatch, mode):
+    """conv_tcgen05_swap7_kernel (7-stage weight ring = one filter column, compile-time stage addresses, elect.sync issue;
+    the default for the 7x7 128->128 layers) issues the same MMAs in the same order as conv_tcgen05_swap_kernel
+    (OPB_SWAP7=0): identical bits, incl. the 8-pixel edge tile, the trimmed last tile row and ring wrap-around."""
+    case = (2, 23, 19, 128, 128, 7, 1)
+    n, h, w, cin, cout, ks, relu = case
+    rs = np.random.RandomState(7)
+    x = rs.standard_normal((n, h, w, cin)).astype(np.float32)
+    W = (rs.standard_normal((cout, cin, ks, ks)) * np.sqrt(2.0 / (cin * ks * ks))).astype(np.float32)
+    b = (rs.standard_normal(cout) * 0.1).astype(np.float32)
+    prec = {"fast": emu_native.PRECISION_FAST, "comp": emu_native.PRECISION_COMP}[mode]
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("OPB_SWAP7", flag)
+        eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params())
+        out.append(eng.test_conv(x, W, b, relu, prec))
+    assert np.array_equal(out[0], out[1])
+
+
 def _emu_stats(lib):
     st = (C.c_longlong * 4)()
     lib.opb_emu_stats(st)

@@ -57,7 +57,7 @@ def emu_lib(request):
 
 # the FMA-contracting build repeats the arithmetic-heavy cases only (suite time); everything else runs once
 _FMA_CASES = ("test_upsample_bilinear_bit_exact", "test_full_postprocess_synth8", "test_postprocess_batch_from_network_resolution_maps",
-              "test_device_resize_linear_u8_bit_exact_vs_cv2", "test_device_resize_cubic_u8_bit_exact_vs_cv2",
+              "test_device_resize_linear_u8_bit_exact_vs_cv2", "test_device_resize_cubic_u8_bit_exact_vs_cv2", "test_device_overlay_pixel_identical_to_cv2",
               "test_keypoints_exact_ties_and_threshold",
               "test_upsample_bicubic_vs_cv2", "test_candidate_connections_single_limb", "test_emulated_library_is_not_the_product")
 
@@ -205,6 +205,10 @@ def test_device_resize_cubic_u8_bit_exact_vs_cv2(engine):
             assert np.array_equal(got[i], cv2.resize(batch[i], (123, 91), interpolation=cv2.INTER_CUBIC))
     finally:
         cv2.ipp.setUseIPP(was)
+
+
+def test_device_overlay_pixel_identical_to_cv2(engine):
+    G.test_device_overlay_pixel_identical_to_cv2(engine)
 
 
 def test_keypoints_exact_ties_and_threshold(engine):

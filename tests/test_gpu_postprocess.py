@@ -283,3 +283,40 @@ def test_device_resize_cubic_u8_bit_exact_vs_cv2(engine):
             assert np.array_equal(got[i], cv2.resize(batch[i], (233, 171), interpolation=cv2.INTER_CUBIC))
     finally:
         cv2.ipp.setUseIPP(was)
+
+
+def _random_poses(rs, n, h, w, border=False):
+    poses = np.zeros((n, 18, 3), np.float64)
+    for p in range(n):
+        cx, cy = rs.uniform(0, w - 1), rs.uniform(0, h - 1)
+        for j in range(18):
+            if rs.rand() < 0.2:
+                continue
+            x = np.clip(cx + rs.normal(0, w / 6.0), 0, w - 1)
+            y = np.clip(cy + rs.normal(0, h / 6.0), 0, h - 1)
+            if border and rs.rand() < 0.3:
+                x = rs.choice([0, 1, w - 2, w - 1])
+            if border and rs.rand() < 0.3:
+                y = rs.choice([0, 1, h - 2, h - 1])
+            poses[p, j] = (x + rs.uniform(-0.49, 0.49) if 1 <= x <= w - 2 else x, y, 2)
+    return poses
+
+
+def test_device_overlay_pixel_identical_to_cv2(engine):
+    """draw_person_pose (pose_detector.py:520-553) on the device vs the host cv2 calls the reference makes: thick lines,
+    filled circles, overwrite order, joints on the image border, degenerate (zero-length) limbs, absent joints."""
+    pd, native = pkg("pose_detector"), pkg("_native")
+    rs = np.random.RandomState(3)
+    for k, (h, w, n) in enumerate([(120, 160, 3), (97, 61, 5), (64, 64, 12), (240, 320, 2), (33, 200, 4), (50, 50, 1)]):
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        poses = _random_poses(rs, n, h, w, border=(k % 2 == 1))
+        if k == 2:
+            poses[0, 3] = poses[0, 2]                      # zero-length limb
+        ref = pd.draw_person_pose(img, poses)
+        got = pd.draw_person_pose(img, poses, engine=engine)
+        assert got.shape == ref.shape and np.array_equal(got, ref), (h, w, n, int((got != ref).any(2).sum()))
+    # no poses: the frame comes back unchanged
+    assert np.array_equal(engine.draw_person_pose(img, np.zeros((0, 18, 3))), img)
+    bad = np.zeros((1, 18, 3)); bad[0, 0] = (w + 5, 3, 2); bad[0, 1] = (3, 3, 2)
+    with pytest.raises(native.OpbError):
+        engine.draw_person_pose(img, bad)
