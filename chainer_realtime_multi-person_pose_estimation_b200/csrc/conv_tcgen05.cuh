@@ -39,6 +39,8 @@
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace opb {
@@ -450,50 +452,67 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           ptx::tc_fence_after();
         }
         uint32_t accumulate = 0;
-        for (int j = 0; j < P.n_pairs; ++j) {
-          const bool f8 = P.comp && (j & 1);   // compensated precision: odd pairs are the 8-bit correction rows
-          for (int s = 0; s < KS; ++s) {
-            ptx::mbar_wait(&a_full[sa], pa);
-            if (DRAIN) {   // two-level accumulation: a fresh TMEM accumulator per A stage
-              ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
-              accumulate = 0;
+        // One (chunk pair, filter column) step: KS weight stages x n_sub sub-tiles x 4 MMAs.  The MMA kind is a compile-time
+        // property of the step, and when the weight ring holds a whole number of steps (NSB % KS == 0) the stage index
+        // inside the unrolled tap loop is `first stage of the step + r`: barrier addresses and descriptors are one base
+        // value per step plus compile-time offsets, and the ring wraps per step, not per tap -- the issuing thread is
+        // the bottleneck of the short-MMA (N <= 128) layers (profiles/r02_issue_path.txt).
+        constexpr bool kAlignedB = (NSB % KS) == 0;
+        const bool first_tile = tile == static_cast<int>(blockIdx.x);
+        auto do_step = [&](auto f8_tag) {
+          constexpr bool F8 = decltype(f8_tag)::value;
+          ptx::mbar_wait(&a_full[sa], pa);
+          if (DRAIN) {   // two-level accumulation: a fresh TMEM accumulator per A stage
+            ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
+            accumulate = 0;
+          }
+          ptx::tc_fence_after();
+          // descriptors differ from the stage-0 descriptor only in the 14-bit address field
+          const uint64_t a_st = a_desc0 + static_cast<uint64_t>((sa * Cfg::A_STAGE_BYTES) >> 4);
+          const uint32_t sb0 = sb;                                   // first weight stage of this step
+          const uint64_t b_st0 = b_desc0 + static_cast<uint64_t>((sb0 * Cfg::B_STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int r = 0; r < KS; ++r) {
+            const uint32_t st = kAlignedB ? sb0 + r : sb;             // aligned: no wrap inside a step
+            if (!BRES || first_tile) {
+              ptx::mbar_wait(&b_full[st], pb);
+              ptx::tc_fence_after();
             }
-            ptx::tc_fence_after();
-            // descriptors differ from the stage-0 descriptor only in the 14-bit address field
-            const uint64_t a_st = a_desc0 + static_cast<uint64_t>((sa * Cfg::A_STAGE_BYTES) >> 4);
+            const uint64_t b_st = kAlignedB ? b_st0 + static_cast<uint64_t>((r * Cfg::B_STAGE_BYTES) >> 4)
+                                            : b_desc0 + static_cast<uint64_t>((sb * Cfg::B_STAGE_BYTES) >> 4);
 #pragma unroll
-            for (int r = 0; r < KS; ++r) {
-              if (!BRES || tile == static_cast<int>(blockIdx.x)) {
-                ptx::mbar_wait(&b_full[sb], pb);
-                ptx::tc_fence_after();
-              }
-              const uint64_t b_st = b_desc0 + static_cast<uint64_t>((sb * Cfg::B_STAGE_BYTES) >> 4);
+            for (int mt = 0; mt < MT; ++mt) {
+              if (mt < n_sub) {
+                const uint32_t d = tmem_base + (acc * MT + mt) * BN;
+                const uint64_t ad0 = a_st + static_cast<uint64_t>((mt * Cfg::A_SUB_BYTES + r * 1024) >> 4);
+                if constexpr (F8) {
+                  ptx::mma_f8_ss(d, ad0, b_st, IDESC8, accumulate);
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                if (mt < n_sub) {
-                  const uint32_t d = tmem_base + (acc * MT + mt) * BN;
-                  const uint64_t ad0 = a_st + static_cast<uint64_t>((mt * Cfg::A_SUB_BYTES + r * 1024) >> 4);
-                  if (f8) {
-                    ptx::mma_f8_ss(d, ad0, b_st, IDESC8, accumulate);
+                  for (int k = 1; k < 4; ++k) ptx::mma_f8_ss(d, ad0 + (k * 32 >> 4), b_st + (k * 32 >> 4), IDESC8, 1u);
+                } else {
+                  ptx::mma_f16_ss(d, ad0, b_st, IDESC, accumulate);
 #pragma unroll
-                    for (int k = 1; k < 4; ++k) ptx::mma_f8_ss(d, ad0 + (k * 32 >> 4), b_st + (k * 32 >> 4), IDESC8, 1u);
-                  } else {
-                    ptx::mma_f16_ss(d, ad0, b_st, IDESC, accumulate);
-#pragma unroll
-                    for (int k = 1; k < 4; ++k) ptx::mma_f16_ss_acc(d, ad0 + (k * 32 >> 4), b_st + (k * 32 >> 4), IDESC);
-                  }
+                  for (int k = 1; k < 4; ++k) ptx::mma_f16_ss_acc(d, ad0 + (k * 32 >> 4), b_st + (k * 32 >> 4), IDESC);
                 }
               }
-              accumulate = 1;
-              if (!BRES) ptx::mma_commit(&b_empty[sb]);
-              if (++sb == NSB) { sb = 0; pb ^= 1; }
             }
-            ptx::mma_commit(&a_empty[sa]);
-            if (++sa == NSA) { sa = 0; pa ^= 1; }
-            if (DRAIN) {
-              ptx::mma_commit(&t_full[acc]);
-              if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
-            }
+            accumulate = 1;
+            if (!BRES) ptx::mma_commit(&b_empty[st]);
+            if constexpr (!kAlignedB) { if (++sb == NSB) { sb = 0; pb ^= 1; } }
+          }
+          if constexpr (kAlignedB) { sb += KS; if (sb == NSB) { sb = 0; pb ^= 1; } }
+          ptx::mma_commit(&a_empty[sa]);
+          if (++sa == NSA) { sa = 0; pa ^= 1; }
+          if (DRAIN) {
+            ptx::mma_commit(&t_full[acc]);
+            if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+          }
+        };
+        for (int j = 0; j < P.n_pairs; ++j) {
+          if (P.comp && (j & 1)) {             // compensated precision: odd pairs are the 8-bit correction rows
+            for (int s = 0; s < KS; ++s) do_step(std::true_type{});
+          } else {
+            for (int s = 0; s < KS; ++s) do_step(std::false_type{});
           }
         }
         if (!DRAIN) {
