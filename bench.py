@@ -482,8 +482,12 @@ def run_ours(args):
     roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                 "traffic": traffic, "traffic_note": traffic_note,
                 "kernel": "grouped L1+L2 7x7 128->128 launch (Mconv2..5 of stages 2-6), 20 launches/step: "
-                          + {"fast": "conv_tcgen05_swap_kernel<7,3,5>", "comp": "conv_tcgen05_swap_kernel<7,3,5,DRAIN> (kind::f16 + kind::f8f6f4)",
-                             "parity": "conv_tcgen05_kernel<7,128,1,3,6,2,DRAIN>"}[args.precision],
+                          + {"fast": "conv_tcgen05_swap7_kernel<COMP=0,DRAIN=0>",
+                             "comp": "conv_tcgen05_swap7_kernel<COMP=1,DRAIN=1> (kind::f16 + kind::f8f6f4, two-level accumulation)",
+                             "parity": "conv_tcgen05_kernel<7,128,1,3,6,2,DRAIN> (split fp16: 3 kind::f16 MMAs per k-step)"}[args.precision],
+                "issued_tensor_work": {"mma_per_kstep": mma_per_kstep, "fp16_equivalent_tflops": ach * (2.0 if args.precision == "comp" else 3.0 if args.precision == "parity" else 1.0),
+                                       "note": "tensor-pipe time actually issued, in units of fp16 MMA work (an 8-bit-float K=32 MMA occupies the pipe as long as an fp16 K=16 MMA); "
+                                               "ncu tensor-pipe-active of the isolated launch: profiles/r02_ncu_%s_swap7x7_summary.txt" % args.precision},
                 "flops_per_launch": flops77, "ms_per_launch": ms77,
                 "note": "achieved = ALGORITHMIC flops (2*Cin*Cout*49 per pixel, true channels) / CUDA-event time; this precision "
                         "issues %d MMA(s) per k-step (8-bit-float correction MMAs run at twice the fp16 rate), so the tensor pipe is "

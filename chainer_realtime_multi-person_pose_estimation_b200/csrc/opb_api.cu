@@ -1187,18 +1187,15 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
       if (rc) return rc;
     }
     if (sep) {
-      // warps per block: 30 owned columns each; pick the count that wastes the fewest lanes over the plane width
-      int nw = 4, best = 1 << 30;
-      for (int k = 4; k <= PKS_MAX_WARPS; ++k) {
-        const int waste = ((W + 30 * k - 1) / (30 * k)) * 30 * k - W;
-        if (waste < best || (waste == best && k > nw)) { best = waste; nw = k; }
-      }
+      // one block per plane; its warps pull 30-column x 32-row cells from a shared counter (no lockstep between warps)
+      const int n_cells = ((W + 29) / 30) * ((H + PKS_SEG - 1) / PKS_SEG);
+      const int nw = std::max(1, std::min(PKS_MAX_WARPS, n_cells));
       static bool attr5_d[64] = {};
       if (!attr5_d[ctx->device & 63]) {
         OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr5_d[ctx->device & 63] = true;
       }
-      dim3 gs((W + 30 * nw - 1) / (30 * nw), 1, n * c_use);
+      dim3 gs(n * c_use, 1, 1);
       SepAxes axes{ws->sep_wy, ws->sep_wx};
       smooth_nms_sep_kernel<<<gs, nw * 32, smooth_nms_sep_smem_bytes(H, nw), ctx->stream>>>(
           heat, c_total, c_use, h_lo, w_lo, H, W, ctx->taps, static_cast<float>(p.heatmap_peak_thresh), axes, ws->keys,

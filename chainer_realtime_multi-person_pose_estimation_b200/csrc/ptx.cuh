@@ -54,11 +54,29 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// try_wait with a suspend-time hint: the thread stays suspended in hardware until the phase completes or `ns` elapse,
+// instead of returning to the polling loop every ~100 ns.  The waiting roles (eight epilogue warps, the TMA producer)
+// otherwise execute more than half of a conv kernel's instructions in their polling loops (ncu source page of the 7x7
+// kernel: 6.4 M polls x 8 instructions of 96 M) -- issue energy that a power-capped GPU would rather spend on MMAs.
+#ifndef OPB_WAIT_HINT_NS
+#define OPB_WAIT_HINT_NS 20000
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(OPB_WAIT_HINT_NS))
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must trap, never hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!(OPB_WAIT_HINT_NS ? mbar_try_wait_hint(bar, parity) : mbar_try_wait(bar, parity))) {
     if (clock64() - t0 > 4000000000LL) {  // ~2-3 s
       printf("opb: mbarrier wait timeout block %d thread %d bar %u parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);

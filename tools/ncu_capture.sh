@@ -16,7 +16,7 @@ METRICS='gpu__time_duration.sum|dram__bytes_read.sum |dram__bytes_write.sum |dra
 for K in "${KERNELS[@]}"; do
   NAME=$(echo "$K" | tr -c 'A-Za-z0-9_' '_' | sed 's/__*/_/g; s/_$//')
   OUT=gpurun_out/ncu_${TAG}_${PREC}_${NAME}
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$K" -s 2 -c 1 -f -o $OUT \
+  timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"$K" -s 2 -c 1 -f -o $OUT \
       python bench.py --precision $PREC --steps 1 --warmup 1 --no-cpu-baseline --no-parity-extra --no-stage-timing ${BENCH_EXTRA:-} > $OUT.log 2>&1
   if [ -f $OUT.ncu-rep ]; then
     ncu -i $OUT.ncu-rep --page raw --csv > $OUT.csv 2>/dev/null
