@@ -441,11 +441,16 @@ int launch_op(opb_ctx* ctx, const Chain* ch, const Op& op) {
   if (op.kind == OP_MLP2) {
     static bool attr_set[64] = {};
     if (!attr_set[ctx->device & 63]) {
-      OPB_CUDA(ctx, cudaFuncSetAttribute(conv_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlp2Smem));
+      OPB_CUDA(ctx, cudaFuncSetAttribute(conv_mlp2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlp2Smem));
+      OPB_CUDA(ctx, cudaFuncSetAttribute(conv_mlp2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlp2SmemComp));
       attr_set[ctx->device & 63] = true;
     }
-    conv_mlp2_kernel<<<op.grid, 128, kMlp2Smem, ctx->stream>>>(op.tmA[0], op.tmB[0], op.tmP16[0], op.tmA[1], op.tmB[1],
-                                                              op.tmP16[1], op.M);
+    if (op.M.corr_off)   // compensated precision
+      conv_mlp2_kernel<true><<<op.grid, 128, kMlp2SmemComp, ctx->stream>>>(op.tmA[0], op.tmB[0], op.tmP16[0], op.tmA[1], op.tmB[1],
+                                                                          op.tmP16[1], op.M);
+    else
+      conv_mlp2_kernel<false><<<op.grid, 128, kMlp2Smem, ctx->stream>>>(op.tmA[0], op.tmB[0], op.tmP16[0], op.tmA[1], op.tmB[1],
+                                                                       op.tmP16[1], op.M);
     ctx->launches++;
     OPB_CUDA(ctx, cudaGetLastError());
     return OPB_OK;
@@ -761,7 +766,7 @@ int build_chain_keypoint(opb_ctx* ctx, Chain* ch, int N, int H, int W);
 // in: 128 channels at in_coff[p] of `in`; out: channel slice out_coff[p] of `out` (+ optional planar fp32 copy).
 bool mlp2_enabled(const opb_ctx* ctx) {
   const char* e = getenv("OPB_NO_MLP2");
-  return ctx->precision == OPB_PRECISION_FAST && !(e && atoi(e));
+  return (ctx->precision == OPB_PRECISION_FAST || ctx->precision == OPB_PRECISION_COMP) && !(e && atoi(e));
 }
 
 int add_mlp2(opb_ctx* ctx, Chain* ch, const std::string& tag, int n_problems, const Act& in, const int in_coff[2],
@@ -780,29 +785,36 @@ int add_mlp2(opb_ctx* ctx, Chain* ch, const std::string& tag, int n_problems, co
   for (int p = 0; p < n_problems; ++p) {
     const PackedW& a = ctx->packed.at(w1[p]);
     const PackedW& b = ctx->packed.at(w2[p]);
+    const bool comp = ctx->precision == OPB_PRECISION_COMP;
+    const int kpt = comp ? 256 : 128;      // compensated precision: 128 fp16 values + 2 x 128 correction bytes per weight row
     if (a.ks != 1 || b.ks != 1 || a.cin_pad != 128 || a.cout_pad != 128 || b.cin_pad != 128 || b.cout_pad != kMlp2N2 ||
-        a.k_per_tap != 128 || b.k_per_tap != 128)
+        a.k_per_tap != kpt || b.k_per_tap != kpt)
       OPB_FAIL(ctx, OPB_ERR_ARG, "fused 1x1 pair needs 128 -> 128 -> <= 48 channels");
     int rc = make_act_map(ctx, &op.tmA[p], in, in_coff[p], 1);
     if (rc) return rc;
     if ((rc = make_w_map(ctx, &op.tmB[p], a, 128))) return rc;
     if ((rc = make_w_map(ctx, &op.tmP16[p], b, kMlp2N2))) return rc;
     M.bias1[p] = a.bias;
+    M.scale1[p] = a.acc_scale;
+    M.corr_off = comp ? in.C : 0;          // relative to the (in_coff-shifted) tensor map, like ConvParams::a_off
+    M.w_corr_off = comp ? 128 : 0;
     ConvProblem& pr = M.prob[p];
     pr.out = out.p;
     pr.out32 = out32[p];
     pr.bias = b.bias;
     pr.out_cstride = out.Ctot;
     pr.out_coff = out_coff[p];
-    pr.out_lo_off = 0;
+    pr.out_lo_off = comp ? out.C : 0;
     pr.cout_valid = cout_valid[p];
     pr.relu = 0;
     pr.pool = 0;
-    pr.acc_scale = 1.f;
+    pr.acc_scale = b.acc_scale;
   }
-  if (n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; op.tmP16[1] = op.tmP16[0]; M.prob[1] = M.prob[0]; M.bias1[1] = M.bias1[0]; }
+  if (n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; op.tmP16[1] = op.tmP16[0]; M.prob[1] = M.prob[0]; M.bias1[1] = M.bias1[0]; M.scale1[1] = M.scale1[0]; }
   const int m_tiles = M.N * M.tiles_y * M.tiles_x;
-  const int per_problem = std::min(m_tiles, 2 * ctx->num_sms / n_problems);    // two CTAs per SM in total
+  // two CTAs per SM in total (fast: 112 KB each); one in compensated precision (216 KB)
+  const int per_sm = (ctx->precision == OPB_PRECISION_COMP) ? 1 : 2;
+  const int per_problem = std::min(m_tiles, std::max(1, per_sm * ctx->num_sms / n_problems));
   op.grid = per_problem * n_problems;
   ch->ops.push_back(op);
   return OPB_OK;
@@ -1054,7 +1066,7 @@ int get_post(opb_ctx* ctx, int n, int H, int W, PostWs** out) {
   RC(dev_alloc(ctx, &ws->heat, static_cast<size_t>(n) * 19 * H * W, ws->allocs, false));
   RC(dev_alloc(ctx, &ws->keys, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
   RC(dev_alloc(ctx, &ws->tile_max, static_cast<size_t>(n) * 18 * ((H + PK_CELL - 1) / PK_CELL) * ((W + PK_CELL - 1) / PK_CELL), ws->allocs));
-  RC(dev_alloc(ctx, &ws->peak_counts, n, ws->allocs));
+  RC(dev_alloc(ctx, &ws->peak_counts, n + 1, ws->allocs));     // [n] counts + the peak kernel's work counter
   RC(dev_alloc(ctx, &ws->peaks, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
   RC(dev_alloc(ctx, &ws->idx_list, static_cast<size_t>(n) * p.max_peaks, ws->allocs));
   RC(dev_alloc(ctx, &ws->type_start, static_cast<size_t>(n) * 19, ws->allocs));
@@ -1157,7 +1169,7 @@ int ensure_sep_axes(opb_ctx* ctx, PostWs* ws, int h_lo, int w_lo, bool* ok) {
 int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total, int H, int W, int h_lo = 0,
                  int w_lo = 0, const float* heat_full = nullptr) {
   const opb_params& p = ctx->prm;
-  OPB_CUDA(ctx, cudaMemsetAsync(ws->peak_counts, 0, sizeof(int) * n, ctx->stream));
+  OPB_CUDA(ctx, cudaMemsetAsync(ws->peak_counts, 0, sizeof(int) * (n + 1), ctx->stream));
   OPB_CUDA(ctx, cudaMemsetAsync(ws->status, 0, sizeof(int) * n, ctx->stream));
   const int c_use = c_total - 1;   // background channel dropped, pose_detector.py:78
   const size_t smem = smooth_nms_smem_bytes(ctx->taps.radius);
@@ -1195,11 +1207,14 @@ int launch_peaks(opb_ctx* ctx, PostWs* ws, const float* heat, int n, int c_total
         OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr5_d[ctx->device & 63] = true;
       }
-      dim3 gs(n * c_use, 1, 1);
+      // persistent blocks (as many as fit: registers / 75 KB of shared memory allow 3 per SM); warps pull (plane, cell)
+      // items from a global counter, so there is no tail of half-empty waves
+      const long long n_items = static_cast<long long>(n) * c_use * n_cells;
+      dim3 gs(static_cast<unsigned>(std::min<long long>((n_items + nw - 1) / nw, 3LL * ctx->num_sms)), 1, 1);
       SepAxes axes{ws->sep_wy, ws->sep_wx};
       smooth_nms_sep_kernel<<<gs, nw * 32, smooth_nms_sep_smem_bytes(H, nw), ctx->stream>>>(
-          heat, c_total, c_use, h_lo, w_lo, H, W, ctx->taps, static_cast<float>(p.heatmap_peak_thresh), axes, ws->keys,
-          ws->peak_counts, p.max_peaks);
+          heat, c_total, c_use, n * c_use, h_lo, w_lo, H, W, ctx->taps, static_cast<float>(p.heatmap_peak_thresh), axes, ws->keys,
+          ws->peak_counts, p.max_peaks, ws->peak_counts + n);
     } else if (heat_full && ctx->peaks_v2 && ctx->taps.radius == PK_R_FAST) {   // + both smoothing passes on all threads
       if (!attr4) {
         OPB_CUDA(ctx, cudaFuncSetAttribute(smooth_nms_loskip_kernel_v2<PK_R_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));

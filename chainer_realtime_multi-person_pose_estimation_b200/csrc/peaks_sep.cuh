@@ -38,32 +38,27 @@ inline size_t smooth_nms_sep_smem_bytes(int H, int n_warps) {
          static_cast<size_t>(n_warps) * (sizeof(double) * 3 * P1W + sizeof(float) * (P1W * P1W + 1));
 }
 
-// Work decomposition: one block per plane; its warps pull CELLS (30 columns x PKS_SEG rows) from a shared counter and
-// process each cell on their own -- skip test, walk, exact re-evaluation of the cell's candidates -- with no block-wide
-// barrier after the row records are loaded.  (The first version walked a whole 300-column strip per block in lockstep:
+// Work decomposition: persistent blocks; every warp pulls (plane, CELL) items (cell = 30 columns x PKS_SEG rows) from a
+// global counter and processes each item on its own -- skip test, walk, exact re-evaluation of the cell's candidates --
+// with no block-wide barrier after the row records (the same for every plane) are loaded.  (The first version walked a whole 300-column strip per block in lockstep:
 // with 38 % of the cells of the benchmark's 8-person maps active, almost every block-wide segment had one active warp
 // and the others waited at the barrier -- 44 % fewer instructions bought 16 % of the time.)
 __global__ void __launch_bounds__(PKS_MAX_WARPS * 32)
-smooth_nms_sep_kernel(const float* __restrict__ heat_lo, int c_total, int c_use, int h_lo, int w_lo, int H, int W,
-                      GaussTaps taps, float thresh, SepAxes ax, PeakKey* __restrict__ out, int* __restrict__ counts,
-                      int cap) {
+smooth_nms_sep_kernel(const float* __restrict__ heat_lo, int c_total, int c_use, int n_planes, int h_lo, int w_lo, int H,
+                      int W, GaussTaps taps, float thresh, SepAxes ax, PeakKey* __restrict__ out, int* __restrict__ counts,
+                      int cap, int* __restrict__ next_item) {
   constexpr int R = PK_R_FAST, P1W = 2 * R + 3;
   const int n_warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int plane = blockIdx.x;
-  const int img = plane / c_use, c = plane - img * c_use;
-  const float* __restrict__ L = heat_lo + (static_cast<size_t>(img) * c_total + c) * h_lo * w_lo;
 
   extern __shared__ __align__(16) double smd[];
   float4* s_row = reinterpret_cast<float4*>(smd);                                   // [H][2]
   int* s_cand_all = reinterpret_cast<int*>(s_row + 2 * H);                          // [n_warps][30 * PKS_SEG]
   double* s_scr = reinterpret_cast<double*>(s_cand_all + 30 * n_warps * PKS_SEG + ((30 * n_warps * PKS_SEG) & 1));
   float* s_win = reinterpret_cast<float*>(s_scr + n_warps * 3 * P1W);               // [n_warps][P1W * P1W + 1]
-  __shared__ int s_next;
   __shared__ int s_cnt[PKS_MAX_WARPS];
 
   for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) s_row[i] = __ldg(reinterpret_cast<const float4*>(ax.wy) + i);
-  if (threadIdx.x == 0) s_next = 0;
   if (lane == 0) s_cnt[warp] = 0;
   __syncthreads();
 
@@ -74,12 +69,16 @@ smooth_nms_sep_kernel(const float* __restrict__ heat_lo, int c_total, int c_use,
   float* win = s_win + warp * (P1W * P1W + 1);
   const double sy = ac_step(h_lo, H), sx = ac_step(w_lo, W);
 
+  const long long n_items = static_cast<long long>(n_planes) * n_cells;
   for (;;) {
-    int cell = 0;
-    if (lane == 0) cell = atomicAdd(&s_next, 1);
-    cell = __shfl_sync(0xffffffffu, cell, 0);
-    if (cell >= n_cells) break;
-    const int seg = cell / n_cg, cg = cell - seg * n_cg;     // consecutive cells: neighbouring column groups of one segment
+    int item = 0;
+    if (lane == 0) item = atomicAdd(next_item, 1);            // persistent blocks: (plane, cell) items from a global counter
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) break;
+    const int plane = item / n_cells, cell = item - plane * n_cells;
+    const int img = plane / c_use, c = plane - img * c_use;
+    const float* __restrict__ L = heat_lo + (static_cast<size_t>(img) * c_total + c) * h_lo * w_lo;
+    const int seg = cell / n_cg, cg = cell - seg * n_cg;     // consecutive items: neighbouring column groups of one segment
     const int y0 = seg * PKS_SEG, y1 = min(y0 + PKS_SEG, H);
     const int x_cell = cg * 30;
     const int x = x_cell + lane - 1;                          // lanes 0 and 31 are halo columns

@@ -177,6 +177,24 @@ def test_whole_network_forward(emu_native, he_weights, mode, tol):
     assert err <= tol, err
 
 
+def test_fused_1x1_pair_compensated_bit_identical_to_two_launches(emu_native, monkeypatch):
+    """conv_mlp2_kernel<COMP> (Mconv6 + Mconv7 of both branches in one launch, the intermediate's fp16 values AND its 8-bit
+    correction bytes written straight into the swizzled operand tile) vs the two separate 1x1 launches (OPB_NO_MLP2=1) in
+    compensated precision: same MMAs in the same order on the same operand bits -> identical network outputs."""
+    syn = pkg("synthetic")
+    model = pkg("models.CocoPoseNet").CocoPoseNet()
+    model.load_npz(syn.he_weights(0))
+    img = syn.procedural_image(176, 128, seed=6)
+    out = []
+    for no_fuse in ("1", "0"):
+        monkeypatch.setenv("OPB_NO_MLP2", no_fuse)
+        eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params(), emu_native.PRECISION_COMP)
+        eng.load_model(model)
+        out.append(eng.forward(img[None]))
+        del eng
+    assert np.isfinite(out[0][0]).all() and np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
 def test_pose_detector_call_end_to_end(emu_native, monkeypatch):
     """PoseDetector.__call__ (pose_detector.py:484-517) entirely under emulation: upload -> device cv2-exact resize ->
     92-conv chain (CTA-pair kernel included) -> upsample -> peaks -> PAF integrals -> assignment -> grouping -> records

@@ -131,10 +131,12 @@ def test_fast_mode_uint8_entry_matches_float_entry(weights_model):
         assert e < 4e-3 * max(mag, 1.0)
 
 
-def test_fused_1x1_pair_is_bit_identical_to_two_launches(weights_model, monkeypatch):
+@pytest.mark.parametrize("precision", ["fast", "comp"])
+def test_fused_1x1_pair_is_bit_identical_to_two_launches(weights_model, monkeypatch, precision):
     """Mconv6 + Mconv7 fused into one kernel (csrc/conv_mlp2.cuh, the 128-channel intermediate stays in shared memory)
     vs the two separate 1x1 launches: same MMA shapes and accumulation order, so the maps must be bit-identical --
-    batch 2 (throughput tile shapes), batch 1 (small-batch shapes) and HandNet (single branch)."""
+    batch 2 (throughput tile shapes), batch 1 (small-batch shapes) and HandNet (single branch); fp16 and compensated
+    precision (there the fused kernel also writes the intermediate's 8-bit correction bytes into the operand tile)."""
     syn = pkg("synthetic")
     imgs = syn.random_images(2, 368, 496, seed=4)
     hn = pkg("models.HandNet")
@@ -144,8 +146,8 @@ def test_fused_1x1_pair_is_bit_identical_to_two_launches(weights_model, monkeypa
     out = []
     for no_fuse in ("0", "1"):
         monkeypatch.setenv("OPB_NO_MLP2", no_fuse)
-        det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision="fast")
-        hd = pkg("hand_detector").HandDetector(model=hand, device=0, precision="fast")
+        det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision=precision)
+        hd = pkg("hand_detector").HandDetector(model=hand, device=0, precision=precision)
         out.append((det.engine.forward(imgs), det.engine.forward(imgs[:1]), hd.engine.forward_keypoint_maps(crop)))
         del det, hd
     (a2, a1, ah), (b2, b1, bh) = out
