@@ -625,7 +625,10 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     const int fam = op.ks == 7 ? 1 : op.ks == 3 ? 2 : 4;
     // default (-1): only the fused Mconv1 launch (7x7, N=256): measured 2.07 -> 1.92 ms per 5 launches.
     // The N=128 families lose more to the 16-column pair granularity (82 -> 96 columns) than they gain.
-    const bool use_pair = (mask < 0) ? (op.ks == 7 && op.bn == 256) : ((mask & fam) != 0);
+    // OPB_PAIR64=1 (experiment): additionally the N=64 3x3 layers (conv1_2): a pair halves the MMA instructions per SM.
+    const char* e64 = getenv("OPB_PAIR64");
+    const bool pair64 = e64 && atoi(e64) && op.ks == 3 && op.bn == 64;
+    const bool use_pair = pair64 || ((mask < 0) ? (op.ks == 7 && op.bn == 256) : ((mask & fam) != 0));
     if (!split && use_pair && op.bn >= 64 && op.bn != 48) {
       op.pair = true;
       if (op.bn == 256 || op.ks == 1) op.mt = 1;
