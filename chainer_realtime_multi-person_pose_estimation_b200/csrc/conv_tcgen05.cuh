@@ -81,6 +81,10 @@ struct ConvParams {
   int a_off[kMaxPairs];  // activation channel offset of chunk pair j
   int b_off[kMaxPairs];  // weight k offset (inside one tap) of chunk pair j
   ConvProblem prob[2];
+  // swap7 kernel: host-computed tile schedule (longest-processing-time first): CTA c works through
+  // sched[c * sched_len + 0 .. sched_len) until it meets -1.  nullptr = tile = blockIdx.x + i * gridDim.x.
+  const int* sched;
+  int sched_len;
 };
 
 template <int KS, int BN, int MT, int NSA, int NSB, int ACC_STAGES>

@@ -93,12 +93,21 @@ conv_tcgen05_swap7_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __g
     return t;
   };
   const int n_steps = P.n_pairs * KS;      // (chunk pair, filter column) steps per tile
+  // Tile sequence of this CTA.  Tiles differ in cost (an 8-pixel edge tile is half a tile, the last tile row of a 46-row
+  // map computes 14 of 16 rows), so `blockIdx.x + i * gridDim.x` left the SMs 15 % apart (ncu: sm__cycles_active.avg /
+  // sm__cycles_elapsed.max = 0.85); the host hands every CTA a longest-processing-time-first list instead.
+  const int* __restrict__ sched = P.sched ? P.sched + static_cast<size_t>(blockIdx.x) * P.sched_len : nullptr;
+  auto next_tile = [&](int i) -> int {
+    if (sched) return (i < P.sched_len) ? __ldg(sched + i) : -1;
+    const int t = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+    return t < total_tiles ? t : -1;
+  };
 
   if (warp == 0) {
     // ================================================================ TMA producer
     if (ptx::elect_one()) {
       uint32_t step = 0;                   // global step counter: pixel stage = step & 1, ring parities from its bits
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int ti = 0, tile = next_tile(0); tile >= 0; tile = next_tile(++ti)) {
         const TileId t = decode(tile);
         const int y0 = t.ty * 16, x0 = t.tx * 16;
         const bool narrow = P.pad_edge8 && (t.tx == P.tiles_x - 1);
@@ -129,7 +138,7 @@ conv_tcgen05_swap7_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __g
       const uint64_t p_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemP), 1024);
       const uint64_t p_desc1 = p_desc0 + static_cast<uint64_t>(Cfg::P_STAGE_BYTES >> 4);
       const uint64_t w_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemW), 1024);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int ti = 0, tile = next_tile(0); tile >= 0; tile = next_tile(++ti)) {
         const TileId t = decode(tile);
         const bool narrow = P.pad_edge8 && (t.tx == P.tiles_x - 1);
         const int rows = min(16, (P.H - t.ty * 16 + 1) & ~1);
@@ -204,7 +213,7 @@ conv_tcgen05_swap7_kernel(const __grid_constant__ CUtensorMap tmP16_0, const __g
     // ================================================================ epilogue: thread = output channel
     const int q = warp & 3;
     uint32_t acc = 0, pacc = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int ti = 0, tile = next_tile(0); tile >= 0; tile = next_tile(++ti)) {
       const TileId t = decode(tile);
       const int p = t.p, nb = t.nb, n = t.n;
       const int y0 = t.ty * 16, x0 = t.tx * 16;

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <queue>
 #include <vector>
 
 #include "../../include/opb.h"
@@ -753,6 +754,46 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
   const int total_tiles = P.n_problems * P.n_blocks * P.N * P.tiles_y * P.tiles_x;
   op.grid = op.pair ? 2 * std::min(total_tiles, ctx->num_sms / 2) : std::min(total_tiles, ctx->num_sms);
   if (op.cluster == 2) op.grid = 2 * std::min(total_tiles / 2, ctx->num_sms / 2);
+  {  // swap7: longest-processing-time-first tile lists per CTA (OPB_SWAP7_LPT=0: round-robin).  Cost of a tile = the
+     // N of its MMAs: rows computed (16, or the even-rounded rest of the last tile row) x 16 or 8 pixels.
+    const char* e = getenv("OPB_SWAP7_LPT");
+    if (op.swap && op.ks == 7 && op.swap7 && op.cluster != 2 && !(e && atoi(e) == 0) && total_tiles > op.grid) {
+      const int m_tiles = P.N * P.tiles_y * P.tiles_x;
+      std::vector<std::pair<int, int>> tiles(total_tiles);        // (cost, tile)
+      for (int t = 0; t < total_tiles; ++t) {
+        const int rem = (t % m_tiles) % (P.tiles_y * P.tiles_x);
+        const int ty = rem / P.tiles_x, tx = rem % P.tiles_x;
+        const int rows = std::min(16, (P.H - ty * 16 + 1) & ~1);
+        const bool narrow = P.pad_edge8 && tx == P.tiles_x - 1;
+        tiles[t] = {rows * (narrow ? 8 : 16), t};
+      }
+      std::stable_sort(tiles.begin(), tiles.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+      std::vector<std::vector<int>> lists(op.grid);
+      std::vector<long long> load(op.grid, 0);
+      // least-loaded CTA first; ties -> lowest index (a heap keyed by (load, index))
+      std::priority_queue<std::pair<long long, int>, std::vector<std::pair<long long, int>>, std::greater<std::pair<long long, int>>> pq;
+      for (int c = 0; c < op.grid; ++c) pq.push({0, c});
+      for (const auto& tc : tiles) {
+        auto top = pq.top(); pq.pop();
+        lists[top.second].push_back(tc.second);
+        pq.push({top.first + tc.first, top.second});
+      }
+      size_t len = 0;
+      for (auto& l : lists) len = std::max(len, l.size());
+      std::vector<int> flat(static_cast<size_t>(op.grid) * len, -1);
+      for (int c = 0; c < op.grid; ++c) {
+        std::sort(lists[c].begin(), lists[c].end());             // natural order inside a CTA (problem, image, row, column)
+        std::copy(lists[c].begin(), lists[c].end(), flat.begin() + static_cast<size_t>(c) * len);
+      }
+      int* d_sched = nullptr;
+      int rc = dev_alloc(ctx, &d_sched, flat.size(), ch->allocs, false);
+      if (rc) return rc;
+      OPB_CUDA(ctx, cudaMemcpyAsync(d_sched, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      OPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // `flat` dies here
+      op.P.sched = d_sched;
+      op.P.sched_len = static_cast<int>(len);
+    }
+  }
   ch->ops.push_back(op);
   return OPB_OK;
 }
@@ -765,11 +806,18 @@ int alloc_act(opb_ctx* ctx, Chain* ch, Act* a, int N, int H, int W, int C) {
 
 int build_chain_keypoint(opb_ctx* ctx, Chain* ch, int N, int H, int W);
 
-// Fused Mconv6 (1x1 128->128 + ReLU) -> Mconv7 (1x1 128->C, C <= 48) of one stage, fast precision (csrc/conv_mlp2.cuh).
+// Fused Mconv6 (1x1 128->128 + ReLU) -> Mconv7 (1x1 128->C, C <= 48) of one stage (csrc/conv_mlp2.cuh): fast precision by
+// default, compensated precision on request.
 // in: 128 channels at in_coff[p] of `in`; out: channel slice out_coff[p] of `out` (+ optional planar fp32 copy).
 bool mlp2_enabled(const opb_ctx* ctx) {
   const char* e = getenv("OPB_NO_MLP2");
-  return (ctx->precision == OPB_PRECISION_FAST || ctx->precision == OPB_PRECISION_COMP) && !(e && atoi(e));
+  if (e && atoi(e)) return false;
+  if (ctx->precision == OPB_PRECISION_FAST) return true;
+  // compensated precision: built and bit-identical (conv_mlp2_kernel<true>), but its 216 KB of operand + correction tiles
+  // allow one CTA per SM, whose load / GEMM / epilogue phases then run back to back: measured 1.30 ms per pass vs
+  // 0.38 + 0.76 ms for the two separate launches (profiles/r02_mlp2_comp_ab.txt) -> opt-in only (OPB_MLP2_COMP=1).
+  const char* c = getenv("OPB_MLP2_COMP");
+  return ctx->precision == OPB_PRECISION_COMP && c && atoi(c);
 }
 
 int add_mlp2(opb_ctx* ctx, Chain* ch, const std::string& tag, int n_problems, const Act& in, const int in_coff[2],

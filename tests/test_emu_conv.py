@@ -186,6 +186,7 @@ def test_fused_1x1_pair_compensated_bit_identical_to_two_launches(emu_native, mo
     model.load_npz(syn.he_weights(0))
     img = syn.procedural_image(176, 128, seed=6)
     out = []
+    monkeypatch.setenv("OPB_MLP2_COMP", "1")   # opt-in variant
     for no_fuse in ("1", "0"):
         monkeypatch.setenv("OPB_NO_MLP2", no_fuse)
         eng = emu_native.Engine(0, pkg("pose_detector").make_opb_params(), emu_native.PRECISION_COMP)

@@ -144,6 +144,7 @@ def test_fused_1x1_pair_is_bit_identical_to_two_launches(weights_model, monkeypa
     hand.load_npz(syn.he_weights(0, layers=hn.LAYERS))
     crop = syn.procedural_image(368, 368, seed=5)[None]
     out = []
+    monkeypatch.setenv("OPB_MLP2_COMP", "1")   # the compensated variant is opt-in (slower than the two launches at batch 32)
     for no_fuse in ("0", "1"):
         monkeypatch.setenv("OPB_NO_MLP2", no_fuse)
         det = pkg("pose_detector").PoseDetector(model=weights_model, device=0, precision=precision)
