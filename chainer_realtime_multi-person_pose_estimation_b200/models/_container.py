@@ -1,6 +1,12 @@
 """Host-side weight container shared by the three nets (CocoPoseNet / FaceNet / HandNet): an object with one
 attribute per conv layer exposing `.W.data` / `.b.data` like a Chainer link, loadable from Chainer's save_npz
-layout.  There is no host forward: `__call__` runs on the B200 through the bound device engine."""
+layout.  There is no host forward: `__call__` runs on the B200 through the bound device engine.
+
+Model <-> engine binding.  A detector snapshots the weights into its own device context when it is constructed
+(`Engine.load_model`); detectors built from one model object therefore stay independent of each other.  The model's own
+`__call__` (the reference's `self.model(x)`) uses the engine of the detector constructed LAST with it.  Changing
+`link.W.data` afterwards does not reach an existing engine -- construct a new detector (or call
+`detector.engine.load_model(model)`); `load_npz` drops the binding so that a stale engine cannot be used by accident."""
 import numpy as np
 
 
