@@ -85,6 +85,10 @@ struct ConvParams {
   // sched[c * sched_len + 0 .. sched_len) until it meets -1.  nullptr = tile = blockIdx.x + i * gridDim.x.
   const int* sched;
   int sched_len;
+  // pair kernel, MT = 1: 1 = tiles_x counts 8-column UNITS and the two CTAs of a pair take units 2t and 2t+1 of the
+  // linear (image, tile row, unit) order -- they need not be neighbours in the image (each CTA loads its own A rows and
+  // stores its own outputs), so an odd number of units per row costs no padding block: 82 columns -> 88, not 96.
+  int pair_units;
 };
 
 template <int KS, int BN, int MT, int NSA, int NSB, int ACC_STAGES>

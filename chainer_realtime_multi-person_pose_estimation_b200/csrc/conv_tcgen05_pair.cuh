@@ -97,7 +97,29 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int m_tiles = P.N * P.tiles_y * P.tiles_x;             // pair tiles (16 x 16*MT pixels)
+  const bool units = (MT == 1) && P.pair_units != 0;           // see ConvParams::pair_units
+  const int m_tiles = units ? (P.N * P.tiles_y * P.tiles_x) >> 1 : P.N * P.tiles_y * P.tiles_x;   // pair tiles
+  struct Pos { int n, y0, x0, n_sub; };                        // x0 = first column of THIS CTA's 8-column block 0
+  auto locate = [&](int rem) {                                 // rem = pair-tile index inside one (problem, channel block)
+    Pos q;
+    if (units) {
+      const int u = 2 * rem + static_cast<int>(rank);
+      q.n = u / (P.tiles_y * P.tiles_x);
+      const int r2 = u - q.n * (P.tiles_y * P.tiles_x);
+      const int ty = r2 / P.tiles_x;
+      q.y0 = ty * 16;
+      q.x0 = (r2 - ty * P.tiles_x) * 8;
+      q.n_sub = 2;
+    } else {
+      q.n = rem / (P.tiles_y * P.tiles_x);
+      const int r2 = rem - q.n * (P.tiles_y * P.tiles_x);
+      const int ty = r2 / P.tiles_x, tx = r2 - ty * P.tiles_x;
+      q.y0 = ty * 16;
+      q.x0 = tx * (16 * MT) + 8 * static_cast<int>(rank);
+      q.n_sub = min(2 * MT, (P.W - tx * (16 * MT) + 7) >> 3);    // valid 8-column blocks in this pair tile
+    }
+    return q;
+  };
   const int tiles_per_problem = P.n_blocks * m_tiles;
   const int total_tiles = P.n_problems * tiles_per_problem;
   const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -111,12 +133,9 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
         int rem = tile - p * tiles_per_problem;
         const int nb = rem / m_tiles;
         rem -= nb * m_tiles;
-        const int n = rem / (P.tiles_y * P.tiles_x);
-        rem -= n * (P.tiles_y * P.tiles_x);
-        const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
-        const int y0 = ty * 16, x0 = tx * (16 * MT);
-        const int n_sub = min(2 * MT, (P.W - x0 + 7) >> 3);    // valid 8-column blocks in this pair tile
-        const int n_mma = (n_sub + 1) >> 1;                    // M=256 MMAs per k-step
+        const Pos q = locate(rem);
+        const int n = q.n, y0 = q.y0;
+        const int n_mma = (q.n_sub + 1) >> 1;                  // M=256 MMAs per k-step
         const CUtensorMap* tmA = p ? &tmA1 : &tmA0;
         const CUtensorMap* tmB = p ? &tmB1 : &tmB0;
         for (int j = 0; j < P.n_pairs; ++j) {
@@ -127,7 +146,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
             const uint32_t afull0 = ptx::mapa_u32(ptx::smem_u32(&a_full[sa]), 0);
             for (int mt = 0; mt < n_mma; ++mt)   // an out-of-image block loads zeros (TMA OOB fill)
               ptx::tma_load_4d_pair(smemA + sa * Cfg::A_STAGE_BYTES + mt * Cfg::A_SUB_BYTES, tmA, afull0, ac,
-                                    x0 + 8 * (2 * mt + static_cast<int>(rank)) + s - PAD, y0 - PAD, n);
+                                    q.x0 + 16 * mt + s - PAD, y0 - PAD, n);
             if (++sa == NSA) { sa = 0; pa ^= 1; }
             for (int r = 0; r < KS; ++r) {
               ptx::mbar_wait(&b_empty[sb], pb ^ 1);
@@ -147,12 +166,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
       const uint64_t a_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemA), 1024);
       const uint64_t b_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smemB), 1024);
       for (int tile = pair_id; tile < total_tiles; tile += n_pairs) {
-        int rem = tile % m_tiles;
-        rem %= (P.tiles_y * P.tiles_x);
-        const int tx = rem % P.tiles_x;
-        const int x0 = tx * (16 * MT);
-        const int n_sub = min(2 * MT, (P.W - x0 + 7) >> 3);
-        const int n_mma = (n_sub + 1) >> 1;
+        const int n_mma = (locate(tile % m_tiles).n_sub + 1) >> 1;
         if (!DRAIN) {
           ptx::mbar_wait(&t_empty[acc], pacc ^ 1);
           ptx::tc_fence_after();
@@ -227,12 +241,10 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
       int rem = tile - p * tiles_per_problem;
       const int nb = rem / m_tiles;
       rem -= nb * m_tiles;
-      const int n = rem / (P.tiles_y * P.tiles_x);
-      rem -= n * (P.tiles_y * P.tiles_x);
-      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
-      const int y = ty * 16 + hl;
-      const int x0 = tx * (16 * MT);
-      const int n_sub = min(2 * MT, (P.W - x0 + 7) >> 3);
+      const Pos pos = locate(rem);
+      const int n = pos.n;
+      const int y = pos.y0 + hl;
+      const int n_sub = pos.n_sub;
       const int n_mma = (n_sub + 1) >> 1;
       const ConvProblem& pr = P.prob[p];
       if (bias_key != p * 1024 + nb) {
@@ -264,7 +276,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
           if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
         }
         if (mine) {
-          const int x = x0 + 8 * static_cast<int>(rank) + wl;
+          const int x = pos.x0 + wl;
           const bool valid = (y < P.H) && (x < P.W);
 #pragma unroll
           for (int cc = 0; cc < 128; cc += 32) {
@@ -281,7 +293,7 @@ conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
       for (int mt = 0; mt < n_mma; ++mt) {
         const int jb = 2 * mt + static_cast<int>(rank);
         if (jb >= n_sub) continue;                       // this CTA's block of the last MMA is outside the image
-        const int x = x0 + 8 * jb + wl;
+        const int x = pos.x0 + 16 * mt + wl;
         const bool valid = (y < P.H) && (x < P.W);
 #pragma unroll 1
         for (int cc = 0; cc < BN; cc += CW, ++item) {

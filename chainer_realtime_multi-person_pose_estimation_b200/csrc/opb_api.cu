@@ -688,6 +688,14 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     P.tiles_x = a0.W / 16 + (rem ? 1 : 0);
   }
   P.tiles_y = (a0.H + 15) / 16;
+  if (op.pair && op.mt == 1) {   // pair kernel: 8-column units paired along the linear unit order (no padding block per row)
+    const char* e = getenv("OPB_PAIR_UNITS");
+    const int units_x = (a0.W + 7) / 8;
+    if (!(e && atoi(e) == 0) && ((static_cast<long long>(P.N) * P.tiles_y * units_x) % 2) == 0) {
+      P.tiles_x = units_x;
+      P.pair_units = 1;
+    }
+  }
   P.n_blocks = per_problem_cout_pad / op.bn;
   P.n_problems = s.n_problems;
   P.b_tap_stride = w0.k_per_tap;
@@ -751,7 +759,7 @@ int add_conv(opb_ctx* ctx, Chain* ch, const std::string& tag, const ConvSpec& s)
     pr.acc_scale = w.acc_scale;
   }
   if (s.n_problems == 1) { op.tmA[1] = op.tmA[0]; op.tmB[1] = op.tmB[0]; op.tmP16[1] = op.tmP16[0]; P.prob[1] = P.prob[0]; }
-  const int total_tiles = P.n_problems * P.n_blocks * P.N * P.tiles_y * P.tiles_x;
+  const int total_tiles = P.n_problems * P.n_blocks * P.N * P.tiles_y * P.tiles_x / (P.pair_units ? 2 : 1);
   op.grid = op.pair ? 2 * std::min(total_tiles, ctx->num_sms / 2) : std::min(total_tiles, ctx->num_sms);
   if (op.cluster == 2) op.grid = 2 * std::min(total_tiles / 2, ctx->num_sms / 2);
   {  // swap7: longest-processing-time-first tile lists per CTA (OPB_SWAP7_LPT=0: round-robin).  Cost of a tile = the
