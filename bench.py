@@ -79,7 +79,7 @@ class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.th = index, [], False, None
@@ -106,8 +106,18 @@ class ClockSampler(object):
         mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(s) >= 6 and s[2 + i] == "Active" for s in self.samples)]
+        def num(i):
+            out = []
+            for smp in self.samples:
+                try:
+                    out.append(float(smp[i]))
+                except (IndexError, ValueError):
+                    pass
+            return out
+        pw, pl = num(6), num(7)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=reasons, samples=len(sm))
+                    reasons=reasons, samples=len(sm),
+                    power_w=float(np.median(pw)) if pw else None, power_limit_w=max(pl) if pl else None)
 
 
 def cpu_reference_step(weights, img, paf_lo, heat_lo):
