@@ -117,7 +117,9 @@ class ClockSampler(object):
         pw, pl = num(6), num(7)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
                     reasons=reasons, samples=len(sm),
-                    power_w=float(np.median(pw)) if pw else None, power_limit_w=max(pl) if pl else None)
+                    power_w=float(np.median(pw)) if pw else None, power_limit_w=max(pl) if pl else None,
+                    power_note="nvidia-smi power.draw is a ~1 s running average: a timed region of a few hundred ms reads low "
+                               "while the throttle reason already reports the instantaneous cap")
 
 
 def cpu_reference_step(weights, img, paf_lo, heat_lo):

@@ -108,3 +108,28 @@ def test_conv_fused_maxpool(engine, case, mode):
     err = np.abs(y - ref).max()
     assert y.shape == ref.shape
     assert err <= _TOL[mode] * scale, "max abs err %.3e (scale %.3f)" % (err, scale)
+
+
+@pytest.mark.parametrize("mode", ["fast", "comp"])
+@pytest.mark.parametrize("knob,case", [
+    ("OPB_SWAP7", (32, 46, 82, 128, 128, 7, 1)),        # lean-issue 7x7 kernel + LPT tile lists vs conv_tcgen05_swap_kernel
+    ("OPB_SWAP7_LPT", (32, 46, 82, 128, 128, 7, 1)),    # LPT tile lists vs round-robin tiles
+    ("OPB_PAIR_UNITS", (32, 46, 82, 185, 256, 7, 1)),   # CTA pairs on consecutive 8-column units vs 16-column pair tiles
+], ids=["swap7", "lpt", "pair_units"])
+def test_scheduling_variants_bit_identical_at_benchmark_size(monkeypatch, knob, case, mode):
+    """BASELINE.json's full size (batch 32, 46x82 maps): the round-2 scheduling changes only reorder WHICH CTA computes
+    which tile (or which kernel issues the same MMAs); every output must be bit-identical to the variant they replace --
+    a size-independent property checked where the tile counts, LPT lists and ring wrap-arounds are the benchmark's."""
+    native = pkg("_native")
+    n, h, w, cin, cout, ks, relu = case
+    rs = np.random.RandomState(11)
+    x = rs.standard_normal((n, h, w, cin)).astype(np.float32)
+    W = (rs.standard_normal((cout, cin, ks, ks)) * np.sqrt(2.0 / (cin * ks * ks))).astype(np.float32)
+    b = (rs.standard_normal(cout) * 0.1).astype(np.float32)
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv(knob, flag)
+        eng = native.Engine(0, pkg("pose_detector").make_opb_params())
+        out.append(eng.test_conv(x, W, b, relu, getattr(native, _PREC[mode])))
+        del eng
+    assert np.isfinite(out[0]).all() and np.array_equal(out[0], out[1])
