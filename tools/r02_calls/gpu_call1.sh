@@ -1,7 +1,7 @@
 #!/bin/bash
 # r02 evidence call: full GPU suite, per-launch event profile, ncu launch list, ncu --set full per kernel, bench lines.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 echo "=== tests $(date +%T)"

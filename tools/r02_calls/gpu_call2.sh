@@ -1,7 +1,7 @@
 #!/bin/bash
 # r02 call 2: elect.sync issue path + lean 7x7 swap kernel: GPU parity, A/B, per-launch profile, ncu of the new kernel
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== tests $(date +%T)"
 timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/gputests2.log 2>&1; tail -n 4 gpurun_out/gputests2.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # r02 call 3: restructured plain-kernel issuer; A/B of CTA pairs on the 3x3 layers; per-launch profiles
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== tests $(date +%T)"
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/gputests3.log 2>&1; tail -n 4 gpurun_out/gputests3.log

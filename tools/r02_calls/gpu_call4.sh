@@ -1,7 +1,7 @@
 #!/bin/bash
 # r02 call 4: mbarrier suspend-time hint A/B, peak-kernel cell skipping, ncu of the plain-kernel layers
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 P=chainer_realtime_multi-person_pose_estimation_b200
 echo "=== tests $(date +%T)"

@@ -1,7 +1,7 @@
 #!/bin/bash
 # r02 call 5: cell-based peak kernel; ncu of the plain-kernel layers (demangled template names)
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== tests $(date +%T)"
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/gputests5.log 2>&1; tail -n 4 gpurun_out/gputests5.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # r02 call 6: comp mlp2 fusion, persistent peak kernel
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== tests $(date +%T)"
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/gputests6.log 2>&1; tail -n 4 gpurun_out/gputests6.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== new tests $(date +%T)"
 timeout 900 python -m pytest tests/test_gpu_conv.py -q -m gpu -k "scheduling_variants" > gpurun_out/t9.log 2>&1; tail -n 3 gpurun_out/t9.log
