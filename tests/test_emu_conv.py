@@ -222,6 +222,9 @@ def test_pose_detector_call_end_to_end(emu_native, monkeypatch):
     ref_poses, ref_scores = R.postprocess_fast(pafs, heat, map_w, img.shape[1], img.shape[0], map_h)
     assert len(scores) > 0, "random-weight maps at this size give some 'persons'; an empty result tests nothing"
     assert np.array_equal(scores, ref_scores) and np.array_equal(poses, ref_poses)
+    # the overlay of the frame just processed, with the poses taken from the device-resident records
+    # (opb_draw_last_result), against the reference's cv2 drawing loop on the returned poses
+    assert np.array_equal(det.draw_last_result(img), PD.draw_person_pose(img, poses))
 
 
 @pytest.mark.parametrize("modname,cls,n_kp", [("models.FaceNet", "FaceNet", 70)])   # HandNet: same chain builder, checked by hand

@@ -397,3 +397,17 @@ def test_precise_path_padded_200x300(weights_model, precision):
     """Precise path with padding: the scaled inputs 184x276 and 552x828 are padded to 280 / 832 columns
     (pad_image, :445) and the x8 maps cropped again (:462,:466)."""
     _check_precise(weights_model, precision, "precise_200x300_he0.npz", pkg("synthetic").procedural_image(200, 300, seed=4), 5)
+
+
+def test_overlay_from_device_records_matches_cv2(det_parity):
+    """draw_person_pose (pose_detector.py:520-553) for the frame just passed to __call__, rasterised on the device from the
+    device-resident person records (opb_draw_last_result: float64 rescale + rint as :513-514 / :539), against the host cv2
+    loop on the returned poses: dense random-weight "persons" (hundreds of overlapping limbs and joints), so the overwrite
+    order matters on most covered pixels."""
+    pd = pkg("pose_detector")
+    for seed, (h, w) in ((2, (480, 640)), (7, (368, 656))):
+        img = pkg("synthetic").procedural_image(h, w, seed=seed)
+        poses, scores = det_parity(img)
+        assert len(scores) > 0
+        assert np.array_equal(det_parity.draw_last_result(img), pd.draw_person_pose(img, poses))
+        assert np.array_equal(pd.draw_person_pose(img, poses, engine=det_parity.engine), pd.draw_person_pose(img, poses))
