@@ -203,19 +203,39 @@ conv_first_tc_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict_
   const int total = N * tiles_y * tiles_x;
   const int hl = tid >> 3, wl = tid & 7;
   uint32_t parity = 0;
+  // The 540 halo bytes of the NEXT tile are fetched into registers while this tile is built, multiplied and stored, so the
+  // global-load latency (long-scoreboard 4.0 per issue with 3-8 CTAs of 4 warps per SM) is off the per-tile critical path.
+  constexpr int kHaloPerThread = (18 * 10 * 3 + 127) / 128;
+  int pre[kHaloPerThread];
+  auto fetch_halo = [&](int t) {
+    const int n = t / (tiles_y * tiles_x);
+    const int rem = t - n * (tiles_y * tiles_x);
+    const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
+#pragma unroll
+    for (int k = 0; k < kHaloPerThread; ++k) {
+      const int i = tid + 128 * k;
+      int v = 256;                                    // 256 = outside the image (zero padding)
+      if (i < 18 * 10 * 3) {
+        const int c = i % 3, q = i / 3;
+        const int xx = x0 - 1 + q % 10, yy = y0 - 1 + q / 10;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x_u8[((static_cast<size_t>(n) * H + yy) * W + xx) * 3 + c];
+      }
+      pre[k] = v;
+    }
+  };
+  if (static_cast<int>(blockIdx.x) < total) fetch_halo(blockIdx.x);
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const int n = tile / (tiles_y * tiles_x);
     const int rem = tile - n * (tiles_y * tiles_x);
     const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
     // (1) halo tile, already normalised to fp16 through the look-up table (entry 256 = zero padding)
-    for (int i = tid; i < 18 * 10 * 3; i += 128) {
-      const int c = i % 3, q = i / 3;
-      const int xx = x0 - 1 + q % 10, yy = y0 - 1 + q / 10;
-      int v = 256;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x_u8[((static_cast<size_t>(n) * H + yy) * W + xx) * 3 + c];
-      s_val[i] = s_lut[v];
+#pragma unroll
+    for (int k = 0; k < kHaloPerThread; ++k) {
+      const int i = tid + 128 * k;
+      if (i < 18 * 10 * 3) s_val[i] = s_lut[pre[k]];
     }
     __syncthreads();
+    if (tile + static_cast<int>(gridDim.x) < total) fetch_halo(tile + gridDim.x);
     // (2) this thread's im2col row: k = (r*3+s)*3 + c = 9 consecutive halfs of each of 3 halo rows.  Each row segment
     //     is fetched as six aligned 32-bit words and funnel-shifted by its parity; the 27 halfs are then packed with
     //     compile-time byte permutes (row r starts at the odd position 9r).
@@ -342,18 +362,37 @@ conv_first_tcx_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict
   const int total = N * tiles_y * tiles_x;
   const int hl = tid >> 3, wl = tid & 7;
   uint32_t parity = 0;
+  // next tile's halo bytes prefetched into registers (see conv_first_tc_kernel)
+  constexpr int kHaloPerThread = (18 * 10 * 3 + 127) / 128;
+  int pre[kHaloPerThread];
+  auto fetch_halo = [&](int t) {
+    const int n = t / (tiles_y * tiles_x);
+    const int rem = t - n * (tiles_y * tiles_x);
+    const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
+#pragma unroll
+    for (int k = 0; k < kHaloPerThread; ++k) {
+      const int i = tid + 128 * k;
+      int v = 0;                                      // zero padding
+      if (i < 18 * 10 * 3) {
+        const int c = i % 3, q = i / 3;
+        const int xx = x0 - 1 + q % 10, yy = y0 - 1 + q / 10;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x_u8[((static_cast<size_t>(n) * H + yy) * W + xx) * 3 + c];
+      }
+      pre[k] = v;
+    }
+  };
+  if (static_cast<int>(blockIdx.x) < total) fetch_halo(blockIdx.x);
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const int n = tile / (tiles_y * tiles_x);
     const int rem = tile - n * (tiles_y * tiles_x);
     const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
-    for (int i = tid; i < 18 * 10 * 3; i += 128) {
-      const int c = i % 3, q = i / 3;
-      const int xx = x0 - 1 + q % 10, yy = y0 - 1 + q / 10;
-      int v = 0;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x_u8[((static_cast<size_t>(n) * H + yy) * W + xx) * 3 + c];
-      s_val[i] = __ushort2half_rn(static_cast<unsigned short>(v));
+#pragma unroll
+    for (int k = 0; k < kHaloPerThread; ++k) {
+      const int i = tid + 128 * k;
+      if (i < 18 * 10 * 3) s_val[i] = __ushort2half_rn(static_cast<unsigned short>(pre[k]));
     }
     __syncthreads();
+    if (tile + static_cast<int>(gridDim.x) < total) fetch_halo(tile + gridDim.x);
     {
       uint32_t seg[3][5];               // seg[r][j] = halfs (2j, 2j+1) of row r's 9-half segment (half 9 is junk)
 #pragma unroll
@@ -420,14 +459,15 @@ conv_first_tcx_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict
       tmem_load_group<32>(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, f);
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(f[i], acc_scale, s_bias[c0 + i]), 0.f);
-      uint32_t h[16], l[16];
+      uint32_t h[16];
+      float d[32];                     // v - fp16(v): the lo plane (parity) / the scaled correction byte (compensated)
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
         h[i] = *reinterpret_cast<const uint32_t*>(&t);
         const float2 back = __half22float2(t);
-        const __half2 tl = __floats2half2_rn(f[2 * i] - back.x, f[2 * i + 1] - back.y);
-        l[i] = *reinterpret_cast<const uint32_t*>(&tl);
+        d[2 * i] = f[2 * i] - back.x;
+        d[2 * i + 1] = f[2 * i + 1] - back.y;
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g)
@@ -435,6 +475,12 @@ conv_first_tcx_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict
             make_uint4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
       uint8_t* row2 = sOut + 128 * 128 + tid * 128;
       if (out_mode == 1) {            // parity: the lo plane
+        uint32_t l[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const __half2 tl = __floats2half2_rn(d[2 * i], d[2 * i + 1]);
+          l[i] = *reinterpret_cast<const uint32_t*>(&tl);
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           *reinterpret_cast<uint4*>(row2 + (((c0 >> 3) + g) ^ (tid & 7)) * 16) = make_uint4(l[4 * g], l[4 * g + 1], l[4 * g + 2], l[4 * g + 3]);
@@ -442,13 +488,7 @@ conv_first_tcx_kernel(const uint8_t* __restrict__ x_u8, const __half* __restrict
         uint32_t xl[8], x8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float lo4[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float v = f[4 * i + k];
-            lo4[k] = (v - __half2float(__float2half_rn(v))) * kCompLoScale;
-          }
-          xl[i] = f32x4_to_act8x4(lo4[0], lo4[1], lo4[2], lo4[3]);
+          xl[i] = f32x4_to_act8x4(d[4 * i] * kCompLoScale, d[4 * i + 1] * kCompLoScale, d[4 * i + 2] * kCompLoScale, d[4 * i + 3] * kCompLoScale);
           x8[i] = f32x4_to_act8x4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
         }
 #pragma unroll
