@@ -170,6 +170,30 @@ __device__ __forceinline__ void comp_store(const float (&f)[CW], __half* o, uint
       *reinterpret_cast<uint4*>(c) = make_uint4(xl[0], xl[1], xl[2], xl[3]);
       *reinterpret_cast<uint4*>(c + 64) = make_uint4(x8[0], x8[1], x8[2], x8[3]);
     }
+  } else if ((t0 & 1) == 0 && (reinterpret_cast<uintptr_t>(o) & 3) == 0 && ((t0 & 63) + CW <= 64)) {
+    // unaligned slice (the heat maps start at channel 166 of the concat tensor, the PAF slice ends after 38): channel
+    // PAIRS -- one 4-byte store for the two fp16 values and one 2-byte store per correction plane -- instead of three
+    // scalar stores per channel.  (Each scattered store instruction of a pixel-per-lane epilogue costs 32 sectors; the
+    // 1x1 head kernel is bound by them: profiles/r02_ncu_plain_comp_1_48_summary.txt.)
+    uint8_t* c = corr + comp_byte_off(t0);
+#pragma unroll
+    for (int i = 0; i < CW / 2; ++i) {
+      if (2 * i + 1 < nvalid) {
+        const float a = f[2 * i], b = f[2 * i + 1];
+        const __half2 t = __floats2half2_rn(a, b);
+        *reinterpret_cast<__half2*>(o + 2 * i) = t;
+        const float2 back = __half22float2(t);
+        *reinterpret_cast<unsigned short*>(c + 2 * i) = static_cast<unsigned short>(
+            __nv_cvt_float2_to_fp8x2(make_float2((a - back.x) * kCompLoScale, (b - back.y) * kCompLoScale), __NV_SATFINITE, OPB_NV_ACT_FMT));
+        *reinterpret_cast<unsigned short*>(c + 64 + 2 * i) =
+            static_cast<unsigned short>(__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, OPB_NV_ACT_FMT));
+      } else if (2 * i < nvalid) {
+        const __half hi = __float2half_rn(f[2 * i]);
+        o[2 * i] = hi;
+        c[2 * i] = f32_to_act8((f[2 * i] - __half2float(hi)) * kCompLoScale);
+        c[64 + 2 * i] = f32_to_act8(f[2 * i]);
+      }
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
@@ -304,6 +328,12 @@ __device__ __forceinline__ void epilogue_store_group(const ConvProblem& pr, cons
 #pragma unroll
         for (int g = 0; g < CW / 8; ++g)
           *reinterpret_cast<uint4*>(o + g * 8) = make_uint4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
+      } else if ((reinterpret_cast<uintptr_t>(o) & 3) == 0) {      // 4-byte aligned slice: channel pairs
+#pragma unroll
+        for (int i = 0; i < CW / 2; ++i) {
+          if (2 * i + 1 < nvalid) reinterpret_cast<uint32_t*>(o)[i] = h[i];
+          else if (2 * i < nvalid) reinterpret_cast<unsigned short*>(o)[2 * i] = static_cast<unsigned short>(h[i] & 0xffffu);
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < CW; ++i) {
